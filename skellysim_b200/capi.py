@@ -1,0 +1,246 @@
+"""ctypes binding of include/skelly_b200.h.
+
+Array convention = the reference's: an Eigen column-major ``3 x n`` matrix is a C-contiguous ``(n, 3)``
+float64 numpy array here (same bytes); stresslet strengths are ``(n, 9)``.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+KERNEL_STOKESLET = 0
+KERNEL_STRESSLET = 1
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = os.path.join(_HERE, "lib", "libskelly_b200.so")
+_dp = C.POINTER(C.c_double)
+_lib = None
+
+
+class SkbError(RuntimeError):
+    """Raised for every non-zero status of the C ABI (mirrors the std::runtime_error of the C++ wrapper)."""
+
+
+class EvalStats(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("n_pairs", C.c_int64),
+                ("launches", C.c_int32), ("targets_per_thread", C.c_int32), ("source_splits", C.c_int32),
+                ("grid_ctas", C.c_int32)]
+
+
+def library_path() -> str:
+    return _LIB
+
+
+def build_library(force: bool = False) -> str:
+    """Compile libskelly_b200.so for sm_100a with nvcc (cross-compiles without a GPU)."""
+    src = os.path.join(_HERE, "csrc")
+    if force:
+        subprocess.run(["make", "-C", src, "clean"], check=True, stdout=subprocess.DEVNULL)
+    r = subprocess.run(["make", "-C", src], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("building libskelly_b200.so failed:\n" + r.stdout[-4000:])
+    return _LIB
+
+
+def library() -> C.CDLL:
+    """Load the CUDA library.  Missing library == hard error: there is no other implementation to fall back to."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(_LIB):
+        raise SkbError(f"{_LIB} is missing: build it with skellysim_b200.build_library() "
+                       "(nvcc, sm_100a). There is no CPU or PyTorch fallback.")
+    L = C.CDLL(_LIB)
+    ctxp = C.c_void_p
+    sig = {
+        "skb_version": ([], C.c_char_p),
+        "skb_last_error_string": ([], C.c_char_p),
+        "skb_device_count": ([C.POINTER(C.c_int)], C.c_int),
+        "skb_stokeslet_direct": ([_dp, _dp, C.c_int, _dp, _dp, C.c_int], C.c_int),
+        "skb_stresslet_direct": ([_dp, _dp, C.c_int, _dp, _dp, C.c_int], C.c_int),
+        "skb_ctx_create": ([C.c_int, C.POINTER(ctxp)], C.c_int),
+        "skb_ctx_create_on": ([C.POINTER(C.c_int), C.c_int, C.POINTER(ctxp)], C.c_int),
+        "skb_ctx_destroy": ([ctxp], C.c_int),
+        "skb_ctx_n_gpus": ([ctxp, C.POINTER(C.c_int)], C.c_int),
+        "skb_set_targets": ([ctxp, _dp, C.c_int64], C.c_int),
+        "skb_set_sources": ([ctxp, C.c_int, _dp, C.c_int64], C.c_int),
+        "skb_eval": ([ctxp, C.c_int, _dp, _dp, C.c_int], C.c_int),
+        "skb_eval_fused": ([ctxp, _dp, _dp, _dp], C.c_int),
+        "skb_set_source_normals": ([ctxp, _dp, C.c_int64], C.c_int),
+        "skb_eval_double_layer": ([ctxp, _dp, C.c_double, _dp, C.c_int], C.c_int),
+        "skb_set_targets_device": ([ctxp, C.c_void_p, C.c_int64, C.c_void_p], C.c_int),
+        "skb_set_sources_device": ([ctxp, C.c_int, C.c_void_p, C.c_int64, C.c_void_p], C.c_int),
+        "skb_eval_device": ([ctxp, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
+        "skb_sync": ([ctxp], C.c_int),
+        "skb_last_eval_stats": ([ctxp, C.POINTER(EvalStats)], C.c_int),
+        "skb_launch_count": ([], C.c_int64),
+        "skb_ctx_set_tuning": ([ctxp, C.c_int, C.c_int], C.c_int),
+        "skb_measure_fp64_peak": ([ctxp, C.POINTER(C.c_double)], C.c_int),
+    }
+    for name, (args, res) in sig.items():
+        fn = getattr(L, name)
+        fn.argtypes = args
+        fn.restype = res
+    _lib = L
+    return L
+
+
+def _check(rc: int):
+    if rc != 0:
+        raise SkbError(f"skelly_b200 error {rc}: {library().skb_last_error_string().decode()}")
+
+
+def _arr(x, cols):
+    x = np.ascontiguousarray(x, dtype=np.float64)
+    if x.size == 0:
+        return x.reshape(0, cols)
+    if x.ndim != 2 or x.shape[1] != cols:
+        raise ValueError(f"expected an (n, {cols}) array, got {x.shape}")
+    return x
+
+
+def _p(x):
+    return x.ctypes.data_as(_dp)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    library().skb_device_count(C.byref(n))
+    return n.value
+
+
+def launch_count() -> int:
+    return int(library().skb_launch_count())
+
+
+def stokeslet_direct(r_src, f_src, r_trg):
+    """kernels::stokeslet_direct_gpu_impl semantics (kernels.hpp:17): 1/(8 pi) included, 1/eta not."""
+    r_src, f_src, r_trg = _arr(r_src, 3), _arr(f_src, 3), _arr(r_trg, 3)
+    if r_src.shape[0] != f_src.shape[0]:
+        raise ValueError("r_src / f_src size mismatch")
+    u = np.empty((r_trg.shape[0], 3))
+    _check(library().skb_stokeslet_direct(_p(r_src), _p(f_src), r_src.shape[0], _p(r_trg), _p(u), r_trg.shape[0]))
+    return u
+
+
+def stresslet_direct(r_src, f_src, r_trg):
+    """kernels::stresslet_direct_gpu_impl semantics (kernels.hpp:19)."""
+    r_src, f_src, r_trg = _arr(r_src, 3), _arr(f_src, 9), _arr(r_trg, 3)
+    if r_src.shape[0] != f_src.shape[0]:
+        raise ValueError("r_src / f_src size mismatch")
+    u = np.empty((r_trg.shape[0], 3))
+    _check(library().skb_stresslet_direct(_p(r_src), _p(f_src), r_src.shape[0], _p(r_trg), _p(u), r_trg.shape[0]))
+    return u
+
+
+class Context:
+    """Evaluator context: positions cached on the device(s), strengths shipped per evaluation."""
+
+    def __init__(self, n_gpus: int = 1, device_ids=None):
+        self._h = C.c_void_p()
+        L = library()
+        if device_ids is None:
+            _check(L.skb_ctx_create(int(n_gpus), C.byref(self._h)))
+        else:
+            ids = (C.c_int * len(device_ids))(*device_ids)
+            _check(L.skb_ctx_create_on(ids, len(device_ids), C.byref(self._h)))
+        self.n_trg = 0
+        self.n_src = {KERNEL_STOKESLET: 0, KERNEL_STRESSLET: 0}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            library().skb_ctx_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def n_gpus(self) -> int:
+        n = C.c_int(0)
+        _check(library().skb_ctx_n_gpus(self._h, C.byref(n)))
+        return n.value
+
+    # ---- host-pointer API ----
+    def set_targets(self, r_trg):
+        r_trg = _arr(r_trg, 3)
+        _check(library().skb_set_targets(self._h, _p(r_trg), r_trg.shape[0]))
+        self.n_trg = r_trg.shape[0]
+
+    def set_sources(self, kind, r_src):
+        r_src = _arr(r_src, 3)
+        _check(library().skb_set_sources(self._h, int(kind), _p(r_src), r_src.shape[0]))
+        self.n_src[int(kind)] = r_src.shape[0]
+
+    def set_source_normals(self, normals):
+        normals = _arr(normals, 3)
+        _check(library().skb_set_source_normals(self._h, _p(normals), normals.shape[0]))
+
+    def eval(self, kind, f_src, out=None, accumulate=False):
+        f_src = _arr(f_src, 3 if kind == KERNEL_STOKESLET else 9)
+        if f_src.shape[0] != self.n_src[int(kind)]:
+            raise ValueError("strength count does not match the sources set")
+        if out is None:
+            if accumulate:
+                raise ValueError("accumulate needs an output array")
+            out = np.empty((self.n_trg, 3))
+        assert out.flags.c_contiguous and out.dtype == np.float64 and out.shape == (self.n_trg, 3)
+        _check(library().skb_eval(self._h, int(kind), _p(f_src), _p(out), int(bool(accumulate))))
+        return out
+
+    def eval_fused(self, f_sl=None, f_dl=None):
+        out = np.empty((self.n_trg, 3))
+        a = _arr(f_sl, 3) if f_sl is not None else None
+        b = _arr(f_dl, 9) if f_dl is not None else None
+        _check(library().skb_eval_fused(self._h, _p(a) if a is not None else None,
+                                        _p(b) if b is not None else None, _p(out)))
+        return out
+
+    def eval_double_layer(self, density, eta, out=None, accumulate=False):
+        density = _arr(density, 3)
+        if out is None:
+            out = np.empty((self.n_trg, 3))
+        _check(library().skb_eval_double_layer(self._h, _p(density), float(eta), _p(out), int(bool(accumulate))))
+        return out
+
+    # ---- device-pointer API (addresses as ints, e.g. torch.Tensor.data_ptr()) ----
+    def set_targets_device(self, ptr: int, n_trg: int, stream: int = 0):
+        _check(library().skb_set_targets_device(self._h, C.c_void_p(ptr), int(n_trg), C.c_void_p(stream)))
+        self.n_trg = int(n_trg)
+
+    def set_sources_device(self, kind, ptr: int, n_src: int, stream: int = 0):
+        _check(library().skb_set_sources_device(self._h, int(kind), C.c_void_p(ptr), int(n_src), C.c_void_p(stream)))
+        self.n_src[int(kind)] = int(n_src)
+
+    def eval_device(self, kind, f_ptr: int, u_ptr: int, accumulate=False, stream: int = 0):
+        _check(library().skb_eval_device(self._h, int(kind), C.c_void_p(f_ptr), C.c_void_p(u_ptr),
+                                         int(bool(accumulate)), C.c_void_p(stream)))
+
+    def sync(self):
+        _check(library().skb_sync(self._h))
+
+    # ---- instrumentation ----
+    def stats(self) -> dict:
+        s = EvalStats()
+        _check(library().skb_last_eval_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in EvalStats._fields_}
+
+    def set_tuning(self, targets_per_thread=0, source_splits=0):
+        _check(library().skb_ctx_set_tuning(self._h, int(targets_per_thread), int(source_splits)))
+
+    def measure_fp64_peak(self) -> float:
+        v = C.c_double(0)
+        _check(library().skb_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value

@@ -1,0 +1,387 @@
+// pair_kernels.cuh -- sm_100a device code of the Stokeslet / stresslet all-pairs summation.
+//
+// What is computed (reference statements: SkellySim src/core/kernels.cu:57-77 Stokeslet, :24-55
+// stresslet, driver :79-123; same math in src/core/kernels.cpp:11-40):
+//   r = x_trg - x_src, rho = 1/|r| (0 when r == 0)
+//   Stokeslet:  u += rho (f + r (f.r) rho^2)                       then u *= 1/(8 pi)
+//   stresslet:  u += r (r.S.r) rho^5,  S = 3x3 from 9 doubles      then u *= -3/(8 pi)
+//
+// Design (B200-first, not a translation of the reference's 1-warp/1-target-per-thread kernel):
+//   * FP64 vector pipe is the roofline (arithmetic intensity ~3e4 flop/B), so everything is shaped to
+//     issue nothing but DFMA/DMUL/DADD on that pipe: 22 FP64 instr per Stokeslet pair, 27 per stresslet
+//     pair.  The reciprocal square root is MUFU.RSQ64H (XU pipe, 2^-22 seed) + ONE third-order
+//     Newton step (5 FP64 ops, rel. error ~1 ulp) instead of CUDA's ~12-instruction rsqrt().
+//     The r == 0 rule is a predicated select on the seed (integer pipe), never a branch.
+//   * register tiling: each consumer thread owns T targets (position + 3 accumulators in registers);
+//     a source is broadcast from shared memory to the whole warp with 128-bit LDS, so shared-memory
+//     traffic is 3 LDS.128 per source per warp against 22*T FP64 instructions.
+//   * sources stream HBM/L2 -> shared memory with TMA bulk copies (cp.async.bulk, SASS UBLKCP) issued by
+//     one elected lane of a dedicated producer warp into a 4-stage ring guarded by full/empty mbarriers;
+//     positions and strengths keep the caller's AoS layout, so a stage is two contiguous byte ranges and
+//     no repacking pass is needed.
+//   * the stresslet strength is pre-contracted once per matvec to its 6 symmetric combinations
+//     (S only enters through r.S.r), cutting shared-memory bytes per source from 96 to 72.
+//   * 2-D decomposition (target tile x source split) sized to the SM count; partial sums of the splits
+//     are combined in a fixed order by a tiny second kernel -> bitwise run-to-run reproducible, no atomics.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace skb {
+
+constexpr int kSrcTile = 128;       // sources per shared-memory stage
+constexpr int kStages = 4;          // TMA ring depth
+constexpr int kConsumerWarps = 4;   // compute warps per CTA
+constexpr int kConsumerThreads = kConsumerWarps * 32;
+constexpr int kCtaThreads = kConsumerThreads + 32; // + producer warp
+constexpr int kMaxSplits = 256;
+
+enum Kind : int { kStokeslet = 0, kStresslet = 1 };
+template <int KIND> struct KindTraits;
+template <> struct KindTraits<kStokeslet> { static constexpr int fdim = 3; };  // packed strengths / source
+template <> struct KindTraits<kStresslet> { static constexpr int fdim = 6; };  // sym6 combinations
+
+struct PairArgs {
+    const double *r_src;   // [n_src_pad*3]   padded to a multiple of kSrcTile (pads replicate the last source)
+    const double *f_src;   // [n_src_pad*fdim] padded with zeros
+    const double *r_trg;   // [n_trg*3]
+    double *partial;       // [n_splits][n_trg*3]
+    long long n_trg;
+    long long n_src;       // valid sources (the last tile is only walked up to here, rounded up to even)
+    int n_src_tiles;       // n_src_pad / kSrcTile
+    int tiles_per_split;   // source tiles handled by one blockIdx.y
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers: mbarrier + TMA bulk copy (Blackwell/Hopper async proxy)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion signalled on `bar` by transaction bytes (SASS: UBLKCP)
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
+// 1/sqrt(r2) in FP64 with the reference's r == 0 rule.
+// MUFU.RSQ64H seed (rel. err <= 2^-22.4), masked to 0 for r2 below the smallest normal (r2 == 0 and
+// subnormal r2, which the seed instruction flushes), then y = y0 + y0 e (1/2 + 3/8 e), e = 1 - r2 y0^2:
+// third-order, residual error ~(5/16) e^3 < 2^-64.  A zero seed stays exactly zero.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ double rinv_masked(double r2) {
+    double y0;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
+    if (__double2hiint(r2) < 0x00100000)
+        y0 = 0.0;
+    const double t = r2 * y0;
+    const double e = fma(-t, y0, 1.0);
+    const double p = fma(0.375, e, 0.5);
+    const double q = y0 * e;
+    return fma(q, p, y0);
+}
+
+// Stokeslet pair, 22 FP64 instructions.  (kernels.cu:62-76)
+__device__ __forceinline__ void stokeslet_pair(double tx, double ty, double tz, double sx, double sy, double sz,
+                                               double fx, double fy, double fz, double &ux, double &uy, double &uz) {
+    const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
+    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    const double y = rinv_masked(r2);
+    const double y2 = y * y;
+    const double fr = fma(fz, dz, fma(fy, dy, fx * dx));
+    const double ip = fr * y2;
+    ux = fma(y, fma(dx, ip, fx), ux);
+    uy = fma(y, fma(dy, ip, fy), uy);
+    uz = fma(y, fma(dz, ip, fz), uz);
+}
+
+// stresslet pair, 27 FP64 instructions; s = (sxx, syy, szz, sxy+syx, sxz+szx, syz+szy); the -3 lives in the
+// post-scale.  (kernels.cu:29-54)
+__device__ __forceinline__ void stresslet_pair(double tx, double ty, double tz, double sx, double sy, double sz,
+                                               double sxx, double syy, double szz, double pxy, double pxz,
+                                               double pyz, double &ux, double &uy, double &uz) {
+    const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
+    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
+    const double y = rinv_masked(r2);
+    const double y2 = y * y;
+    const double y5 = (y2 * y2) * y;
+    const double v1 = fma(pxz, dz, fma(pxy, dy, sxx * dx));
+    const double v2 = fma(pyz, dz, syy * dy);
+    const double v3 = szz * dz;
+    const double co = fma(v3, dz, fma(v2, dy, v1 * dx)) * y5;
+    ux = fma(dx, co, ux);
+    uy = fma(dy, co, uy);
+    uz = fma(dz, co, uz);
+}
+
+// shared-memory footprint of the main kernel
+template <int KIND, int T> struct SmemLayout {
+    static constexpr int fdim = KindTraits<KIND>::fdim;
+    static constexpr int pos_stage_bytes = kSrcTile * 3 * 8;
+    static constexpr int f_stage_bytes = kSrcTile * fdim * 8;
+    static constexpr int stage_bytes = pos_stage_bytes + f_stage_bytes;
+    static constexpr int trg_bytes = kConsumerThreads * T * 3 * 8;
+    static constexpr int bar_offset = kStages * stage_bytes + trg_bytes;
+    static constexpr int total_bytes = bar_offset + 2 * kStages * 8;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Main kernel: grid = (target tiles, source splits), block = 4 consumer warps + 1 TMA producer warp.
+// ---------------------------------------------------------------------------------------------
+template <int KIND, int T, int MINB>
+__global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairArgs a) {
+    using L = SmemLayout<KIND, T>;
+    constexpr int fdim = L::fdim;
+    constexpr int kTileT = kConsumerThreads * T;
+    extern __shared__ __align__(128) unsigned char smem[];
+    double *trg_s = reinterpret_cast<double *>(smem + kStages * L::stage_bytes);
+    uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::bar_offset);
+    uint64_t *empty_bar = full_bar + kStages;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const long long t_base = (long long)blockIdx.x * kTileT;
+    const int first_tile = blockIdx.y * a.tiles_per_split;
+    int n_tiles = a.n_src_tiles - first_tile;
+    n_tiles = n_tiles < a.tiles_per_split ? n_tiles : a.tiles_per_split;
+    if (n_tiles < 0)
+        n_tiles = 0;
+
+    if (tid == 0) {
+#pragma unroll
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full_bar[s], 1);
+            mbar_init(&empty_bar[s], kConsumerWarps);
+        }
+        mbar_fence_init();
+    }
+    // coalesced load of this CTA's contiguous target block (AoS xyz) into shared memory; the tail is
+    // filled with the last valid target so no lane ever computes on garbage
+    {
+        long long n_valid = a.n_trg - t_base;
+        n_valid = n_valid < kTileT ? n_valid : kTileT;
+        const double *g = a.r_trg + 3 * t_base;
+        const int n_dbl = (int)n_valid * 3;
+        for (int i = tid; i < kTileT * 3; i += kCtaThreads)
+            trg_s[i] = (i < n_dbl) ? __ldg(g + i) : __ldg(g + (n_dbl - 3) + (i % 3));
+    }
+    __syncthreads();
+
+    if (warp == kConsumerWarps) {
+        // ------------------------------ producer warp ------------------------------
+        if (lane == 0) {
+            const char *gp = reinterpret_cast<const char *>(a.r_src) + (size_t)first_tile * L::pos_stage_bytes;
+            const char *gf = reinterpret_cast<const char *>(a.f_src) + (size_t)first_tile * L::f_stage_bytes;
+            for (int k = 0; k < n_tiles; ++k) {
+                const int s = k % kStages;
+                if (k >= kStages)
+                    mbar_wait(&empty_bar[s], ((k / kStages) - 1) & 1);
+                unsigned char *dst = smem + s * L::stage_bytes;
+                mbar_arrive_expect_tx(&full_bar[s], L::stage_bytes);
+                tma_bulk_g2s(dst, gp + (size_t)k * L::pos_stage_bytes, L::pos_stage_bytes, &full_bar[s]);
+                tma_bulk_g2s(dst + L::pos_stage_bytes, gf + (size_t)k * L::f_stage_bytes, L::f_stage_bytes,
+                             &full_bar[s]);
+            }
+        }
+        return;
+    }
+
+    // ------------------------------ consumer warps ------------------------------
+    double tx[T], ty[T], tz[T], ux[T], uy[T], uz[T];
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const int i = t * kConsumerThreads + tid;
+        tx[t] = trg_s[3 * i + 0];
+        ty[t] = trg_s[3 * i + 1];
+        tz[t] = trg_s[3 * i + 2];
+        ux[t] = uy[t] = uz[t] = 0.0;
+    }
+
+    for (int k = 0; k < n_tiles; ++k) {
+        const int s = k % kStages;
+        mbar_wait(&full_bar[s], (k / kStages) & 1);
+        const double2 *ps = reinterpret_cast<const double2 *>(smem + s * L::stage_bytes);
+        const double2 *fs = reinterpret_cast<const double2 *>(smem + s * L::stage_bytes + L::pos_stage_bytes);
+        // pairs of sources to walk in this tile (the padded tail of the last tile is skipped)
+        long long left = a.n_src - (long long)(first_tile + k) * kSrcTile;
+        const int jmax = left >= kSrcTile ? kSrcTile / 2 : (int)((left + 1) >> 1);
+#pragma unroll 1
+        for (int j = 0; j < jmax; ++j) {
+            // two sources per iteration: 48 B of positions = 3 x LDS.128 (warp-wide broadcast)
+            const double2 p0 = ps[3 * j + 0], p1 = ps[3 * j + 1], p2 = ps[3 * j + 2];
+            if constexpr (KIND == kStokeslet) {
+                const double2 f0 = fs[3 * j + 0], f1 = fs[3 * j + 1], f2 = fs[3 * j + 2];
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                    stokeslet_pair(tx[t], ty[t], tz[t], p0.x, p0.y, p1.x, f0.x, f0.y, f1.x, ux[t], uy[t], uz[t]);
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                    stokeslet_pair(tx[t], ty[t], tz[t], p1.y, p2.x, p2.y, f1.y, f2.x, f2.y, ux[t], uy[t], uz[t]);
+            } else {
+                const double2 f0 = fs[6 * j + 0], f1 = fs[6 * j + 1], f2 = fs[6 * j + 2];
+                const double2 f3 = fs[6 * j + 3], f4 = fs[6 * j + 4], f5 = fs[6 * j + 5];
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                    stresslet_pair(tx[t], ty[t], tz[t], p0.x, p0.y, p1.x, f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, ux[t],
+                                   uy[t], uz[t]);
+#pragma unroll
+                for (int t = 0; t < T; ++t)
+                    stresslet_pair(tx[t], ty[t], tz[t], p1.y, p2.x, p2.y, f3.x, f3.y, f4.x, f4.y, f5.x, f5.y, ux[t],
+                                   uy[t], uz[t]);
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(&empty_bar[s]);
+    }
+
+    double *out = a.partial + (size_t)blockIdx.y * (size_t)a.n_trg * 3;
+#pragma unroll
+    for (int t = 0; t < T; ++t) {
+        const long long i = t_base + t * kConsumerThreads + tid;
+        if (i < a.n_trg) {
+            out[3 * i + 0] = ux[t];
+            out[3 * i + 1] = uy[t];
+            out[3 * i + 2] = uz[t];
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Fixed-order combination of the source-split partials, post-scale, optional accumulate.
+//   u[i] = (accumulate ? u[i] : 0) + scale * sum_s partial[s][i]
+// ---------------------------------------------------------------------------------------------
+__global__ void reduce_partials_kernel(const double *__restrict__ partial, double *__restrict__ u, long long n3,
+                                       int n_splits, double scale, int accumulate) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n3)
+        return;
+    double acc = 0.0;
+    for (int s = 0; s < n_splits; ++s)
+        acc += partial[(size_t)s * n3 + i];
+    acc *= scale;
+    u[i] = accumulate ? u[i] + acc : acc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Strength packing (once per matvec, O(n_src)).
+// ---------------------------------------------------------------------------------------------
+// Stokeslet: copy + optional per-source weight (trapezoid quadrature weight of
+// fiber_container_finite_difference.cpp:185-193) + zero pad.
+__global__ void pack_sl_kernel(const double *__restrict__ f, const double *__restrict__ w, double *__restrict__ out,
+                               long long n_src, long long n_pad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad * 3)
+        return;
+    const long long s = i / 3;
+    double v = 0.0;
+    if (s < n_src) {
+        v = f[i];
+        if (w)
+            v *= w[s];
+    }
+    out[i] = v;
+}
+// stresslet 9 -> sym6: (sxx, syy, szz, sxy+syx, sxz+szx, syz+szy)   (kernels.cu:41-49)
+__global__ void pack_dl9_kernel(const double *__restrict__ f9, double *__restrict__ out, long long n_src,
+                                long long n_pad) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_pad)
+        return;
+    double o[6] = {0, 0, 0, 0, 0, 0};
+    if (s < n_src) {
+        const double *f = f9 + 9 * s;
+        o[0] = f[0];
+        o[1] = f[4];
+        o[2] = f[8];
+        o[3] = f[1] + f[3];
+        o[4] = f[2] + f[6];
+        o[5] = f[5] + f[7];
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        out[6 * s + k] = o[k];
+}
+// stresslet strength formed on the device: S = 2 eta n (x) rho  (periphery.cpp:68-71,
+// body_container.cpp:296-302) contracted straight to sym6.  Products are formed exactly as the reference
+// does (2*eta*n_a*rho_b, left to right) before the symmetric sums, so the result equals pack_dl9 of the
+// host-formed f_dl bit for bit.
+__global__ void pack_dl_normal_density_kernel(const double *__restrict__ nrm, const double *__restrict__ rho,
+                                              double two_eta, double *__restrict__ out, long long n_src,
+                                              long long n_pad) {
+    const long long s = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_pad)
+        return;
+    double o[6] = {0, 0, 0, 0, 0, 0};
+    if (s < n_src) {
+        const double n0 = two_eta * nrm[3 * s + 0], n1 = two_eta * nrm[3 * s + 1], n2 = two_eta * nrm[3 * s + 2];
+        const double r0 = rho[3 * s + 0], r1 = rho[3 * s + 1], r2 = rho[3 * s + 2];
+        o[0] = n0 * r0;
+        o[1] = n1 * r1;
+        o[2] = n2 * r2;
+        // no FMA contraction here: the host forms the 9 products separately, then kernels.cu:47-49 adds them
+        o[3] = __dadd_rn(__dmul_rn(n0, r1), __dmul_rn(n1, r0));
+        o[4] = __dadd_rn(__dmul_rn(n0, r2), __dmul_rn(n2, r0));
+        o[5] = __dadd_rn(__dmul_rn(n1, r2), __dmul_rn(n2, r1));
+    }
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        out[6 * s + k] = o[k];
+}
+// positions: copy + pad by replicating the last source (zero strength there => exact zero contribution)
+__global__ void pad_positions_kernel(const double *__restrict__ r, double *__restrict__ out, long long n_src,
+                                     long long n_pad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_pad * 3)
+        return;
+    const long long s = i / 3;
+    out[i] = (s < n_src) ? r[i] : r[3 * (n_src - 1) + (i % 3)];
+}
+
+// ---------------------------------------------------------------------------------------------
+// Pure DFMA throughput probe (roofline denominator measured on the box).
+// ---------------------------------------------------------------------------------------------
+__global__ void dfma_probe_kernel(double *out, int iters, double a, double b) {
+    double x[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        x[k] = threadIdx.x * 1e-9 + k;
+    for (int i = 0; i < iters; ++i) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            x[k] = fma(x[k], a, b);
+    }
+    double s = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k)
+        s += x[k];
+    if (s == 12345.678)
+        out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+} // namespace skb

@@ -1,0 +1,822 @@
+// skb_runtime.cu -- host side of libskelly_b200.so: evaluator contexts, launch planning, the C ABI
+// declared in include/skelly_b200.h, and the reference-named C++ entry points
+// kernels::stokeslet_direct_gpu_impl / kernels::stresslet_direct_gpu_impl (SkellySim
+// include/kernels.hpp:17-20) so the library links in place of src/core/kernels.cu.
+//
+// No CPU fallback exists here: every path ends in a CUDA launch or an error code.
+#include "pair_kernels.cuh"
+#include "skb_internal.hpp"
+
+#include <algorithm>
+#include <atomic>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+namespace skb {
+
+// ------------------------------------------------------------------------------------------------
+// errors / bookkeeping
+// ------------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error = "";
+static std::atomic<long long> g_launches{0};
+
+int set_error(int code, const char *fmt, ...) {
+    char buf[1024];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+const char *last_error() { return g_last_error.c_str(); }
+void count_launch(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
+// ------------------------------------------------------------------------------------------------
+// launch planning
+// ------------------------------------------------------------------------------------------------
+template <int KIND, int T, int MINB> static cudaError_t launch_variant(const PairArgs &a, dim3 grid, cudaStream_t st) {
+    using L = SmemLayout<KIND, T>;
+    auto kern = pair_sum_kernel<KIND, T, MINB>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total_bytes);
+        if (e != cudaSuccess)
+            return e;
+        attr_set[dev] = true;
+    }
+    kern<<<grid, kCtaThreads, L::total_bytes, st>>>(a);
+    return cudaGetLastError();
+}
+
+template <int KIND, int T, int MINB> static int occupancy_variant() {
+    using L = SmemLayout<KIND, T>;
+    auto kern = pair_sum_kernel<KIND, T, MINB>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total_bytes);
+    int nb = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, kern, kCtaThreads, L::total_bytes) != cudaSuccess)
+        nb = 1;
+    return nb < 1 ? 1 : nb;
+}
+
+// min-blocks-per-SM hints (register caps): T=1:6  T=2:5  T=4:4  T=8:2
+#define SKB_DISPATCH_T(KIND, T, CALL)                                                                                 \
+    switch (T) {                                                                                                      \
+    case 1: CALL(KIND, 1, 6); break;                                                                                  \
+    case 2: CALL(KIND, 2, 5); break;                                                                                  \
+    case 4: CALL(KIND, 4, 4); break;                                                                                  \
+    default: CALL(KIND, 8, 2); break;                                                                                 \
+    }
+
+static int t_index(int T) { return T == 1 ? 0 : T == 2 ? 1 : T == 4 ? 2 : 3; }
+
+DeviceInfo query_device(int dev) {
+    DeviceInfo di;
+    di.dev = dev;
+    cudaDeviceProp p;
+    cudaSetDevice(dev);
+    cudaGetDeviceProperties(&p, dev);
+    di.num_sms = p.multiProcessorCount;
+    di.cc_major = p.major;
+    di.cc_minor = p.minor;
+    const int Ts[4] = {1, 2, 4, 8};
+    for (int k = 0; k < 2; ++k)
+        for (int ti = 0; ti < 4; ++ti) {
+            int occ = 1;
+#define OCC_CALL(KIND, T, MINB) occ = occupancy_variant<KIND, T, MINB>()
+            if (k == 0) {
+                SKB_DISPATCH_T(kStokeslet, Ts[ti], OCC_CALL)
+            } else {
+                SKB_DISPATCH_T(kStresslet, Ts[ti], OCC_CALL)
+            }
+#undef OCC_CALL
+            di.occupancy[k][ti] = occ;
+        }
+    return di;
+}
+
+// Pick targets-per-thread T and the number of source splits S.
+//   cost(T,S) ~ (CTAs on the busiest SM) x (source tiles per CTA) x T x penalty(T, resident chains)
+// The busiest SM runs ceil(n_ctas / num_sms) CTAs; a CTA's time is proportional to the pairs it owns
+// (T targets/thread x tiles) because the FP64 pipe is shared by the co-resident CTAs.
+LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_src_tiles, int force_T, int force_S) {
+    LaunchPlan best;
+    double best_cost = 1e300;
+    const int Ts[4] = {1, 2, 4, 8};
+    for (int ti = 0; ti < 4; ++ti) {
+        const int T = Ts[ti];
+        if (force_T > 0 && T != force_T)
+            continue;
+        const int occ = di.occupancy[kind][ti];
+        const long long tile_t = (long long)kConsumerThreads * T;
+        const long long n_tiles_t = (n_trg + tile_t - 1) / tile_t;
+        // efficiency of the inner loop vs T (LDS + loop overhead amortised over T pairs); calibrated on B200
+        const double t_pen = (T == 1) ? 1.30 : (T == 2) ? 1.10 : (T == 4) ? 1.0 : 1.0;
+        const int s_max = std::min(n_src_tiles, kMaxSplits);
+        for (int S = 1; S <= s_max; ++S) {
+            if (force_S > 0 && S != std::min(force_S, s_max))
+                continue;
+            const int per = (n_src_tiles + S - 1) / S;
+            const int S_eff = (n_src_tiles + per - 1) / per;
+            if (S_eff != S && force_S <= 0)
+                continue; // duplicate of a smaller S
+            const long long n_ctas = n_tiles_t * S_eff;
+            const long long per_sm = (n_ctas + di.num_sms - 1) / di.num_sms;
+            // CTAs beyond the resident limit run in later waves; same total either way
+            const double resident = (double)std::min<long long>(per_sm, occ);
+            // latency hiding: want >= ~12 independent pair chains per scheduler (1 warp/CTA/SMSP, T chains each)
+            const double chains = resident * T;
+            const double lat_pen = chains >= 12.0 ? 1.0 : (12.0 / chains) * 0.5 + 0.5;
+            // fixed per-CTA cost (barrier init, target staging, partial write) in units of source tiles
+            const double cta_overhead = 0.5;
+            double cost = (double)per_sm * ((double)per + cta_overhead) * T * t_pen * lat_pen;
+            // reduction cost of S partial slabs, in the same units (tiny, breaks ties toward small S)
+            cost += 1e-3 * S_eff;
+            if (cost < best_cost) {
+                best_cost = cost;
+                best.T = T;
+                best.n_splits = S_eff;
+                best.tiles_per_split = per;
+                best.grid_x = (unsigned)n_tiles_t;
+            }
+        }
+    }
+    return best;
+}
+
+int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const double *d_f_packed, long long n_src,
+                    long long n_src_pad, const double *d_r_trg, long long n_trg, double *d_partial,
+                    const LaunchPlan &plan, cudaStream_t st) {
+    PairArgs a;
+    a.r_src = d_r_src;
+    a.f_src = d_f_packed;
+    a.r_trg = d_r_trg;
+    a.partial = d_partial;
+    a.n_trg = n_trg;
+    a.n_src = n_src;
+    a.n_src_tiles = (int)(n_src_pad / kSrcTile);
+    a.tiles_per_split = plan.tiles_per_split;
+    dim3 grid(plan.grid_x, plan.n_splits, 1);
+    cudaError_t e = cudaSuccess;
+#define LAUNCH_CALL(KIND, T, MINB) e = launch_variant<KIND, T, MINB>(a, grid, st)
+    if (kind == kStokeslet) {
+        SKB_DISPATCH_T(kStokeslet, plan.T, LAUNCH_CALL)
+    } else {
+        SKB_DISPATCH_T(kStresslet, plan.T, LAUNCH_CALL)
+    }
+#undef LAUNCH_CALL
+    if (e != cudaSuccess)
+        return set_error(SKB_ERR_CUDA, "pair_sum_kernel launch failed: %s", cudaGetErrorString(e));
+    count_launch(1);
+    return SKB_OK;
+}
+
+int launch_reduce(const double *d_partial, double *d_u, long long n_trg, int n_splits, double scale, int accumulate,
+                  cudaStream_t st) {
+    const long long n3 = 3 * n_trg;
+    const int bs = 256;
+    reduce_partials_kernel<<<(unsigned)((n3 + bs - 1) / bs), bs, 0, st>>>(d_partial, d_u, n3, n_splits, scale,
+                                                                          accumulate);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return set_error(SKB_ERR_CUDA, "reduce_partials_kernel launch failed: %s", cudaGetErrorString(e));
+    count_launch(1);
+    return SKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// device buffers
+// ------------------------------------------------------------------------------------------------
+int DevBuf::ensure(size_t bytes) {
+    if (bytes <= cap)
+        return SKB_OK;
+    if (ptr)
+        cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+    size_t want = bytes + bytes / 8 + 256;
+    cudaError_t e = cudaMalloc(&ptr, want);
+    if (e != cudaSuccess) {
+        ptr = nullptr;
+        return set_error(SKB_ERR_ALLOC, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+    }
+    cap = want;
+    return SKB_OK;
+}
+void DevBuf::release() {
+    if (ptr)
+        cudaFree(ptr);
+    ptr = nullptr;
+    cap = 0;
+}
+
+} // namespace skb
+
+using namespace skb;
+
+#define CUDA_TRY(expr)                                                                                                \
+    do {                                                                                                              \
+        cudaError_t _e = (expr);                                                                                      \
+        if (_e != cudaSuccess)                                                                                        \
+            return set_error(SKB_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                      \
+                             cudaGetErrorString(_e));                                                                 \
+    } while (0)
+#define SKB_TRY(expr)                                                                                                 \
+    do {                                                                                                              \
+        int _rc = (expr);                                                                                             \
+        if (_rc != SKB_OK)                                                                                            \
+            return _rc;                                                                                               \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------
+// context
+// ------------------------------------------------------------------------------------------------
+struct SourceSet {
+    long long n = -1; // -1 = never set
+    long long n_pad = 0;
+    bool has_normals = false;
+    DevBuf r;       // padded positions
+    DevBuf normals; // optional (double layer formed on device)
+    DevBuf f_raw;   // strengths as shipped by the caller (3 or 9 per source; all-gather landing zone)
+    DevBuf f_packed;
+};
+
+struct DeviceState {
+    DeviceInfo info;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    long long trg_begin = 0, n_trg = 0; // this device's block of the global target list
+    DevBuf r_trg, u, partial, scratch;
+    SourceSet src[2];
+};
+
+struct skb_ctx {
+    std::vector<DeviceState> devs;
+    long long n_trg = -1;
+    int force_T = 0, force_S = 0;
+    skb_eval_stats stats{};
+    bool kernel_events_pending = false; // device-pointer path: kernel_ms is read back lazily
+    void *nccl = nullptr; // NcclGroup*, multi-device contexts only
+};
+
+static int check_kind(int kind) {
+    if (kind != SKB_STOKESLET && kind != SKB_STRESSLET)
+        return set_error(SKB_ERR_INVALID, "unknown kernel kind %d", kind);
+    return SKB_OK;
+}
+
+static int ctx_create_impl(const int *ids, int n, skb_ctx **out) {
+    if (!out)
+        return set_error(SKB_ERR_INVALID, "skb_ctx_create: out == NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    cudaError_t e = cudaGetDeviceCount(&n_dev);
+    if (e != cudaSuccess || n_dev == 0)
+        return set_error(SKB_ERR_NO_DEVICE, "no CUDA device available (%s); this library has no CPU fallback",
+                         e == cudaSuccess ? "device count is 0" : cudaGetErrorString(e));
+    if (n < 1 || n > n_dev)
+        return set_error(SKB_ERR_INVALID, "skb_ctx_create: n_gpus=%d but %d device(s) visible", n, n_dev);
+    std::unique_ptr<skb_ctx> ctx(new skb_ctx);
+    ctx->devs.resize(n);
+    for (int g = 0; g < n; ++g) {
+        DeviceState &d = ctx->devs[g];
+        const int dev = ids ? ids[g] : g;
+        if (dev < 0 || dev >= n_dev)
+            return set_error(SKB_ERR_INVALID, "device id %d out of range", dev);
+        CUDA_TRY(cudaSetDevice(dev));
+        d.info = query_device(dev);
+        if (d.info.cc_major < 10)
+            return set_error(SKB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
+                             d.info.cc_major, d.info.cc_minor);
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&d.ev_t0));
+        CUDA_TRY(cudaEventCreate(&d.ev_t1));
+        CUDA_TRY(cudaEventCreate(&d.ev_k0));
+        CUDA_TRY(cudaEventCreate(&d.ev_k1));
+    }
+    if (n > 1)
+        SKB_TRY(nccl_group_create(ctx->devs.size(), [&](int g) { return ctx->devs[g].info.dev; }, &ctx->nccl));
+    *out = ctx.release();
+    return SKB_OK;
+}
+
+extern "C" {
+
+const char *skb_version(void) { return "skelly_b200 0.1.0 (sm_100a)"; }
+const char *skb_last_error_string(void) { return last_error(); }
+int64_t skb_launch_count(void) { return launch_count(); }
+
+int skb_device_count(int *n) {
+    if (!n)
+        return set_error(SKB_ERR_INVALID, "skb_device_count: NULL");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) {
+        *n = 0;
+        return set_error(SKB_ERR_NO_DEVICE, "cudaGetDeviceCount: %s", cudaGetErrorString(e));
+    }
+    *n = c;
+    return SKB_OK;
+}
+
+int skb_ctx_create(int n_gpus, skb_ctx **out) { return ctx_create_impl(nullptr, n_gpus, out); }
+int skb_ctx_create_on(const int *device_ids, int n_gpus, skb_ctx **out) {
+    if (!device_ids)
+        return set_error(SKB_ERR_INVALID, "skb_ctx_create_on: device_ids == NULL");
+    return ctx_create_impl(device_ids, n_gpus, out);
+}
+
+int skb_ctx_destroy(skb_ctx *ctx) {
+    if (!ctx)
+        return SKB_OK;
+    for (auto &d : ctx->devs) {
+        cudaSetDevice(d.info.dev);
+        if (d.stream)
+            cudaStreamSynchronize(d.stream);
+        d.r_trg.release();
+        d.u.release();
+        d.partial.release();
+        d.scratch.release();
+        for (auto &s : d.src) {
+            s.r.release();
+            s.normals.release();
+            s.f_raw.release();
+            s.f_packed.release();
+        }
+        if (d.ev_t0) cudaEventDestroy(d.ev_t0);
+        if (d.ev_t1) cudaEventDestroy(d.ev_t1);
+        if (d.ev_k0) cudaEventDestroy(d.ev_k0);
+        if (d.ev_k1) cudaEventDestroy(d.ev_k1);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    if (ctx->nccl)
+        nccl_group_destroy(ctx->nccl);
+    delete ctx;
+    return SKB_OK;
+}
+
+int skb_ctx_n_gpus(const skb_ctx *ctx, int *n) {
+    if (!ctx || !n)
+        return set_error(SKB_ERR_INVALID, "skb_ctx_n_gpus: NULL");
+    *n = (int)ctx->devs.size();
+    return SKB_OK;
+}
+
+int skb_ctx_set_tuning(skb_ctx *ctx, int T, int S) {
+    if (!ctx)
+        return set_error(SKB_ERR_INVALID, "skb_ctx_set_tuning: NULL ctx");
+    if (!(T == 0 || T == 1 || T == 2 || T == 4 || T == 8) || S < 0)
+        return set_error(SKB_ERR_INVALID, "tuning: targets_per_thread must be 0/1/2/4/8, source_splits >= 0");
+    ctx->force_T = T;
+    ctx->force_S = S;
+    return SKB_OK;
+}
+
+int skb_last_eval_stats(const skb_ctx *ctx, skb_eval_stats *out) {
+    if (!ctx || !out)
+        return set_error(SKB_ERR_INVALID, "skb_last_eval_stats: NULL");
+    *out = ctx->stats;
+    if (ctx->kernel_events_pending) {
+        // asynchronous evaluation: the events are valid once the caller's stream has passed them
+        const DeviceState &d = ctx->devs[0];
+        float ms = 0;
+        cudaSetDevice(d.info.dev);
+        if (cudaEventElapsedTime(&ms, d.ev_k0, d.ev_k1) == cudaSuccess)
+            out->kernel_ms = ms;
+        else
+            (void)cudaGetLastError(); // not ready yet: leave 0
+    }
+    return SKB_OK;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// positions
+// ------------------------------------------------------------------------------------------------
+static void partition_targets(skb_ctx *ctx, long long n_trg) {
+    const long long P = (long long)ctx->devs.size();
+    const long long chunk = (n_trg + P - 1) / P;
+    for (long long g = 0; g < P; ++g) {
+        DeviceState &d = ctx->devs[g];
+        d.trg_begin = std::min(n_trg, g * chunk);
+        d.n_trg = std::min(n_trg, (g + 1) * chunk) - d.trg_begin;
+    }
+    ctx->n_trg = n_trg;
+}
+
+static int set_targets_impl(skb_ctx *ctx, const double *r_trg, long long n_trg, bool on_device, cudaStream_t user) {
+    if (!ctx)
+        return set_error(SKB_ERR_INVALID, "set_targets: NULL ctx");
+    if (n_trg < 0 || (n_trg > 0 && !r_trg))
+        return set_error(SKB_ERR_INVALID, "set_targets: bad arguments (n_trg=%lld)", n_trg);
+    if (on_device && ctx->devs.size() != 1)
+        return set_error(SKB_ERR_INVALID, "device-pointer entry points need a single-GPU context");
+    partition_targets(ctx, n_trg);
+    for (auto &d : ctx->devs) {
+        if (d.n_trg == 0)
+            continue;
+        CUDA_TRY(cudaSetDevice(d.info.dev));
+        SKB_TRY(d.r_trg.ensure((size_t)d.n_trg * 24));
+        SKB_TRY(d.u.ensure((size_t)d.n_trg * 24));
+        cudaStream_t st = user ? user : d.stream;
+        CUDA_TRY(cudaMemcpyAsync(d.r_trg.ptr, r_trg + 3 * d.trg_begin, (size_t)d.n_trg * 24,
+                                 on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
+    }
+    if (!on_device)
+        for (auto &d : ctx->devs) {
+            CUDA_TRY(cudaSetDevice(d.info.dev));
+            CUDA_TRY(cudaStreamSynchronize(d.stream));
+        }
+    return SKB_OK;
+}
+
+static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long long n_src, bool on_device,
+                            cudaStream_t user) {
+    if (!ctx)
+        return set_error(SKB_ERR_INVALID, "set_sources: NULL ctx");
+    SKB_TRY(check_kind(kind));
+    if (n_src < 0 || (n_src > 0 && !r_src))
+        return set_error(SKB_ERR_INVALID, "set_sources: bad arguments (n_src=%lld)", n_src);
+    if (n_src > (1LL << 31) - 1 - kSrcTile)
+        return set_error(SKB_ERR_INVALID, "set_sources: n_src=%lld exceeds the supported range", n_src);
+    if (on_device && ctx->devs.size() != 1)
+        return set_error(SKB_ERR_INVALID, "device-pointer entry points need a single-GPU context");
+    const long long n_pad = ((n_src + kSrcTile - 1) / kSrcTile) * kSrcTile;
+    const int fdim_raw = kind == SKB_STOKESLET ? 3 : 9;
+    const int fdim_packed = kind == SKB_STOKESLET ? 3 : 6;
+    const long long P = (long long)ctx->devs.size();
+    const long long chunk = (n_src + P - 1) / P; // all-gather slot per device
+    for (auto &d : ctx->devs) {
+        SourceSet &s = d.src[kind];
+        s.n = n_src;
+        s.n_pad = n_pad;
+        s.has_normals = false;
+        if (n_src == 0)
+            continue;
+        CUDA_TRY(cudaSetDevice(d.info.dev));
+        cudaStream_t st = user ? user : d.stream;
+        SKB_TRY(s.r.ensure((size_t)n_pad * 24));
+        SKB_TRY(s.f_raw.ensure((size_t)chunk * P * fdim_raw * 8));
+        SKB_TRY(s.f_packed.ensure((size_t)n_pad * fdim_packed * 8));
+        const double *d_in = r_src;
+        if (!on_device) {
+            SKB_TRY(d.scratch.ensure((size_t)n_src * 24));
+            CUDA_TRY(cudaMemcpyAsync(d.scratch.ptr, r_src, (size_t)n_src * 24, cudaMemcpyHostToDevice, st));
+            d_in = (const double *)d.scratch.ptr;
+        }
+        const int bs = 256;
+        pad_positions_kernel<<<(unsigned)((n_pad * 3 + bs - 1) / bs), bs, 0, st>>>(d_in, (double *)s.r.ptr, n_src,
+                                                                                   n_pad);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+    }
+    if (!on_device)
+        for (auto &d : ctx->devs) {
+            CUDA_TRY(cudaSetDevice(d.info.dev));
+            CUDA_TRY(cudaStreamSynchronize(d.stream));
+        }
+    return SKB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// evaluation
+// ------------------------------------------------------------------------------------------------
+enum StrengthMode { kRaw = 0, kNormalDensity = 1 };
+
+// device-side part for one device: pack -> pair kernel -> reduce into d_u_out.  f_raw already resident.
+static int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, const double *d_f_raw,
+                          double two_eta, double *d_u_out, int accumulate, cudaStream_t st, bool record_events,
+                          int *launches, LaunchPlan *plan_out) {
+    SourceSet &s = d.src[kind];
+    const int bs = 256;
+    if (d.n_trg == 0)
+        return SKB_OK;
+    if (s.n == 0) {
+        if (!accumulate)
+            CUDA_TRY(cudaMemsetAsync(d_u_out, 0, (size_t)d.n_trg * 24, st));
+        return SKB_OK;
+    }
+    // 1. strengths -> packed, padded layout
+    if (kind == SKB_STOKESLET) {
+        pack_sl_kernel<<<(unsigned)((s.n_pad * 3 + bs - 1) / bs), bs, 0, st>>>(d_f_raw, nullptr,
+                                                                                (double *)s.f_packed.ptr, s.n, s.n_pad);
+    } else if (mode == kRaw) {
+        pack_dl9_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(d_f_raw, (double *)s.f_packed.ptr, s.n,
+                                                                             s.n_pad);
+    } else {
+        pack_dl_normal_density_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(
+            (const double *)s.normals.ptr, d_f_raw, two_eta, (double *)s.f_packed.ptr, s.n, s.n_pad);
+    }
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    // 2. pair sums
+    LaunchPlan plan = plan_launch(d.info, kind, d.n_trg, (int)(s.n_pad / kSrcTile), ctx->force_T, ctx->force_S);
+    SKB_TRY(d.partial.ensure((size_t)plan.n_splits * (size_t)d.n_trg * 24));
+    if (record_events)
+        CUDA_TRY(cudaEventRecord(d.ev_k0, st));
+    SKB_TRY(launch_pair_sum(d.info, kind, (const double *)s.r.ptr, (const double *)s.f_packed.ptr, s.n, s.n_pad,
+                            (const double *)d.r_trg.ptr, d.n_trg, (double *)d.partial.ptr, plan, st));
+    if (record_events)
+        CUDA_TRY(cudaEventRecord(d.ev_k1, st));
+    // 3. combine splits, scale: 1/(8 pi) (kernels.cu:59) or -3/(8 pi) (kernels.cu:26,51)
+    const double scale = (kind == SKB_STOKESLET ? 1.0 : -3.0) / (8.0 * M_PI);
+    SKB_TRY(launch_reduce((const double *)d.partial.ptr, d_u_out, d.n_trg, plan.n_splits, scale, accumulate, st));
+    if (launches)
+        *launches += 3;
+    if (plan_out)
+        *plan_out = plan;
+    return SKB_OK;
+}
+
+// host-pointer evaluation over all devices of the context
+static int eval_host(skb_ctx *ctx, int kind, StrengthMode mode, const double *f_src, double eta, double *u_trg,
+                     int accumulate) {
+    if (!ctx)
+        return set_error(SKB_ERR_INVALID, "eval: NULL ctx");
+    SKB_TRY(check_kind(kind));
+    if (ctx->n_trg < 0)
+        return set_error(SKB_ERR_STATE, "eval: skb_set_targets has not been called");
+    const long long n_src = ctx->devs[0].src[kind].n;
+    if (n_src < 0)
+        return set_error(SKB_ERR_STATE, "eval: skb_set_sources(kind=%d) has not been called", kind);
+    if ((n_src > 0 && !f_src) || (ctx->n_trg > 0 && !u_trg))
+        return set_error(SKB_ERR_INVALID, "eval: NULL strength or output pointer");
+    if (mode == kNormalDensity && n_src > 0 && !ctx->devs[0].src[kind].has_normals)
+        return set_error(SKB_ERR_STATE, "eval_double_layer: skb_set_source_normals has not been called");
+    const int fdim = (kind == SKB_STOKESLET || mode == kNormalDensity) ? 3 : 9;
+    const long long P = (long long)ctx->devs.size();
+    const long long chunk = (n_src + P - 1) / P;
+    int launches = 0;
+    LaunchPlan plan{};
+
+    // stage 1: strengths to the devices.  P == 1: one H2D.  P > 1: each device receives its 1/P slice over
+    // PCIe, then ONE NCCL all-gather per evaluation distributes the slices over NVLink.
+    for (long long g = 0; g < P; ++g) {
+        DeviceState &d = ctx->devs[g];
+        CUDA_TRY(cudaSetDevice(d.info.dev));
+        CUDA_TRY(cudaEventRecord(d.ev_t0, d.stream));
+        if (n_src == 0)
+            continue;
+        SourceSet &s = d.src[kind];
+        const long long b = std::min(n_src, g * chunk), e = std::min(n_src, (g + 1) * chunk);
+        if (e > b)
+            CUDA_TRY(cudaMemcpyAsync((double *)s.f_raw.ptr + (size_t)g * chunk * fdim, f_src + (size_t)b * fdim,
+                                     (size_t)(e - b) * fdim * 8, cudaMemcpyHostToDevice, d.stream));
+    }
+    if (P > 1 && n_src > 0) {
+        std::vector<void *> bufs(P);
+        std::vector<cudaStream_t> sts(P);
+        for (long long g = 0; g < P; ++g) {
+            bufs[g] = ctx->devs[g].src[kind].f_raw.ptr;
+            sts[g] = ctx->devs[g].stream;
+        }
+        SKB_TRY(nccl_group_allgather_inplace(ctx->nccl, bufs.data(), (size_t)chunk * fdim, sts.data()));
+    }
+    // stage 2: every device evaluates its target block against all sources
+    for (long long g = 0; g < P; ++g) {
+        DeviceState &d = ctx->devs[g];
+        if (d.n_trg == 0)
+            continue;
+        CUDA_TRY(cudaSetDevice(d.info.dev));
+        if (accumulate)
+            CUDA_TRY(cudaMemcpyAsync(d.u.ptr, u_trg + 3 * d.trg_begin, (size_t)d.n_trg * 24, cudaMemcpyHostToDevice,
+                                     d.stream));
+        SKB_TRY(eval_on_device(ctx, d, kind, mode, (const double *)d.src[kind].f_raw.ptr, 2.0 * eta,
+                               (double *)d.u.ptr, accumulate, d.stream, true, &launches, g == 0 ? &plan : nullptr));
+        CUDA_TRY(cudaMemcpyAsync(u_trg + 3 * d.trg_begin, d.u.ptr, (size_t)d.n_trg * 24, cudaMemcpyDeviceToHost,
+                                 d.stream));
+        CUDA_TRY(cudaEventRecord(d.ev_t1, d.stream));
+    }
+    // stage 3: wait, collect timings
+    double k_ms = 0, t_ms = 0;
+    for (long long g = 0; g < P; ++g) {
+        DeviceState &d = ctx->devs[g];
+        CUDA_TRY(cudaSetDevice(d.info.dev));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        if (d.n_trg == 0)
+            continue;
+        float ms = 0;
+        if (n_src > 0 && cudaEventElapsedTime(&ms, d.ev_k0, d.ev_k1) == cudaSuccess)
+            k_ms = std::max(k_ms, (double)ms);
+        if (cudaEventElapsedTime(&ms, d.ev_t0, d.ev_t1) == cudaSuccess)
+            t_ms = std::max(t_ms, (double)ms);
+    }
+    ctx->kernel_events_pending = false;
+    ctx->stats.kernel_ms = k_ms;
+    ctx->stats.total_ms = t_ms;
+    ctx->stats.n_pairs = n_src * ctx->n_trg;
+    ctx->stats.launches = launches;
+    ctx->stats.targets_per_thread = plan.T;
+    ctx->stats.source_splits = plan.n_splits;
+    ctx->stats.grid_ctas = (int)(plan.grid_x * plan.n_splits);
+    return SKB_OK;
+}
+
+// process-wide context behind the stateless reference-shaped entry points
+static std::mutex g_default_mu;
+static skb_ctx *g_default_ctx = nullptr;
+static int default_ctx(skb_ctx **out) {
+    if (!g_default_ctx) {
+        int rc = skb_ctx_create(1, &g_default_ctx);
+        if (rc != SKB_OK)
+            return rc;
+    }
+    *out = g_default_ctx;
+    return SKB_OK;
+}
+
+static int direct_impl(int kind, const double *r_src, const double *f_src, int n_src, const double *r_trg,
+                       double *u_trg, int n_trg) {
+    if (n_src < 0 || n_trg < 0)
+        return set_error(SKB_ERR_INVALID, "negative count");
+    std::lock_guard<std::mutex> lock(g_default_mu);
+    skb_ctx *ctx = nullptr;
+    SKB_TRY(default_ctx(&ctx));
+    SKB_TRY(skb_set_sources(ctx, kind, r_src, n_src));
+    SKB_TRY(skb_set_targets(ctx, r_trg, n_trg));
+    return skb_eval(ctx, kind, f_src, u_trg, 0);
+}
+
+extern "C" {
+
+int skb_set_targets(skb_ctx *ctx, const double *r_trg, int64_t n_trg) {
+    return set_targets_impl(ctx, r_trg, n_trg, false, nullptr);
+}
+int skb_set_targets_device(skb_ctx *ctx, const double *d_r_trg, int64_t n_trg, void *stream) {
+    return set_targets_impl(ctx, d_r_trg, n_trg, true, (cudaStream_t)stream);
+}
+int skb_set_sources(skb_ctx *ctx, int kind, const double *r_src, int64_t n_src) {
+    return set_sources_impl(ctx, kind, r_src, n_src, false, nullptr);
+}
+int skb_set_sources_device(skb_ctx *ctx, int kind, const double *d_r_src, int64_t n_src, void *stream) {
+    return set_sources_impl(ctx, kind, d_r_src, n_src, true, (cudaStream_t)stream);
+}
+
+int skb_set_source_normals(skb_ctx *ctx, const double *normals, int64_t n_src) {
+    if (!ctx)
+        return set_error(SKB_ERR_INVALID, "set_source_normals: NULL ctx");
+    const long long n = ctx->devs[0].src[SKB_STRESSLET].n;
+    if (n < 0)
+        return set_error(SKB_ERR_STATE, "set_source_normals: call skb_set_sources(SKB_STRESSLET, ...) first");
+    if (n_src != n || (n > 0 && !normals))
+        return set_error(SKB_ERR_INVALID, "set_source_normals: n_src=%lld does not match the %lld stresslet sources",
+                         (long long)n_src, n);
+    for (auto &d : ctx->devs) {
+        SourceSet &s = d.src[SKB_STRESSLET];
+        s.has_normals = true;
+        if (n == 0)
+            continue;
+        CUDA_TRY(cudaSetDevice(d.info.dev));
+        SKB_TRY(s.normals.ensure((size_t)n * 24));
+        CUDA_TRY(cudaMemcpyAsync(s.normals.ptr, normals, (size_t)n * 24, cudaMemcpyHostToDevice, d.stream));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+    }
+    return SKB_OK;
+}
+
+int skb_eval(skb_ctx *ctx, int kind, const double *f_src, double *u_trg, int accumulate) {
+    return eval_host(ctx, kind, kRaw, f_src, 0.0, u_trg, accumulate);
+}
+
+int skb_eval_double_layer(skb_ctx *ctx, const double *density, double eta, double *u_trg, int accumulate) {
+    return eval_host(ctx, SKB_STRESSLET, kNormalDensity, density, eta, u_trg, accumulate);
+}
+
+int skb_eval_fused(skb_ctx *ctx, const double *f_sl, const double *f_dl, double *u_trg) {
+    if (!ctx)
+        return set_error(SKB_ERR_INVALID, "eval_fused: NULL ctx");
+    int acc = 0;
+    skb_eval_stats total{};
+    if (f_sl) {
+        SKB_TRY(eval_host(ctx, SKB_STOKESLET, kRaw, f_sl, 0.0, u_trg, acc));
+        acc = 1;
+        total = ctx->stats;
+    }
+    if (f_dl) {
+        SKB_TRY(eval_host(ctx, SKB_STRESSLET, kRaw, f_dl, 0.0, u_trg, acc));
+        acc = 1;
+        total.kernel_ms += ctx->stats.kernel_ms;
+        total.total_ms += ctx->stats.total_ms;
+        total.n_pairs += ctx->stats.n_pairs;
+        total.launches += ctx->stats.launches;
+        total.targets_per_thread = ctx->stats.targets_per_thread;
+        total.source_splits = ctx->stats.source_splits;
+        total.grid_ctas = ctx->stats.grid_ctas;
+        ctx->stats = total;
+    }
+    if (!acc && ctx->n_trg > 0) {
+        if (!u_trg)
+            return set_error(SKB_ERR_INVALID, "eval_fused: NULL output");
+        std::memset(u_trg, 0, (size_t)ctx->n_trg * 24);
+    }
+    return SKB_OK;
+}
+
+int skb_eval_device(skb_ctx *ctx, int kind, const double *d_f_src, double *d_u_trg, int accumulate, void *stream) {
+    if (!ctx)
+        return set_error(SKB_ERR_INVALID, "eval_device: NULL ctx");
+    SKB_TRY(check_kind(kind));
+    if (ctx->devs.size() != 1)
+        return set_error(SKB_ERR_INVALID, "device-pointer entry points need a single-GPU context");
+    DeviceState &d = ctx->devs[0];
+    if (ctx->n_trg < 0 || d.src[kind].n < 0)
+        return set_error(SKB_ERR_STATE, "eval_device: targets / sources not set");
+    if ((d.src[kind].n > 0 && !d_f_src) || (ctx->n_trg > 0 && !d_u_trg))
+        return set_error(SKB_ERR_INVALID, "eval_device: NULL pointer");
+    CUDA_TRY(cudaSetDevice(d.info.dev));
+    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+    int launches = 0;
+    LaunchPlan plan{};
+    SKB_TRY(eval_on_device(ctx, d, kind, kRaw, d_f_src, 0.0, d_u_trg, accumulate, st, true, &launches, &plan));
+    ctx->kernel_events_pending = d.src[kind].n > 0 && d.n_trg > 0;
+    ctx->stats.kernel_ms = 0;
+    ctx->stats.total_ms = 0;
+    ctx->stats.n_pairs = d.src[kind].n * ctx->n_trg;
+    ctx->stats.launches = launches;
+    ctx->stats.targets_per_thread = plan.T;
+    ctx->stats.source_splits = plan.n_splits;
+    ctx->stats.grid_ctas = (int)(plan.grid_x * plan.n_splits);
+    return SKB_OK;
+}
+
+int skb_sync(skb_ctx *ctx) {
+    if (!ctx)
+        return set_error(SKB_ERR_INVALID, "skb_sync: NULL ctx");
+    for (auto &d : ctx->devs) {
+        CUDA_TRY(cudaSetDevice(d.info.dev));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+    }
+    return SKB_OK;
+}
+
+int skb_stokeslet_direct(const double *r_src, const double *f_src, int n_src, const double *r_trg, double *u_trg,
+                         int n_trg) {
+    return direct_impl(SKB_STOKESLET, r_src, f_src, n_src, r_trg, u_trg, n_trg);
+}
+int skb_stresslet_direct(const double *r_src, const double *f_src, int n_src, const double *r_trg, double *u_trg,
+                         int n_trg) {
+    return direct_impl(SKB_STRESSLET, r_src, f_src, n_src, r_trg, u_trg, n_trg);
+}
+
+int skb_measure_fp64_peak(skb_ctx *ctx, double *flops_per_s) {
+    if (!ctx || !flops_per_s)
+        return set_error(SKB_ERR_INVALID, "skb_measure_fp64_peak: NULL");
+    DeviceState &d = ctx->devs[0];
+    CUDA_TRY(cudaSetDevice(d.info.dev));
+    const int blocks = d.info.num_sms * 8, threads = 256, iters = 1 << 15;
+    SKB_TRY(d.scratch.ensure((size_t)blocks * threads * 8));
+    double best = 0;
+    for (int rep = 0; rep < 5; ++rep) {
+        CUDA_TRY(cudaEventRecord(d.ev_k0, d.stream));
+        dfma_probe_kernel<<<blocks, threads, 0, d.stream>>>((double *)d.scratch.ptr, iters, 0.999999, 1e-9);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        CUDA_TRY(cudaEventRecord(d.ev_k1, d.stream));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        float ms = 0;
+        CUDA_TRY(cudaEventElapsedTime(&ms, d.ev_k0, d.ev_k1));
+        const double fl = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3);
+        if (rep > 0)
+            best = std::max(best, fl);
+    }
+    *flops_per_s = best;
+    return SKB_OK;
+}
+
+} // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Reference-named C++ entry points (SkellySim include/kernels.hpp:17-20).  Linking this library in
+// place of src/core/kernels.cu keeps kernels::stokeslet_direct_gpu / stresslet_direct_gpu
+// (src/core/kernels.cpp:354-366) and `pair_evaluator = "GPU"` working unchanged.  Error behaviour
+// follows the reference's CUDA path: message on stderr, exit(EXIT_FAILURE) (kernels.cu:8-15).
+// ------------------------------------------------------------------------------------------------
+namespace kernels {
+__attribute__((visibility("default"))) void stokeslet_direct_gpu_impl(const double *r_src, const double *f_src,
+                                                                      int n_src, const double *r_trg, double *u_trg,
+                                                                      int n_trg) {
+    if (skb_stokeslet_direct(r_src, f_src, n_src, r_trg, u_trg, n_trg) != SKB_OK) {
+        fprintf(stderr, "skelly_b200: stokeslet_direct_gpu_impl: %s\n", skb_last_error_string());
+        exit(EXIT_FAILURE);
+    }
+}
+__attribute__((visibility("default"))) void stresslet_direct_gpu_impl(const double *r_src, const double *f_src,
+                                                                      int n_src, const double *r_trg, double *u_trg,
+                                                                      int n_trg) {
+    if (skb_stresslet_direct(r_src, f_src, n_src, r_trg, u_trg, n_trg) != SKB_OK) {
+        fprintf(stderr, "skelly_b200: stresslet_direct_gpu_impl: %s\n", skb_last_error_string());
+        exit(EXIT_FAILURE);
+    }
+}
+} // namespace kernels

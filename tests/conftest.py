@@ -1,0 +1,49 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (B200); run with -m gpu on the GPU box")
+
+
+def _has_gpu():
+    try:
+        import skellysim_b200.capi as capi
+        return capi.device_count() > 0
+    except Exception:
+        return False
+
+
+def pytest_collection_modifyitems(config, items):
+    # `-m gpu` on a box without a GPU must fail loudly, not skip: a silent skip would read as green.
+    pass
+
+
+@pytest.fixture(scope="session")
+def golden_cases():
+    import glob
+    out = {}
+    for p in sorted(glob.glob(os.path.join(GOLDEN_DIR, "ref_numba_*.npz"))):
+        name = os.path.basename(p)[len("ref_numba_"):-4]
+        out[name] = dict(np.load(p))
+    assert out, "golden fixtures missing"
+    return out
+
+
+def rel_max(a, b):
+    """max|a-b| / max|b|  (the parity metric of SURVEY.md 8d / BASELINE.md 2.4)"""
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+def rel_l2(a, b):
+    """||a-b||_2 / ||b||_2  (performance_hydrodynamics_combined.cpp:95)"""
+    return float(np.linalg.norm(a - b) / np.linalg.norm(b))

@@ -1,0 +1,159 @@
+"""CPU tests of the oracle (oracle/oracle.c): pinned against the reference's own outputs (golden fixtures
+generated from src/skelly_sim/kernels.py by tests/golden/make_golden.py), against an independent numpy
+restatement, against 80-bit arithmetic and against analytic Stokes-flow identities."""
+import numpy as np
+import pytest
+
+import oracle as orc
+from conftest import rel_l2, rel_max
+
+TOL = 1e-12  # north_star: <= 1e-12 relative FP64
+
+
+@pytest.mark.parametrize("case", ["kernel_test", "ragged", "single", "fibers16x32", "wide_range"])
+def test_oracle_matches_reference_numba_golden(golden_cases, case):
+    g = golden_cases[case]
+    eta = float(g["eta"])
+    # Stokeslet: reference python returns u/(8 pi eta)  (kernels.py:292)
+    u = orc.stokeslet_direct(g["r_src"], g["f_sl"], g["r_trg"]) / eta
+    assert rel_max(u, g["u_stokeslet"]) < TOL and rel_l2(u, g["u_stokeslet"]) < TOL
+    # stresslet through Periphery::flow's strength formation f = 2 eta n (x) rho, then / eta
+    d = orc.periphery_flow(g["r_trg"], g["r_src"], g["normals"], g["density"], eta)
+    assert rel_max(d, g["u_stresslet"]) < TOL and rel_l2(d, g["u_stresslet"]) < TOL
+    r = orc.rotlet(g["r_src"], g["r_trg"], g["torque"], eta)
+    assert rel_max(r, g["u_rotlet"]) < TOL
+
+
+def _rand(seed, ns, nt, coincident=0):
+    rng = np.random.default_rng(seed)
+    rs = rng.uniform(-1, 1, (ns, 3))
+    rt = rng.uniform(-1, 1, (nt, 3))
+    if coincident:
+        rt[:coincident] = rs[:coincident]
+    return rs, rt, rng.uniform(-1, 1, (ns, 3)), rng.uniform(-1, 1, (ns, 9))
+
+
+def test_c_oracle_vs_numpy_and_long_double():
+    rs, rt, f3, f9 = _rand(7, 311, 97, coincident=13)
+    u = orc.stokeslet_direct(rs, f3, rt)
+    assert rel_max(u, orc.stokeslet_direct_numpy(rs, f3, rt)) < 1e-13
+    assert rel_max(u, orc.stokeslet_direct_ld(rs, f3, rt)) < 1e-13
+    d = orc.stresslet_direct(rs, f9, rt)
+    assert rel_max(d, orc.stresslet_direct_numpy(rs, f9, rt)) < 1e-13
+    assert rel_max(d, orc.stresslet_direct_ld(rs, f9, rt)) < 1e-13
+    assert np.isfinite(u).all() and np.isfinite(d).all()
+
+
+def test_coincident_pairs_contribute_zero():
+    # kernels.cu:39,70: r == 0 -> no contribution, no NaN
+    rs = np.array([[0.1, 0.2, 0.3], [1.0, 0.0, 0.0]])
+    f3 = np.array([[1.0, 2.0, 3.0], [0.0, 1.0, 0.0]])
+    u = orc.stokeslet_direct(rs, f3, rs[:1])
+    u_only_other = orc.stokeslet_direct(rs[1:], f3[1:], rs[:1])
+    assert np.array_equal(u, u_only_other)
+    f9 = np.arange(18.0).reshape(2, 9)
+    d = orc.stresslet_direct(rs, f9, rs[:1])
+    assert np.array_equal(d, orc.stresslet_direct(rs[1:], f9[1:], rs[:1]))
+
+
+def test_analytic_single_stokeslet():
+    # u = f/(4 pi eta r) along f, f/(8 pi eta r) perpendicular (SURVEY 8c item iii)
+    f = np.array([[0.0, 0.0, 2.0]])
+    src = np.zeros((1, 3))
+    r = 1.7
+    along = orc.stokeslet_direct(src, f, np.array([[0, 0, r]]))
+    perp = orc.stokeslet_direct(src, f, np.array([[r, 0, 0]]))
+    assert abs(along[0, 2] - 2.0 / (4 * np.pi * r)) < 1e-15
+    assert abs(perp[0, 2] - 2.0 / (8 * np.pi * r)) < 1e-15
+    assert abs(along[0, 0]) + abs(along[0, 1]) + abs(perp[0, 0]) + abs(perp[0, 1]) == 0.0
+
+
+def _sphere_quadrature(n_theta=48, n_phi=96, radius=1.0):
+    # Gauss-Legendre in cos(theta) x trapezoid in phi: spectrally accurate on the sphere
+    x, w = np.polynomial.legendre.leggauss(n_theta)
+    phi = 2 * np.pi * np.arange(n_phi) / n_phi
+    ct, ph = np.meshgrid(x, phi, indexing="ij")
+    st = np.sqrt(1 - ct**2)
+    n = np.stack([st * np.cos(ph), st * np.sin(ph), ct], -1).reshape(-1, 3)
+    wts = (w[:, None] * np.full((1, n_phi), 2 * np.pi / n_phi)).reshape(-1) * radius**2
+    return radius * n, n, wts
+
+
+def test_double_layer_closed_surface_identity():
+    # int_S T_ijk(x - y) n_k(y) dS(y) = -delta_ij inside a closed surface (outward n), 0 outside; with the
+    # reference's kernel u = -(3/4pi) sum (r.n)(r.q) r / r^5 w and constant density q this gives  u = q inside
+    # ... sign fixed by the reference's convention: check |u| = |q| inside, 0 outside.
+    pos, nrm, w = _sphere_quadrature()
+    q = np.array([0.3, -1.1, 0.7])
+    dens = np.tile(q, (pos.shape[0], 1)) * w[:, None]
+    inside = np.array([[0.1, 0.2, -0.15], [0.0, 0.0, 0.0]])
+    outside = np.array([[1.9, 0.3, 0.2], [0.0, -3.0, 1.0]])
+    ui = orc.periphery_flow(inside, pos, nrm, dens, 1.0)
+    uo = orc.periphery_flow(outside, pos, nrm, dens, 1.0)
+    assert np.abs(uo).max() < 1e-10
+    assert np.allclose(np.abs(ui), np.abs(q)[None, :], atol=1e-9)
+    assert np.allclose(ui[0], ui[1], atol=1e-9)
+
+
+@pytest.mark.parametrize("simd", [0, 1, 2])
+@pytest.mark.parametrize("threads", [1, 3, 4])
+def test_cpu_baseline_port_matches_scalar_oracle(simd, threads):
+    # the "port" of kernels::stokeslet_direct_cpu / stresslet_direct_cpu (OpenMP chunks + SIMD) against the
+    # scalar restatement; this is the reference kernel_test's own comparison (single vs openmp), 5e-9 there
+    if simd > orc.simd_level():
+        pytest.skip("SIMD level not available on this CPU")
+    rs, rt, f3, f9 = _rand(11, 1229, 743, coincident=5)
+    eta = 1.3
+    a = orc.stokeslet_direct_cpu(rs, f3, rt, eta, threads, simd)
+    b = orc.stresslet_direct_cpu(rs, f9, rt, eta, threads, simd)
+    assert rel_max(a, orc.stokeslet_direct(rs, f3, rt) / eta) < TOL
+    assert rel_max(b, orc.stresslet_direct(rs, f9, rt) / eta) < TOL
+    assert np.linalg.norm(a - orc.stokeslet_direct(rs, f3, rt) / eta) < 5e-9  # kernel_test.cpp:92
+
+
+def test_empty_inputs():
+    e3 = np.zeros((0, 3))
+    rt = np.ones((4, 3))
+    assert np.array_equal(orc.stokeslet_direct(e3, e3, rt), np.zeros((4, 3)))
+    assert orc.stokeslet_direct(rt, rt, e3).shape == (0, 3)
+    assert np.array_equal(orc.stresslet_direct(e3, np.zeros((0, 9)), rt), np.zeros((4, 3)))
+
+
+def test_fiber_flow_self_subtraction_equals_exclusion():
+    # all-pairs minus the regularised self block == sum over OTHER fibers only
+    # (fiber_container_finite_difference.cpp:198-210; node spacing 1/31 >> eps so no regularisation)
+    rng = np.random.default_rng(3)
+    n_f, n = 5, 16
+    pos = []
+    for _ in range(n_f):
+        x0 = rng.uniform(-1, 1, 3)
+        nh = rng.normal(size=3)
+        nh /= np.linalg.norm(nh)
+        pos.append(x0 + np.linspace(0, 1, n)[:, None] * nh)
+    pos = np.concatenate(pos)
+    forces = rng.uniform(-1, 1, pos.shape)
+    eta = 0.9
+    v = orc.fiber_flow(pos, pos, [n] * n_f, [1.0] * n_f, forces, eta, subtract_self=True)
+    w = np.concatenate([orc.trapezoid_weights(n, 1.0)] * n_f)
+    wf = forces * w[:, None]
+    ref = np.zeros_like(v)
+    for i in range(n_f):
+        others = np.r_[0:i * n, (i + 1) * n:n_f * n]
+        ref[i * n:(i + 1) * n] = orc.stokeslet_direct(pos[others], wf[others], pos[i * n:(i + 1) * n]) / eta
+    assert rel_max(v, ref) < 1e-11
+
+
+def test_matvec_flow_shell_mask():
+    # shell sources never act on shell targets (system.cpp:301-315)
+    rng = np.random.default_rng(5)
+    fib = dict(pos=rng.uniform(-1, 1, (32, 3)), n_nodes=[16, 16], lengths=[1.0, 1.0],
+               forces=rng.normal(size=(32, 3)))
+    shell = dict(pos=rng.uniform(-3, 3, (40, 3)), normals=rng.normal(size=(40, 3)), density=rng.normal(size=(40, 3)))
+    body = dict(pos=rng.uniform(-1, 1, (10, 3)) + 5, normals=rng.normal(size=(10, 3)),
+                density=rng.normal(size=(10, 3)), centers=np.array([[5.0, 5, 5]]),
+                forces=rng.normal(size=(1, 3)), torques=rng.normal(size=(1, 3)))
+    v = orc.matvec_flow(fib, shell, body, 1.0)
+    shell0 = dict(shell, density=np.zeros((40, 3)))
+    v0 = orc.matvec_flow(fib, shell0, body, 1.0)
+    assert np.array_equal(v[32:72], v0[32:72])
+    assert not np.allclose(v[:32], v0[:32])
