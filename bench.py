@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the SkellySim pair-kernel hot path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c2|c3]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+Metric (BASELINE.json): Stokeslet pair-interactions/s.  One "step" = one Stokeslet evaluator call of a GMRES
+matvec (FiberContainer::flow's all-pairs call, fiber nodes -> fiber+shell nodes) on the BASELINE `configs[1]`
+geometry (ellipsoidal periphery + 1000 fibers x 32 nodes), positions resident on the device(s) exactly as they are
+between the matvecs of one timestep, strengths changing every step.
+
+  value : whole-job pairs/s with the step's strengths already in HBM (device-pointer C-ABI entry points).
+  e2e   : the same step through the host-pointer path: strengths start in (pinned) host memory, velocities end in
+          host memory; H2D + D2H copies are inside the timed region.
+  N > 1 : one rank per GPU; targets AND sources block-partitioned over ranks (weak scaling: the suspension grows
+          so that pairs per GPU stay fixed: n_nodes ~ sqrt(N)); per step ONE NCCL all-gather of the source
+          strengths, then every rank evaluates its target block against all sources.  No other collective.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference's OpenMP direct path
+(oracle/, all host threads) on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+SL_FLOP_PER_PAIR = 28  # SURVEY.md 8d / BASELINE.md 2.1 (kernels.cu:65-75)
+DL_FLOP_PER_PAIR = 40
+NOMINAL_FP64_TFLOPS = 148 * 64 * 2 * 1.965e9 / 1e12  # 148 SMs x 64 DFMA/clk x 2 flop x max SM clock = 37.2
+
+
+# ------------------------------------------------------------------------------------------------
+# synthetic suspension
+# ------------------------------------------------------------------------------------------------
+def make_suspension(n_fibers: int, n_shell: int, seed: int = 1, n_nodes: int = 32, length: float = 1.0):
+    """Straight fibers x0 + L*linspace(0,1,n)*nhat (skelly_config.py:306-308) with random centres inside the
+    ellipsoid a,b,c = 7.8,4.16,4.16 (skelly_config.py:548-550) scaled with the fiber count; shell nodes on the
+    1.04x surface (precompute.py:34) with inward normals (precompute.py:78-80)."""
+    rng = np.random.default_rng(seed)
+    scale = max(1.0, (n_fibers / 1000.0) ** (1.0 / 3.0))
+    abc = np.array([7.8, 4.16, 4.16]) * scale
+    c = rng.normal(size=(n_fibers, 3))
+    c /= np.linalg.norm(c, axis=1)[:, None]
+    c *= (rng.uniform(0, 1, n_fibers) ** (1 / 3))[:, None] * 0.85
+    centres = c * abc
+    nh = rng.normal(size=(n_fibers, 3))
+    nh /= np.linalg.norm(nh, axis=1)[:, None]
+    s = np.linspace(-0.5 * length, 0.5 * length, n_nodes)
+    fib = (centres[:, None, :] + s[None, :, None] * nh[:, None, :]).reshape(-1, 3)
+    d = rng.normal(size=(n_shell, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    shell = d * abc * 1.04
+    nrm = -(shell / (abc * 1.04) ** 2)
+    nrm /= np.linalg.norm(nrm, axis=1)[:, None]
+    return np.ascontiguousarray(fib), np.ascontiguousarray(shell), np.ascontiguousarray(nrm)
+
+
+def workload_sizes(name: str, n_gpus: int):
+    g = math.sqrt(n_gpus)
+    if name == "c2":   # configs[1]: 1000 fibers x 32 + 8000-node ellipsoid shell
+        return int(round(1000 * g)), int(round(8000 * g))
+    if name == "c3":   # configs[2]-like: 3000 x 32 + 6000 shell nodes (~1e5 nodes)
+        return int(round(3000 * g)), int(round(6400 * g))
+    raise SystemExit(f"unknown workload {name}")
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks / throttle sampling during the timed region (pynvml, no subprocess)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap",
+               0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting", 0x100: "display_clock_setting"}
+
+    def __init__(self, index: int, period_s: float = 0.02):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nv = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception as e:  # pragma: no cover
+            self._nv = None
+            self.err = str(e)
+        self.period = period_s
+
+    def _run(self):
+        nv = self._nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(self.period)
+
+    def __enter__(self):
+        if self._nv:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        if self._thr:
+            self._thr.join()
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": 0}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU arm (oracle port of kernels::stokeslet_direct_cpu, all host threads)
+# ------------------------------------------------------------------------------------------------
+def cpu_sample_plan(orc, r_src, f_src, r_trg, budget_s: float):
+    """Pick how many targets a bounded CPU sample evaluates so that one call takes ~budget_s."""
+    n_probe = min(r_trg.shape[0], max(256, 16 * orc.max_threads()))
+    t0 = time.perf_counter()
+    orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n_probe], 1.0)
+    t0 = time.perf_counter()
+    orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n_probe], 1.0)
+    dt = time.perf_counter() - t0
+    rate = r_src.shape[0] * n_probe / max(dt, 1e-9)
+    n = int(min(r_trg.shape[0], max(n_probe, rate * budget_s / r_src.shape[0])))
+    return n, rate
+
+
+def cpu_baseline_leg(r_src, f_src, r_trg, budget_s=10.0):
+    import oracle as orc
+    n, _ = cpu_sample_plan(orc, r_src, f_src, r_trg, budget_s)
+    calls, t0 = 0, time.perf_counter()
+    while True:  # bounded sample: repeat the call until ~budget_s of CPU work has been timed
+        orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n], 1.0)
+        calls += 1
+        dt = time.perf_counter() - t0
+        if dt >= budget_s or calls >= 10000:
+            break
+    return {"value": calls * r_src.shape[0] * n / dt, "unit": "pairs/s", "cores": orc.max_threads(), "kind": "port",
+            "simd": {0: "scalar", 1: "avx2+fma", 2: "avx512"}[orc.simd_level()],
+            "sample": f"all {r_src.shape[0]} sources x first {n} of {r_trg.shape[0]} targets, {calls} calls, "
+                      f"{dt:.2f} s; OpenMP static target chunks as kernels.cpp:42-65 (the reference CPU path itself "
+                      "needs PVFMM: unbuildable here)"}
+
+
+def run_reference_arm(args, rank, world):
+    """--impl reference: the CPU implementation of the path on the host cores (oracle port; the reference's own
+    kernels.cpp cannot be compiled without PVFMM/Eigen/MPI)."""
+    if rank != 0:
+        return
+    import oracle as orc
+    n_fib, n_shell = workload_sizes(args.workload, args.gpus)
+    fib, shell, _ = make_suspension(n_fib, n_shell)
+    r_src, r_trg = fib, np.concatenate([fib, shell])
+    rng = np.random.default_rng(7)
+    f = rng.uniform(-1, 1, r_src.shape)
+    per_step = min(20.0, 150.0 / max(1, args.steps + args.warmup))
+    n, _ = cpu_sample_plan(orc, r_src, f, r_trg, per_step)
+    for _ in range(args.warmup):
+        orc.stokeslet_direct_cpu(r_src, f, r_trg[:n], 1.0)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.stokeslet_direct_cpu(r_src, f, r_trg[:n], 1.0)
+    dt = time.perf_counter() - t0
+    val = args.steps * r_src.shape[0] * n / dt
+    sample = f"each step = all {r_src.shape[0]} sources x first {n} of {r_trg.shape[0]} targets"
+    print(json.dumps({
+        "impl": "reference", "metric": "stokeslet_pair_interactions_per_s", "value": val, "unit": "pairs/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args.workload, n_fib, n_shell), "n_src": int(r_src.shape[0]),
+                   "n_trg": int(r_trg.shape[0]), "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": orc.max_threads(), "kind": "port",
+                         "simd": {0: "scalar", 1: "avx2+fma", 2: "avx512"}[orc.simd_level()], "sample": sample},
+        "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+def workload_name(w, n_fib, n_shell):
+    return (f"{w}: ellipsoid periphery ({n_shell} nodes) + {n_fib} fibers x 32 nodes; Stokeslet call of "
+            f"FiberContainer::flow (fiber nodes -> fiber+shell nodes), FP64 direct kernel")
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference_arm(args, rank, world)
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("--gpus N > 1 must be launched with torch.distributed.run --nproc-per-node N")
+        args.gpus = world
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+
+    import skellysim_b200 as skb
+    from skellysim_b200 import capi
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    n_fib, n_shell = workload_sizes(args.workload, world)
+    fib, shell, _ = make_suspension(n_fib, n_shell)
+    r_src_all = fib
+    r_trg_all = np.concatenate([fib, shell])
+    n_src, n_trg = r_src_all.shape[0], r_trg_all.shape[0]
+    src_chunk = -(-n_src // world)
+    trg_chunk = -(-n_trg // world)
+    s0, s1 = min(n_src, rank * src_chunk), min(n_src, (rank + 1) * src_chunk)
+    t0_, t1_ = min(n_trg, rank * trg_chunk), min(n_trg, (rank + 1) * trg_chunk)
+    my_trg = np.ascontiguousarray(r_trg_all[t0_:t1_])
+    n_my_trg = my_trg.shape[0]
+    rng = np.random.default_rng(7)
+    f_all = rng.uniform(-1, 1, (n_src, 3))  # trapezoid-weighted forces, U[-1,1]
+
+    # device state: positions once ("per timestep"); strengths per step
+    ctx = skb.Context(1, device_ids=[local_rank])
+    stream = torch.cuda.current_stream().cuda_stream  # kernels are launched on torch's current stream
+    d_rsrc = torch.from_numpy(r_src_all).to(dev)
+    d_rtrg = torch.from_numpy(my_trg).to(dev)
+    ctx.set_sources_device(skb.KERNEL_STOKESLET, d_rsrc.data_ptr(), n_src, stream)
+    ctx.set_targets_device(d_rtrg.data_ptr(), n_my_trg, stream)
+    d_f_gather = torch.zeros((world * src_chunk, 3), dtype=torch.float64, device=dev)  # all-gather landing zone
+    d_f_mine = d_f_gather[rank * src_chunk:(rank + 1) * src_chunk]
+    h_f_mine = torch.zeros((src_chunk, 3), dtype=torch.float64).pin_memory()
+    h_f_mine[:s1 - s0] = torch.from_numpy(f_all[s0:s1])
+    d_f_mine.copy_(h_f_mine, non_blocking=True)
+    d_u = torch.empty((max(n_my_trg, 1), 3), dtype=torch.float64, device=dev)
+    h_u = torch.empty((max(n_my_trg, 1), 3), dtype=torch.float64).pin_memory()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+    torch.cuda.synchronize()
+
+    # The gathered strength buffer has `world*src_chunk` rows; rows beyond n_src are zero strengths at padded
+    # positions only when world*src_chunk > n_src.  Sources are registered with exactly n_src rows, and the
+    # gather layout is contiguous by rank, so rows [0, n_src) are the real sources when src_chunk*world == n_src;
+    # otherwise the tail ranks are short.  Keep it simple: require divisibility (sizes above are multiples of 32).
+    def step_device():
+        if world > 1:
+            dist.all_gather_into_tensor(d_f_gather, d_f_mine)
+        ctx.eval_device(skb.KERNEL_STOKESLET, d_f_gather.data_ptr(), d_u.data_ptr(), False, stream)
+
+    def step_e2e():
+        d_f_mine.copy_(h_f_mine, non_blocking=True)
+        step_device()
+        h_u.copy_(d_u, non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        kms = []
+        barrier()
+        wall0 = time.perf_counter()
+        for a, b in evs:
+            flush.zero_()  # evict L2 between timed iterations (not timed)
+            a.record()
+            fn()
+            b.record()
+            if len(kms) < 8:  # a few kernel-only samples for the roofline (needs the step finished)
+                b.synchronize()
+                kms.append(ctx.stats()["kernel_ms"])
+        barrier()
+        wall = time.perf_counter() - wall0
+        tot_ms = sum(a.elapsed_time(b) for a, b in evs)
+        t = torch.tensor([tot_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), wall, kms
+
+    # correctness gate inside the bench (subset vs the CPU oracle), rank 0
+    for _ in range(args.warmup):
+        step_device()
+    torch.cuda.synchronize()
+    acc = None
+    if rank == 0:
+        import oracle as orc
+        idx = np.random.default_rng(3).choice(n_my_trg, size=min(128, n_my_trg), replace=False)
+        ref = orc.stokeslet_direct_cpu(r_src_all, f_all, my_trg[idx], 1.0)
+        got = d_u.cpu().numpy()[idx]
+        acc = float(np.abs(got - ref).max() / np.abs(ref).max())
+
+    with ClockSampler(local_rank) as clk:
+        n0 = capi.launch_count()
+        tot_ms, wall, kms = timed(step_device, args.steps)
+        launches = capi.launch_count() - n0
+    for _ in range(args.warmup):
+        step_e2e()
+    e2e_ms, _, _ = timed(step_e2e, args.steps)
+
+    pairs_total = float(n_src) * float(n_trg)
+    pairs_rank = float(n_src) * float(n_my_trg)
+    ms_per_step = tot_ms / args.steps
+    value = pairs_total / (ms_per_step * 1e-3)
+    e2e_val = pairs_total / (e2e_ms / args.steps * 1e-3)
+    k_ms = float(np.median(kms)) if kms else float("nan")
+    stats = ctx.stats()
+    launches_all = launches
+    if world > 1:
+        t = torch.tensor([launches], dtype=torch.int64, device=dev)
+        dist.all_reduce(t)
+        launches_all = int(t.item())
+
+    out = None
+    if rank == 0:
+        peak = ctx.measure_fp64_peak()
+        achieved = SL_FLOP_PER_PAIR * pairs_rank / (k_ms * 1e-3)
+        peaks_file = os.path.join(ROOT, "MEASURED_PEAKS.json")
+        hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        if os.path.exists(peaks_file):
+            hbm_peak = float(json.load(open(peaks_file))["hbm_gbs"])
+            hbm_src = "measured (MEASURED_PEAKS.json)"
+        # algorithmic HBM bytes per launch with cached positions: 24 B/source strengths read
+        # + positions 24 B/source + targets 24 B read + 24 B written per target
+        alg_bytes = 24.0 * n_src + 24.0 * n_src + 48.0 * n_my_trg
+        roofline = {
+            "bound": "fp64", "kernel": f"pair_sum_kernel<stokeslet,T={stats['targets_per_thread']}>",
+            "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
+            "peak_source": "measured on this GPU by skb_measure_fp64_peak (register-resident DFMA loop)",
+            "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved / 1e12 / NOMINAL_FP64_TFLOPS,
+            "flop_per_pair": SL_FLOP_PER_PAIR, "kernel_ms": k_ms,
+            "fp64_instr_per_pair": 22,
+            "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
+                    "algorithmic_bytes_per_launch": alg_bytes},
+            "traffic": None,
+        }
+        prof = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(prof):
+            roofline["traffic"] = json.load(open(prof)).get(args.workload)
+        out = {
+            "metric": "stokeslet_pair_interactions_per_s", "value": value, "unit": "pairs/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": workload_name(args.workload, n_fib, n_shell), "n_src": n_src, "n_trg": n_trg,
+                       "pairs_per_step": pairs_total, "parallelism": f"targets+sources block-partitioned x{world}"
+                       + (", 1 NCCL all-gather of strengths per step" if world > 1 else ""),
+                       "l2": "flushed between timed steps (256 MiB memset, untimed)",
+                       "timing": "per-step CUDA events on the launch stream, summed; max over ranks",
+                       "positions": "device-resident across steps (constant within a timestep, system.cpp:486-489)"},
+            "e2e": {"value": e2e_val, "unit": "pairs/s", "ms_per_step": e2e_ms / args.steps,
+                    "h2d_bytes_per_step": int(h_f_mine.numel() * 8 * world),
+                    "d2h_bytes_per_step": int(n_trg * 24),
+                    "path": "pinned host strengths -> H2D -> (all-gather) -> skb_eval_device -> D2H velocities"},
+            "gpu_launches": launches_all,
+            "launches_per_step": launches_all / args.steps / world,
+            "clocks": clk.summary(),
+            "roofline": roofline,
+            "accuracy": {"max_rel_err_vs_oracle": acc, "targets_checked": 128, "gate": 1e-12},
+            "wall_s_timed_region": wall,
+        }
+        if acc is not None and not (acc < 1e-12):
+            out["error"] = f"accuracy gate failed: {acc}"
+        if world == 1 and not args.no_cpu_baseline:
+            out["cpu_baseline"] = cpu_baseline_leg(r_src_all, f_all, r_trg_all)
+        print(json.dumps(out))
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

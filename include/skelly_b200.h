@@ -107,8 +107,9 @@ SKB_API int skb_eval_double_layer(skb_ctx *ctx, const double *density, double et
 
 /* ---- device-pointer entry points (single-GPU contexts) ----------------------------------------
  * For hosts that already own device memory and a stream (one rank per GPU under NCCL: the caller
- * all-gathers strengths itself, then evaluates its target block).  Asynchronous on `stream`
- * (a cudaStream_t passed as void*; NULL = the context's own stream, on which skb_sync waits). */
+ * all-gathers strengths itself, then evaluates its target block).  Asynchronous on `stream`, a
+ * cudaStream_t passed as void* and used verbatim (NULL = CUDA's legacy default stream); the caller
+ * synchronises that stream.  skb_sync only waits for the context's own (host-pointer path) stream. */
 SKB_API int skb_set_targets_device(skb_ctx *ctx, const double *d_r_trg, int64_t n_trg, void *stream);
 SKB_API int skb_set_sources_device(skb_ctx *ctx, int kind, const double *d_r_src, int64_t n_src, void *stream);
 SKB_API int skb_eval_device(skb_ctx *ctx, int kind, const double *d_f_src, double *d_u_trg, int accumulate,

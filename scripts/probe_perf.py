@@ -22,10 +22,14 @@ def run(ctx, kind, f, reps=5):
     return k, t, ks[-1]
 
 
+QUICK = "--quick" in sys.argv
+
+
 def main():
     shapes = [(32000, 40000), (96000, 102400)]
-    if len(sys.argv) > 1:
-        shapes = [tuple(int(x) for x in a.split("x")) for a in sys.argv[1:]]
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    if args:
+        shapes = [tuple(int(x) for x in a.split("x")) for a in args]
     rng = np.random.default_rng(0)
     out = []
     with skb.Context(1) as ctx:
@@ -39,7 +43,7 @@ def main():
                 ctx.set_sources(kind, rs)
                 f = rng.uniform(-1, 1, (ns, fdim))
                 for T in (0, 1, 2, 4, 8):
-                    for S in ((0,) if T == 0 else (0, 1, 2, 3, 4, 6, 8)):
+                    for S in ((0,) if (T == 0 or QUICK) else (0, 4, 8, 16)):
                         ctx.set_tuning(T, S)
                         k, t, st = run(ctx, kind, f)
                         pairs = ns * nt

@@ -16,7 +16,7 @@
 //     a source is broadcast from shared memory to the whole warp with 128-bit LDS, so shared-memory
 //     traffic is 3 LDS.128 per source per warp against 22*T FP64 instructions.
 //   * sources stream HBM/L2 -> shared memory with TMA bulk copies (cp.async.bulk, SASS UBLKCP) issued by
-//     one elected lane of a dedicated producer warp into a 4-stage ring guarded by full/empty mbarriers;
+//     one elected lane two tiles ahead of use into a 4-stage ring guarded by full/empty mbarriers;
 //     positions and strengths keep the caller's AoS layout, so a stage is two contiguous byte ranges and
 //     no repacking pass is needed.
 //   * the stresslet strength is pre-contracted once per matvec to its 6 symmetric combinations
@@ -31,9 +31,8 @@ namespace skb {
 
 constexpr int kSrcTile = 128;       // sources per shared-memory stage
 constexpr int kStages = 4;          // TMA ring depth
-constexpr int kConsumerWarps = 4;   // compute warps per CTA
-constexpr int kConsumerThreads = kConsumerWarps * 32;
-constexpr int kCtaThreads = kConsumerThreads + 32; // + producer warp
+constexpr int kPrefetch = 2;        // tiles in flight ahead of the one being consumed (< kStages - 1)
+constexpr int kCtaThreads = 128;    // 4 warps, one per SM sub-partition; every warp computes
 constexpr int kMaxSplits = 256;
 
 enum Kind : int { kStokeslet = 0, kStresslet = 1 };
@@ -106,37 +105,287 @@ __device__ __forceinline__ double rinv_masked(double r2) {
     return fma(q, p, y0);
 }
 
-// Stokeslet pair, 22 FP64 instructions.  (kernels.cu:62-76)
-__device__ __forceinline__ void stokeslet_pair(double tx, double ty, double tz, double sx, double sy, double sz,
-                                               double fx, double fy, double fz, double &ux, double &uy, double &uz) {
-    const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
-    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-    const double y = rinv_masked(r2);
-    const double y2 = y * y;
-    const double fr = fma(fz, dz, fma(fy, dy, fx * dx));
-    const double ip = fr * y2;
-    ux = fma(y, fma(dx, ip, fx), ux);
-    uy = fma(y, fma(dy, ip, fy), uy);
-    uz = fma(y, fma(dz, ip, fz), uz);
+// ---------------------------------------------------------------------------------------------
+// C independent (target, source) pair chains evaluated stage by stage, so a warp always has C FP64
+// instructions in flight.  A single pair's chain is ~15 dependent FP64 instructions; issued back to back
+// (what ptxas produces from a per-pair function under a tight register cap) it left the FP64 pipe idle
+// for most of the DFMA latency: 78.6% pipe utilisation in profiles/r1_ncu_pair_v1.md.
+// Stokeslet: 22 FP64 instructions per pair (kernels.cu:62-76);  outputs rinv y[c] and v = f + d (f.d) y^2.
+// ---------------------------------------------------------------------------------------------
+template <int C>
+__device__ __forceinline__ void stokeslet_chains(const double (&tx)[C], const double (&ty)[C], const double (&tz)[C],
+                                                 const double (&sx)[C], const double (&sy)[C], const double (&sz)[C],
+                                                 const double (&fx)[C], const double (&fy)[C], const double (&fz)[C],
+                                                 double (&y)[C], double (&vx)[C], double (&vy)[C], double (&vz)[C]) {
+    // Instruction ORDER matters beyond dependencies: an FP64 instruction that reads 3 distinct 64-bit registers
+    // occupies the pipe for 3 cycles instead of 2 (register-file read limit, scripts/ubench/fp64_ubench.cu) unless
+    // one operand comes from the operand-reuse cache, i.e. the previous instruction read the same register in the
+    // same operand slot.  Every 3-operand stage below therefore runs over the chains with one operand held fixed.
+    double r2[C], fr[C], q[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        vx[c] = tx[c] - sx[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        vy[c] = ty[c] - sy[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        vz[c] = tz[c] - sz[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = vx[c] * vx[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = fma(vy[c], vy[c], r2[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = fma(vz[c], vz[c], r2[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        double y0;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2[c]));
+        if (__double2hiint(r2[c]) < 0x00100000) // r2 == 0 (or subnormal): the pair contributes exactly 0
+            y0 = 0.0;
+        y[c] = y0;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        fr[c] = fx[c] * vx[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        fr[c] = fma(fy[c], vy[c], fr[c]); // fy held fixed across the chains of one source
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        fr[c] = fma(fz[c], vz[c], fr[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = r2[c] * y[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = fma(-r2[c], y[c], 1.0); // e = 1 - r2 y0^2
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        q[c] = fma(0.375, r2[c], 0.5);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        q[c] = r2[c] * q[c]; // h = e (1/2 + 3/8 e)
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        y[c] = fma(y[c], q[c], y[c]); // 1/|r| = y0 + y0 h   (2 distinct registers)
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        q[c] = y[c] * y[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        q[c] = fr[c] * q[c]; // (f.d)/|r|^2
+    // v_k = d_k q + f_k, walked so that consecutive instructions share f_k (within a row) or q (at the turns)
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        vx[c] = fma(vx[c], q[c], fx[c]);
+#pragma unroll
+    for (int c = C - 1; c >= 0; --c)
+        vy[c] = fma(vy[c], q[c], fy[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        vz[c] = fma(vz[c], q[c], fz[c]);
 }
 
-// stresslet pair, 27 FP64 instructions; s = (sxx, syy, szz, sxy+syx, sxz+szx, syz+szy); the -3 lives in the
-// post-scale.  (kernels.cu:29-54)
-__device__ __forceinline__ void stresslet_pair(double tx, double ty, double tz, double sx, double sy, double sz,
-                                               double sxx, double syy, double szz, double pxy, double pxz,
-                                               double pyz, double &ux, double &uy, double &uz) {
-    const double dx = tx - sx, dy = ty - sy, dz = tz - sz;
-    const double r2 = fma(dz, dz, fma(dy, dy, dx * dx));
-    const double y = rinv_masked(r2);
-    const double y2 = y * y;
-    const double y5 = (y2 * y2) * y;
-    const double v1 = fma(pxz, dz, fma(pxy, dy, sxx * dx));
-    const double v2 = fma(pyz, dz, syy * dy);
-    const double v3 = szz * dz;
-    const double co = fma(v3, dz, fma(v2, dy, v1 * dx)) * y5;
-    ux = fma(dx, co, ux);
-    uy = fma(dy, co, uy);
-    uz = fma(dz, co, uz);
+// stresslet: 27 FP64 instructions per pair; s = (sxx, syy, szz, sxy+syx, sxz+szx, syz+szy), the -3 lives in the
+// post-scale (kernels.cu:29-54).  Outputs d[c] and the scalar coefficient co[c] = (d.S.d)/|d|^5.
+template <int C>
+__device__ __forceinline__ void stresslet_chains(const double (&tx)[C], const double (&ty)[C], const double (&tz)[C],
+                                                 const double (&sx)[C], const double (&sy)[C], const double (&sz)[C],
+                                                 const double (&sxx)[C], const double (&syy)[C],
+                                                 const double (&szz)[C], const double (&pxy)[C],
+                                                 const double (&pxz)[C], const double (&pyz)[C], double (&dx)[C],
+                                                 double (&dy)[C], double (&dz)[C], double (&co)[C]) {
+    // same ordering rule as stokeslet_chains: 3-register stages keep one operand fixed across the chains
+    double r2[C], y[C], v2[C], q[C];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        dx[c] = tx[c] - sx[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        dy[c] = ty[c] - sy[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        dz[c] = tz[c] - sz[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = dx[c] * dx[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = fma(dy[c], dy[c], r2[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = fma(dz[c], dz[c], r2[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c) {
+        double y0;
+        asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2[c]));
+        if (__double2hiint(r2[c]) < 0x00100000)
+            y0 = 0.0;
+        y[c] = y0;
+    }
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        co[c] = sxx[c] * dx[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        co[c] = fma(pxy[c], dy[c], co[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        co[c] = fma(pxz[c], dz[c], co[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        v2[c] = syy[c] * dy[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        v2[c] = fma(pyz[c], dz[c], v2[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = r2[c] * y[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = fma(-r2[c], y[c], 1.0);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        q[c] = fma(0.375, r2[c], 0.5);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        q[c] = r2[c] * q[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        y[c] = fma(y[c], q[c], y[c]); // 1/|r|
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        co[c] = co[c] * dx[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        q[c] = szz[c] * dz[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        co[c] = fma(v2[c], dy[c], co[c]);
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = y[c] * y[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        co[c] = fma(q[c], dz[c], co[c]); // d.S.d
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = r2[c] * r2[c];
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        r2[c] = r2[c] * y[c]; // 1/|r|^5
+#pragma unroll
+    for (int c = 0; c < C; ++c)
+        co[c] = co[c] * r2[c];
+}
+
+// Two sources (a, b) against the thread's T targets, as groups of independent chains:
+//   T == 1: one group of 2 chains (a, b);  T == 2: one group of 4 (2 targets x 2 sources);
+//   T >= 4: per source, groups of 4 targets.
+template <int T>
+__device__ __forceinline__ void stokeslet_two_sources(const double (&tx)[T], const double (&ty)[T],
+                                                      const double (&tz)[T], const double (&sa)[3],
+                                                      const double (&fa)[3], const double (&sb)[3],
+                                                      const double (&fb)[3], double (&ux)[T], double (&uy)[T],
+                                                      double (&uz)[T]) {
+    if constexpr (T <= 2) {
+        constexpr int C = 2 * T;
+        double cx[C], cy[C], cz[C], sx[C], sy[C], sz[C], fx[C], fy[C], fz[C], y[C], vx[C], vy[C], vz[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int t = c % T;
+            const bool second = c >= T;
+            cx[c] = tx[t], cy[c] = ty[t], cz[c] = tz[t];
+            sx[c] = second ? sb[0] : sa[0], sy[c] = second ? sb[1] : sa[1], sz[c] = second ? sb[2] : sa[2];
+            fx[c] = second ? fb[0] : fa[0], fy[c] = second ? fb[1] : fa[1], fz[c] = second ? fb[2] : fa[2];
+        }
+        stokeslet_chains<C>(cx, cy, cz, sx, sy, sz, fx, fy, fz, y, vx, vy, vz);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int t = c % T;
+            ux[t] = fma(y[c], vx[c], ux[t]);
+            uy[t] = fma(y[c], vy[c], uy[t]);
+            uz[t] = fma(y[c], vz[c], uz[t]);
+        }
+    } else {
+#pragma unroll
+        for (int src = 0; src < 2; ++src) {
+#pragma unroll
+            for (int g = 0; g < T / 4; ++g) {
+                double cx[4], cy[4], cz[4], sx[4], sy[4], sz[4], fx[4], fy[4], fz[4], y[4], vx[4], vy[4], vz[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    cx[c] = tx[4 * g + c], cy[c] = ty[4 * g + c], cz[c] = tz[4 * g + c];
+                    sx[c] = src ? sb[0] : sa[0], sy[c] = src ? sb[1] : sa[1], sz[c] = src ? sb[2] : sa[2];
+                    fx[c] = src ? fb[0] : fa[0], fy[c] = src ? fb[1] : fa[1], fz[c] = src ? fb[2] : fa[2];
+                }
+                stokeslet_chains<4>(cx, cy, cz, sx, sy, sz, fx, fy, fz, y, vx, vy, vz);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    ux[4 * g + c] = fma(y[c], vx[c], ux[4 * g + c]);
+                    uy[4 * g + c] = fma(y[c], vy[c], uy[4 * g + c]);
+                    uz[4 * g + c] = fma(y[c], vz[c], uz[4 * g + c]);
+                }
+            }
+        }
+    }
+}
+
+template <int T>
+__device__ __forceinline__ void stresslet_two_sources(const double (&tx)[T], const double (&ty)[T],
+                                                      const double (&tz)[T], const double (&sa)[3],
+                                                      const double (&fa)[6], const double (&sb)[3],
+                                                      const double (&fb)[6], double (&ux)[T], double (&uy)[T],
+                                                      double (&uz)[T]) {
+    if constexpr (T <= 2) {
+        constexpr int C = 2 * T;
+        double cx[C], cy[C], cz[C], sx[C], sy[C], sz[C], s0[C], s1[C], s2[C], s3[C], s4[C], s5[C];
+        double dx[C], dy[C], dz[C], co[C];
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int t = c % T;
+            const bool second = c >= T;
+            cx[c] = tx[t], cy[c] = ty[t], cz[c] = tz[t];
+            sx[c] = second ? sb[0] : sa[0], sy[c] = second ? sb[1] : sa[1], sz[c] = second ? sb[2] : sa[2];
+            s0[c] = second ? fb[0] : fa[0], s1[c] = second ? fb[1] : fa[1], s2[c] = second ? fb[2] : fa[2];
+            s3[c] = second ? fb[3] : fa[3], s4[c] = second ? fb[4] : fa[4], s5[c] = second ? fb[5] : fa[5];
+        }
+        stresslet_chains<C>(cx, cy, cz, sx, sy, sz, s0, s1, s2, s3, s4, s5, dx, dy, dz, co);
+#pragma unroll
+        for (int c = 0; c < C; ++c) {
+            const int t = c % T;
+            ux[t] = fma(dx[c], co[c], ux[t]);
+            uy[t] = fma(dy[c], co[c], uy[t]);
+            uz[t] = fma(dz[c], co[c], uz[t]);
+        }
+    } else {
+#pragma unroll
+        for (int src = 0; src < 2; ++src) {
+#pragma unroll
+            for (int g = 0; g < T / 4; ++g) {
+                double cx[4], cy[4], cz[4], sx[4], sy[4], sz[4], s0[4], s1[4], s2[4], s3[4], s4[4], s5[4];
+                double dx[4], dy[4], dz[4], co[4];
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    cx[c] = tx[4 * g + c], cy[c] = ty[4 * g + c], cz[c] = tz[4 * g + c];
+                    sx[c] = src ? sb[0] : sa[0], sy[c] = src ? sb[1] : sa[1], sz[c] = src ? sb[2] : sa[2];
+                    s0[c] = src ? fb[0] : fa[0], s1[c] = src ? fb[1] : fa[1], s2[c] = src ? fb[2] : fa[2];
+                    s3[c] = src ? fb[3] : fa[3], s4[c] = src ? fb[4] : fa[4], s5[c] = src ? fb[5] : fa[5];
+                }
+                stresslet_chains<4>(cx, cy, cz, sx, sy, sz, s0, s1, s2, s3, s4, s5, dx, dy, dz, co);
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    ux[4 * g + c] = fma(dx[c], co[c], ux[4 * g + c]);
+                    uy[4 * g + c] = fma(dy[c], co[c], uy[4 * g + c]);
+                    uz[4 * g + c] = fma(dz[c], co[c], uz[4 * g + c]);
+                }
+            }
+        }
+    }
 }
 
 // shared-memory footprint of the main kernel
@@ -145,40 +394,54 @@ template <int KIND, int T> struct SmemLayout {
     static constexpr int pos_stage_bytes = kSrcTile * 3 * 8;
     static constexpr int f_stage_bytes = kSrcTile * fdim * 8;
     static constexpr int stage_bytes = pos_stage_bytes + f_stage_bytes;
-    static constexpr int trg_bytes = kConsumerThreads * T * 3 * 8;
+    static constexpr int trg_bytes = kCtaThreads * T * 3 * 8;
     static constexpr int bar_offset = kStages * stage_bytes + trg_bytes;
     static constexpr int total_bytes = bar_offset + 2 * kStages * 8;
 };
 
 // ---------------------------------------------------------------------------------------------
-// Main kernel: grid = (target tiles, source splits), block = 4 consumer warps + 1 TMA producer warp.
+// Main kernel: grid = (target tiles, source splits), block = 4 warps, all of them compute.
+// Lane 0 of warp 0 doubles as the TMA producer: before computing tile k it issues the bulk copies of tile
+// k + kPrefetch into the ring slot that every warp released two tiles ago, so the wait on that slot's
+// "empty" barrier never blocks in practice and no registers are spent on a dedicated producer warp.
 // ---------------------------------------------------------------------------------------------
 template <int KIND, int T, int MINB>
 __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairArgs a) {
     using L = SmemLayout<KIND, T>;
-    constexpr int fdim = L::fdim;
-    constexpr int kTileT = kConsumerThreads * T;
+    constexpr int kTileT = kCtaThreads * T;
     extern __shared__ __align__(128) unsigned char smem[];
     double *trg_s = reinterpret_cast<double *>(smem + kStages * L::stage_bytes);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::bar_offset);
     uint64_t *empty_bar = full_bar + kStages;
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    const int lane = tid & 31;
     const long long t_base = (long long)blockIdx.x * kTileT;
     const int first_tile = blockIdx.y * a.tiles_per_split;
     int n_tiles = a.n_src_tiles - first_tile;
     n_tiles = n_tiles < a.tiles_per_split ? n_tiles : a.tiles_per_split;
     if (n_tiles < 0)
         n_tiles = 0;
+    const char *gp = reinterpret_cast<const char *>(a.r_src) + (size_t)first_tile * L::pos_stage_bytes;
+    const char *gf = reinterpret_cast<const char *>(a.f_src) + (size_t)first_tile * L::f_stage_bytes;
+
+    auto issue_tile = [&](int k) {
+        const int s = k % kStages;
+        unsigned char *dst = smem + s * L::stage_bytes;
+        mbar_arrive_expect_tx(&full_bar[s], L::stage_bytes);
+        tma_bulk_g2s(dst, gp + (size_t)k * L::pos_stage_bytes, L::pos_stage_bytes, &full_bar[s]);
+        tma_bulk_g2s(dst + L::pos_stage_bytes, gf + (size_t)k * L::f_stage_bytes, L::f_stage_bytes, &full_bar[s]);
+    };
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kConsumerWarps);
+            mbar_init(&empty_bar[s], kCtaThreads / 32);
         }
         mbar_fence_init();
+        for (int k = 0; k < kPrefetch && k < n_tiles; ++k)
+            issue_tile(k);
     }
     // coalesced load of this CTA's contiguous target block (AoS xyz) into shared memory; the tail is
     // filled with the last valid target so no lane ever computes on garbage
@@ -190,32 +453,12 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
         for (int i = tid; i < kTileT * 3; i += kCtaThreads)
             trg_s[i] = (i < n_dbl) ? __ldg(g + i) : __ldg(g + (n_dbl - 3) + (i % 3));
     }
-    __syncthreads();
+    __syncthreads(); // barrier init + target block visible to everyone
 
-    if (warp == kConsumerWarps) {
-        // ------------------------------ producer warp ------------------------------
-        if (lane == 0) {
-            const char *gp = reinterpret_cast<const char *>(a.r_src) + (size_t)first_tile * L::pos_stage_bytes;
-            const char *gf = reinterpret_cast<const char *>(a.f_src) + (size_t)first_tile * L::f_stage_bytes;
-            for (int k = 0; k < n_tiles; ++k) {
-                const int s = k % kStages;
-                if (k >= kStages)
-                    mbar_wait(&empty_bar[s], ((k / kStages) - 1) & 1);
-                unsigned char *dst = smem + s * L::stage_bytes;
-                mbar_arrive_expect_tx(&full_bar[s], L::stage_bytes);
-                tma_bulk_g2s(dst, gp + (size_t)k * L::pos_stage_bytes, L::pos_stage_bytes, &full_bar[s]);
-                tma_bulk_g2s(dst + L::pos_stage_bytes, gf + (size_t)k * L::f_stage_bytes, L::f_stage_bytes,
-                             &full_bar[s]);
-            }
-        }
-        return;
-    }
-
-    // ------------------------------ consumer warps ------------------------------
     double tx[T], ty[T], tz[T], ux[T], uy[T], uz[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        const int i = t * kConsumerThreads + tid;
+        const int i = t * kCtaThreads + tid;
         tx[t] = trg_s[3 * i + 0];
         ty[t] = trg_s[3 * i + 1];
         tz[t] = trg_s[3 * i + 2];
@@ -224,6 +467,12 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
 
     for (int k = 0; k < n_tiles; ++k) {
         const int s = k % kStages;
+        if (tid == 0 && k + kPrefetch < n_tiles) {
+            const int kn = k + kPrefetch;
+            if (kn >= kStages)
+                mbar_wait(&empty_bar[kn % kStages], ((kn / kStages) - 1) & 1);
+            issue_tile(kn);
+        }
         mbar_wait(&full_bar[s], (k / kStages) & 1);
         const double2 *ps = reinterpret_cast<const double2 *>(smem + s * L::stage_bytes);
         const double2 *fs = reinterpret_cast<const double2 *>(smem + s * L::stage_bytes + L::pos_stage_bytes);
@@ -234,25 +483,17 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
         for (int j = 0; j < jmax; ++j) {
             // two sources per iteration: 48 B of positions = 3 x LDS.128 (warp-wide broadcast)
             const double2 p0 = ps[3 * j + 0], p1 = ps[3 * j + 1], p2 = ps[3 * j + 2];
+            const double sa[3] = {p0.x, p0.y, p1.x}, sb[3] = {p1.y, p2.x, p2.y};
             if constexpr (KIND == kStokeslet) {
                 const double2 f0 = fs[3 * j + 0], f1 = fs[3 * j + 1], f2 = fs[3 * j + 2];
-#pragma unroll
-                for (int t = 0; t < T; ++t)
-                    stokeslet_pair(tx[t], ty[t], tz[t], p0.x, p0.y, p1.x, f0.x, f0.y, f1.x, ux[t], uy[t], uz[t]);
-#pragma unroll
-                for (int t = 0; t < T; ++t)
-                    stokeslet_pair(tx[t], ty[t], tz[t], p1.y, p2.x, p2.y, f1.y, f2.x, f2.y, ux[t], uy[t], uz[t]);
+                const double fa[3] = {f0.x, f0.y, f1.x}, fb[3] = {f1.y, f2.x, f2.y};
+                stokeslet_two_sources<T>(tx, ty, tz, sa, fa, sb, fb, ux, uy, uz);
             } else {
                 const double2 f0 = fs[6 * j + 0], f1 = fs[6 * j + 1], f2 = fs[6 * j + 2];
                 const double2 f3 = fs[6 * j + 3], f4 = fs[6 * j + 4], f5 = fs[6 * j + 5];
-#pragma unroll
-                for (int t = 0; t < T; ++t)
-                    stresslet_pair(tx[t], ty[t], tz[t], p0.x, p0.y, p1.x, f0.x, f0.y, f1.x, f1.y, f2.x, f2.y, ux[t],
-                                   uy[t], uz[t]);
-#pragma unroll
-                for (int t = 0; t < T; ++t)
-                    stresslet_pair(tx[t], ty[t], tz[t], p1.y, p2.x, p2.y, f3.x, f3.y, f4.x, f4.y, f5.x, f5.y, ux[t],
-                                   uy[t], uz[t]);
+                const double fa[6] = {f0.x, f0.y, f1.x, f1.y, f2.x, f2.y};
+                const double fb[6] = {f3.x, f3.y, f4.x, f4.y, f5.x, f5.y};
+                stresslet_two_sources<T>(tx, ty, tz, sa, fa, sb, fb, ux, uy, uz);
             }
         }
         __syncwarp();
@@ -263,7 +504,7 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
     double *out = a.partial + (size_t)blockIdx.y * (size_t)a.n_trg * 3;
 #pragma unroll
     for (int t = 0; t < T; ++t) {
-        const long long i = t_base + t * kConsumerThreads + tid;
+        const long long i = t_base + t * kCtaThreads + tid;
         if (i < a.n_trg) {
             out[3 * i + 0] = ux[t];
             out[3 * i + 1] = uy[t];

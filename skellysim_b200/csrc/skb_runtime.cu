@@ -69,16 +69,14 @@ template <int KIND, int T, int MINB> static int occupancy_variant() {
     return nb < 1 ? 1 : nb;
 }
 
-// min-blocks-per-SM hints (register caps): T=1:6  T=2:5  T=4:4  T=8:2
+// min-blocks-per-SM hints (register caps at 128 threads/CTA): T=1:8 (64)  T=2:6 (85)  T=4:4 (128)  T=8:2 (255)
 #define SKB_DISPATCH_T(KIND, T, CALL)                                                                                 \
     switch (T) {                                                                                                      \
-    case 1: CALL(KIND, 1, 6); break;                                                                                  \
-    case 2: CALL(KIND, 2, 5); break;                                                                                  \
+    case 1: CALL(KIND, 1, 8); break;                                                                                  \
+    case 2: CALL(KIND, 2, 6); break;                                                                                  \
     case 4: CALL(KIND, 4, 4); break;                                                                                  \
     default: CALL(KIND, 8, 2); break;                                                                                 \
     }
-
-static int t_index(int T) { return T == 1 ? 0 : T == 2 ? 1 : T == 4 ? 2 : 3; }
 
 DeviceInfo query_device(int dev) {
     DeviceInfo di;
@@ -118,7 +116,7 @@ LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_sr
         if (force_T > 0 && T != force_T)
             continue;
         const int occ = di.occupancy[kind][ti];
-        const long long tile_t = (long long)kConsumerThreads * T;
+        const long long tile_t = (long long)kCtaThreads * T;
         const long long n_tiles_t = (n_trg + tile_t - 1) / tile_t;
         // efficiency of the inner loop vs T (LDS + loop overhead amortised over T pairs); calibrated on B200
         const double t_pen = (T == 1) ? 1.30 : (T == 2) ? 1.10 : (T == 4) ? 1.0 : 1.0;
@@ -416,6 +414,7 @@ static void partition_targets(skb_ctx *ctx, long long n_trg) {
 }
 
 static int set_targets_impl(skb_ctx *ctx, const double *r_trg, long long n_trg, bool on_device, cudaStream_t user) {
+    // on_device: `user` is used verbatim (0 = CUDA's legacy default stream); host path: the context's stream
     if (!ctx)
         return set_error(SKB_ERR_INVALID, "set_targets: NULL ctx");
     if (n_trg < 0 || (n_trg > 0 && !r_trg))
@@ -429,7 +428,7 @@ static int set_targets_impl(skb_ctx *ctx, const double *r_trg, long long n_trg, 
         CUDA_TRY(cudaSetDevice(d.info.dev));
         SKB_TRY(d.r_trg.ensure((size_t)d.n_trg * 24));
         SKB_TRY(d.u.ensure((size_t)d.n_trg * 24));
-        cudaStream_t st = user ? user : d.stream;
+        cudaStream_t st = on_device ? user : d.stream;
         CUDA_TRY(cudaMemcpyAsync(d.r_trg.ptr, r_trg + 3 * d.trg_begin, (size_t)d.n_trg * 24,
                                  on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
     }
@@ -465,7 +464,7 @@ static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long lo
         if (n_src == 0)
             continue;
         CUDA_TRY(cudaSetDevice(d.info.dev));
-        cudaStream_t st = user ? user : d.stream;
+        cudaStream_t st = on_device ? user : d.stream;
         SKB_TRY(s.r.ensure((size_t)n_pad * 24));
         SKB_TRY(s.f_raw.ensure((size_t)chunk * P * fdim_raw * 8));
         SKB_TRY(s.f_packed.ensure((size_t)n_pad * fdim_packed * 8));
@@ -735,7 +734,7 @@ int skb_eval_device(skb_ctx *ctx, int kind, const double *d_f_src, double *d_u_t
     if ((d.src[kind].n > 0 && !d_f_src) || (ctx->n_trg > 0 && !d_u_trg))
         return set_error(SKB_ERR_INVALID, "eval_device: NULL pointer");
     CUDA_TRY(cudaSetDevice(d.info.dev));
-    cudaStream_t st = stream ? (cudaStream_t)stream : d.stream;
+    cudaStream_t st = (cudaStream_t)stream; // verbatim: 0 is CUDA's legacy default stream
     int launches = 0;
     LaunchPlan plan{};
     SKB_TRY(eval_on_device(ctx, d, kind, kRaw, d_f_src, 0.0, d_u_trg, accumulate, st, true, &launches, &plan));
