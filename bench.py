@@ -244,10 +244,12 @@ def main():
     r_src_all = fib
     r_trg_all = np.concatenate([fib, shell])
     n_src, n_trg = r_src_all.shape[0], r_trg_all.shape[0]
-    src_chunk = -(-n_src // world)
-    trg_chunk = -(-n_trg // world)
-    s0, s1 = min(n_src, rank * src_chunk), min(n_src, (rank + 1) * src_chunk)
-    t0_, t1_ = min(n_trg, rank * trg_chunk), min(n_trg, (rank + 1) * trg_chunk)
+    from skellysim_b200.distributed import RankPartition, allgather_strengths
+    part = RankPartition(n_src, n_trg, world, rank)
+    src_chunk = part.src_chunk
+    (s0, s1), (t0_, t1_) = part.src_range, part.trg_range
+    if part.gathered_rows != n_src:
+        raise SystemExit("bench workloads keep n_src divisible by the rank count")
     my_trg = np.ascontiguousarray(r_trg_all[t0_:t1_])
     n_my_trg = my_trg.shape[0]
     rng = np.random.default_rng(7)
@@ -275,8 +277,7 @@ def main():
     # gather layout is contiguous by rank, so rows [0, n_src) are the real sources when src_chunk*world == n_src;
     # otherwise the tail ranks are short.  Keep it simple: require divisibility (sizes above are multiples of 32).
     def step_device():
-        if world > 1:
-            dist.all_gather_into_tensor(d_f_gather, d_f_mine)
+        allgather_strengths(d_f_gather, d_f_mine)  # ONE NCCL all-gather per step (no-op at world == 1)
         ctx.eval_device(skb.KERNEL_STOKESLET, d_f_gather.data_ptr(), d_u.data_ptr(), False, stream)
 
     def step_e2e():

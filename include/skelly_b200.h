@@ -12,10 +12,10 @@
  *                                        include/kernels.hpp:136-191  skb_ctx_* / skb_set_* / skb_eval
  *   kernels::FMM<Stk3DFMM>::operator()   include/kernels.hpp:78-122   same (positions cached per timestep,
  *                                                                      strengths shipped per matvec)
- *   FiberContainerFiniteDifference::flow src/core/fiber_container_finite_difference.cpp:172-214  skb_mv_*
- *   Periphery::flow                      src/core/periphery.cpp:55-79                             skb_mv_*
- *   BodyContainer::flow                  src/core/body_container.cpp:269-477                      skb_mv_*
- *   System::apply_matvec (flow part)     src/core/system.cpp:284-316                              skb_mv_apply
+ *   FiberContainerFiniteDifference::flow src/core/fiber_container_finite_difference.cpp:172-214  skb_flow_* (skelly_b200_flow.h)
+ *   Periphery::flow                      src/core/periphery.cpp:55-79                             skb_flow_* (skelly_b200_flow.h)
+ *   BodyContainer::flow                  src/core/body_container.cpp:269-477                      skb_flow_* (skelly_b200_flow.h)
+ *   System::apply_matvec (flow part)     src/core/system.cpp:284-316                              skb_flow_matvec (skelly_b200_flow.h)
  *
  * Conventions (identical to the reference):
  *   - all coordinates / strengths / velocities FP64, Eigen column-major 3 x n == AoS xyz: r[3*i + k];

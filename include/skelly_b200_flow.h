@@ -1,0 +1,79 @@
+/*
+ * skelly_b200_flow.h -- C ABI of the device-resident flow() layer: the three container flows that
+ * System::apply_matvec evaluates every GMRES iteration, and their fused sum.
+ *
+ *   reference (SkellySim)                                                       here
+ *   --------------------------------------------------------------------------  -----------------------
+ *   FiberContainerFiniteDifference::flow   fiber_container_finite_difference.cpp:172-214   skb_flow_fibers
+ *   Periphery::flow                        periphery.cpp:55-79                             skb_flow_periphery
+ *   BodyContainer::flow (spherical/ellipsoidal)  body_container.cpp:269-411,471-477        skb_flow_bodies
+ *   System::apply_matvec, hydrodynamic part      system.cpp:284-316                        skb_flow_matvec
+ *
+ * A skb_flow object holds the geometry of ONE timestep on the device (node positions, normals, quadrature
+ * weights, body centres); positions only change in System::step (system.cpp:486-489), so every GMRES
+ * iteration ships densities/forces only.  Layouts are the reference's: Eigen column-major 3 x n == AoS xyz.
+ * Velocities returned here are the reference's flow() return values, i.e. they INCLUDE the 1/eta of the
+ * evaluator wrappers (kernels.cpp:358,365).
+ */
+#ifndef SKELLY_B200_FLOW_H
+#define SKELLY_B200_FLOW_H
+
+#include "skelly_b200.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct skb_flow skb_flow;
+
+SKB_API int skb_flow_create(int device, skb_flow **out);
+SKB_API int skb_flow_destroy(skb_flow *fl);
+
+/* ---- geometry, once per timestep --------------------------------------------------------------------- */
+/* r_fib: 3 x N_f node positions of all fibers, concatenated in container order; n_nodes[f] nodes and
+ * length[f] per fiber (trapezoid weights 0.5 L weights_0 are formed on the device,
+ * fiber_container_finite_difference.cpp:185-193).  n_fibers == 0 is allowed (flow returns zeros, :178-179). */
+SKB_API int skb_flow_set_fibers(skb_flow *fl, const double *r_fib, const int *n_nodes, const double *length,
+                                int n_fibers);
+/* periphery quadrature nodes and (inward) normals, periphery.hpp node_pos_ / node_normal_ */
+SKB_API int skb_flow_set_periphery(skb_flow *fl, const double *node_pos, const double *node_normal, int64_t n_nodes);
+/* all body surface nodes / normals concatenated [spherical..., ellipsoidal...] (body_container.cpp:286-290),
+ * and the body centres (get_local_center_positions) */
+SKB_API int skb_flow_set_bodies(skb_flow *fl, const double *node_pos, const double *node_normal, int64_t n_nodes,
+                                const double *centers, int n_bodies);
+
+/* ---- the three flows at arbitrary targets (velocity_at_targets / listener path, system.cpp:330-384) ------
+ * Targets are cached on the device and re-uploaded only when they differ from the previous call's (the same
+ * full compare the reference's FMM functor does, kernels.hpp:81-83). */
+SKB_API int skb_flow_fibers(skb_flow *fl, const double *r_trg, int64_t n_trg, const double *fib_forces, double eta,
+                            int subtract_self, double *vel);
+SKB_API int skb_flow_periphery(skb_flow *fl, const double *r_trg, int64_t n_trg, const double *density, double eta,
+                               double *vel);
+/* densities: 3 x N_b body-node densities; forces_torques: 6 x n_bodies (net force then torque per body,
+ * body_container.cpp:128-135) */
+SKB_API int skb_flow_bodies(skb_flow *fl, const double *r_trg, int64_t n_trg, const double *densities,
+                            const double *forces_torques, double eta, double *vel);
+
+/* ---- fused matvec flow -------------------------------------------------------------------------------
+ * v_all over targets [fibers | periphery | bodies] (get_node_maps, system.cpp:234-241):
+ *   v_all  = fiber flow (all targets, self term subtracted)
+ *   v_fib, v_body += periphery flow   (shell sources never act on shell targets, system.cpp:301-315)
+ *   v_all += body flow
+ * Any class may be empty.  One H2D of the four strength arrays, one D2H of v_all; everything in between stays
+ * on the device. */
+SKB_API int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double *shell_density,
+                            const double *body_densities, const double *body_forces_torques, double eta,
+                            double *v_all);
+
+typedef struct skb_flow_stats {
+    double device_ms;   /* CUDA-event time of the last call, first launch to last kernel (copies excluded) */
+    double total_ms;    /* including H2D / D2H */
+    int64_t n_pairs;    /* source x target pairs evaluated by the pair kernels */
+    int32_t launches;
+} skb_flow_stats;
+SKB_API int skb_flow_last_stats(const skb_flow *fl, skb_flow_stats *out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

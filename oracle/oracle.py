@@ -182,7 +182,8 @@ def trapezoid_weights(n_nodes: int, length: float):
     """0.5 * L * weights_0 (fiber_container_finite_difference.cpp:186, fiber_finite_difference.cpp:545-548)."""
     w = np.full(n_nodes, 2.0)
     w[0] = w[-1] = 1.0
-    return 0.5 * length * w / (n_nodes - 1)
+    w /= (n_nodes - 1)          # weights_0 /= (n_nodes - 1)        fiber_finite_difference.cpp:548
+    return (0.5 * length) * w   # 0.5 * fib.length_ * weights_0     fiber_container_finite_difference.cpp:186
 
 
 def fiber_flow(r_trg, fiber_pos, fiber_n_nodes, fiber_lengths, fib_forces, eta, subtract_self=True):

@@ -30,6 +30,10 @@ class EvalStats(C.Structure):
                 ("grid_ctas", C.c_int32)]
 
 
+class FlowStats(C.Structure):
+    _fields_ = [("device_ms", C.c_double), ("total_ms", C.c_double), ("n_pairs", C.c_int64), ("launches", C.c_int32)]
+
+
 def library_path() -> str:
     return _LIB
 
@@ -79,6 +83,17 @@ def library() -> C.CDLL:
         "skb_launch_count": ([], C.c_int64),
         "skb_ctx_set_tuning": ([ctxp, C.c_int, C.c_int], C.c_int),
         "skb_measure_fp64_peak": ([ctxp, C.POINTER(C.c_double)], C.c_int),
+        # include/skelly_b200_flow.h
+        "skb_flow_create": ([C.c_int, C.POINTER(ctxp)], C.c_int),
+        "skb_flow_destroy": ([ctxp], C.c_int),
+        "skb_flow_set_fibers": ([ctxp, _dp, C.POINTER(C.c_int), _dp, C.c_int], C.c_int),
+        "skb_flow_set_periphery": ([ctxp, _dp, _dp, C.c_int64], C.c_int),
+        "skb_flow_set_bodies": ([ctxp, _dp, _dp, C.c_int64, _dp, C.c_int], C.c_int),
+        "skb_flow_fibers": ([ctxp, _dp, C.c_int64, _dp, C.c_double, C.c_int, _dp], C.c_int),
+        "skb_flow_periphery": ([ctxp, _dp, C.c_int64, _dp, C.c_double, _dp], C.c_int),
+        "skb_flow_bodies": ([ctxp, _dp, C.c_int64, _dp, _dp, C.c_double, _dp], C.c_int),
+        "skb_flow_matvec": ([ctxp, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
+        "skb_flow_last_stats": ([ctxp, C.POINTER(FlowStats)], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -244,3 +259,83 @@ class Context:
         v = C.c_double(0)
         _check(library().skb_measure_fp64_peak(self._h, C.byref(v)))
         return v.value
+
+
+class Flow:
+    """Device-resident flow() layer (include/skelly_b200_flow.h): FiberContainer / Periphery / BodyContainer flows
+    and the fused hydrodynamic part of System::apply_matvec."""
+
+    def __init__(self, device: int = 0):
+        self._h = C.c_void_p()
+        _check(library().skb_flow_create(int(device), C.byref(self._h)))
+        self.n_fib = self.n_shell = self.n_body = self.n_bodies = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            library().skb_flow_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_fibers(self, r_fib, n_nodes, lengths):
+        r_fib = _arr(r_fib, 3)
+        n_nodes = np.ascontiguousarray(n_nodes, dtype=np.int32)
+        lengths = np.ascontiguousarray(lengths, dtype=np.float64)
+        assert n_nodes.shape == lengths.shape and int(n_nodes.sum()) == r_fib.shape[0]
+        _check(library().skb_flow_set_fibers(self._h, _p(r_fib), n_nodes.ctypes.data_as(C.POINTER(C.c_int)),
+                                             _p(lengths), int(n_nodes.shape[0])))
+        self.n_fib = r_fib.shape[0]
+
+    def set_periphery(self, node_pos, node_normal):
+        node_pos, node_normal = _arr(node_pos, 3), _arr(node_normal, 3)
+        _check(library().skb_flow_set_periphery(self._h, _p(node_pos), _p(node_normal), node_pos.shape[0]))
+        self.n_shell = node_pos.shape[0]
+
+    def set_bodies(self, node_pos, node_normal, centers):
+        node_pos, node_normal, centers = _arr(node_pos, 3), _arr(node_normal, 3), _arr(centers, 3)
+        _check(library().skb_flow_set_bodies(self._h, _p(node_pos), _p(node_normal), node_pos.shape[0], _p(centers),
+                                             centers.shape[0]))
+        self.n_body, self.n_bodies = node_pos.shape[0], centers.shape[0]
+
+    def fiber_flow(self, r_trg, fib_forces, eta, subtract_self=True):
+        r_trg, fib_forces = _arr(r_trg, 3), _arr(fib_forces, 3)
+        vel = np.empty((r_trg.shape[0], 3))
+        _check(library().skb_flow_fibers(self._h, _p(r_trg), r_trg.shape[0], _p(fib_forces), float(eta),
+                                         int(bool(subtract_self)), _p(vel)))
+        return vel
+
+    def periphery_flow(self, r_trg, density, eta):
+        r_trg, density = _arr(r_trg, 3), _arr(density, 3)
+        vel = np.empty((r_trg.shape[0], 3))
+        _check(library().skb_flow_periphery(self._h, _p(r_trg), r_trg.shape[0], _p(density), float(eta), _p(vel)))
+        return vel
+
+    def body_flow(self, r_trg, densities, forces_torques, eta):
+        r_trg, densities = _arr(r_trg, 3), _arr(densities, 3)
+        ft = _arr(forces_torques, 6)
+        vel = np.empty((r_trg.shape[0], 3))
+        _check(library().skb_flow_bodies(self._h, _p(r_trg), r_trg.shape[0], _p(densities), _p(ft), float(eta),
+                                         _p(vel)))
+        return vel
+
+    def matvec(self, fib_forces, shell_density, body_densities, body_forces_torques, eta):
+        a, b, c = _arr(fib_forces, 3), _arr(shell_density, 3), _arr(body_densities, 3)
+        ft = _arr(body_forces_torques, 6)
+        v = np.empty((self.n_fib + self.n_shell + self.n_body, 3))
+        _check(library().skb_flow_matvec(self._h, _p(a), _p(b), _p(c), _p(ft), float(eta), _p(v)))
+        return v
+
+    def stats(self) -> dict:
+        s = FlowStats()
+        _check(library().skb_flow_last_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in FlowStats._fields_}

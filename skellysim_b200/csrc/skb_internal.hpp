@@ -5,6 +5,7 @@
 #include <cuda_runtime.h>
 #include <functional>
 #include <stddef.h>
+#include <vector>
 
 namespace skb {
 
@@ -41,6 +42,49 @@ int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const
                     const LaunchPlan &plan, cudaStream_t st);
 int launch_reduce(const double *d_partial, double *d_u, long long n_trg, int n_splits, double scale, int accumulate,
                   cudaStream_t st);
+
+enum StrengthMode { kRaw = 0, kNormalDensity = 1 };
+
+} // namespace skb
+
+// ---- context internals (shared by skb_runtime.cu and skb_matvec.cu) ----
+struct SourceSet {
+    long long n = -1; // -1 = never set
+    long long n_pad = 0;
+    bool has_normals = false;
+    skb::DevBuf r;       // padded positions
+    bool has_weights = false;
+    skb::DevBuf normals; // optional (double layer formed on device)
+    skb::DevBuf weights; // optional per-source quadrature weight folded into the Stokeslet strengths
+    skb::DevBuf f_raw;   // strengths as shipped by the caller (3 or 9 per source; all-gather landing zone)
+    skb::DevBuf f_packed;
+};
+
+struct DeviceState {
+    skb::DeviceInfo info;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    long long trg_begin = 0, n_trg = 0; // this device's block of the global target list
+    skb::DevBuf r_trg, u, partial, scratch;
+    SourceSet src[2];
+};
+
+struct skb_ctx {
+    std::vector<DeviceState> devs;
+    long long n_trg = -1;
+    int force_T = 0, force_S = 0;
+    skb_eval_stats stats{};
+    bool kernel_events_pending = false; // device-pointer path: kernel_ms is read back lazily
+    void *nccl = nullptr; // NcclGroup*, multi-device contexts only
+};
+
+
+namespace skb {
+// pack -> pair sums -> split reduction for one device; strengths already resident at d_f_raw.
+// result (=|+=) scale_mul * [1 | -3]/(8 pi) * sum.
+int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, const double *d_f_raw, double two_eta,
+                   double *d_u_out, int accumulate, cudaStream_t st, bool record_events, int *launches,
+                   LaunchPlan *plan_out, double scale_mul);
 
 // NCCL is bound at run time (dlopen "libnccl.so.2"): a single-GPU user never needs it, and a host that
 // already loaded NCCL (PyTorch) shares that copy instead of getting a second one.

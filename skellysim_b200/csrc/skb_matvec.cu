@@ -1,1 +1,474 @@
-// placeholder: flow()/matvec layer (filled in next)
+// skb_matvec.cu -- device-resident flow() layer (include/skelly_b200_flow.h): FiberContainer / Periphery /
+// BodyContainer flows of SkellySim and their fused sum, the hydrodynamic part of System::apply_matvec
+// (src/core/system.cpp:284-316).  Built on the pair-kernel contexts of skb_runtime.cu; everything between the
+// upload of the strengths and the download of the velocities stays on the device.
+#include "aux_kernels.cuh"
+#include "skb_internal.hpp"
+#include "../../include/skelly_b200_flow.h"
+
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+using namespace skb;
+
+#define CUDA_TRY(expr)                                                                                                \
+    do {                                                                                                              \
+        cudaError_t _e = (expr);                                                                                      \
+        if (_e != cudaSuccess)                                                                                        \
+            return set_error(SKB_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                      \
+                             cudaGetErrorString(_e));                                                                 \
+    } while (0)
+#define SKB_TRY(expr)                                                                                                 \
+    do {                                                                                                              \
+        int _rc = (expr);                                                                                             \
+        if (_rc != SKB_OK)                                                                                            \
+            return _rc;                                                                                               \
+    } while (0)
+
+namespace {
+// reference defaults of the regularised helpers (include/kernels.hpp:38-46): reg = 5e-3, eps = 1e-5
+constexpr double kReg = 5e-3;
+constexpr double kEps = 1e-5;
+
+struct TargetCache {
+    std::vector<double> host;
+    bool valid = false;
+    bool same(const double *r, long long n) const {
+        return valid && (long long)host.size() == 3 * n && (n == 0 || std::memcmp(host.data(), r, (size_t)n * 24) == 0);
+    }
+    void store(const double *r, long long n) {
+        host.assign(r, r + 3 * n);
+        valid = true;
+    }
+};
+} // namespace
+
+struct skb_flow {
+    int dev = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr, evt0 = nullptr, evt1 = nullptr;
+    // geometry
+    long long n_fib = 0, n_shell = 0, n_body = 0;
+    int n_fibers = 0, n_bodies = 0, max_fiber_nodes = 0;
+    DevBuf fiber_offset, fiber_length, r_fib, r_shell, r_body, centers;
+    std::vector<double> h_r_fib, h_r_shell, h_r_body; // host copies to assemble the matvec target lists
+    // evaluators: [0] arbitrary targets, [1] matvec target lists
+    skb_ctx *fib[2] = {nullptr, nullptr}, *shell[2] = {nullptr, nullptr}, *body[2] = {nullptr, nullptr};
+    TargetCache tc_fib, tc_shell, tc_body;
+    bool mv_dirty = true;
+    // staging
+    DevBuf in_fib, in_shell, in_body, in_force, in_torque, vel, tmp;
+    skb_flow_stats stats{};
+    int launches = 0;
+    long long pairs = 0;
+};
+
+static int ensure_ctx(skb_flow *fl, skb_ctx **slot) {
+    if (*slot)
+        return SKB_OK;
+    return skb_ctx_create_on(&fl->dev, 1, slot);
+}
+
+// ---- device-side flows: ctx already has its targets and sources ------------------------------------------------
+static int fibers_dev(skb_flow *fl, skb_ctx *ctx, const double *d_forces, double eta, int subtract_self,
+                      double *d_vel, int accumulate) {
+    DeviceState &d = ctx->devs[0];
+    if (d.n_trg == 0)
+        return SKB_OK;
+    if (fl->n_fibers == 0) { // fiber_container_finite_difference.cpp:178-179
+        if (!accumulate)
+            CUDA_TRY(cudaMemsetAsync(d_vel, 0, (size_t)d.n_trg * 24, fl->stream));
+        return SKB_OK;
+    }
+    // weighted forces -> Stokeslet all-to-all, / eta  (fcfd.cpp:185-199, kernels.cpp:365)
+    SKB_TRY(eval_on_device(ctx, d, SKB_STOKESLET, kRaw, d_forces, 0.0, d_vel, accumulate, fl->stream, false,
+                           &fl->launches, nullptr, 1.0 / eta));
+    fl->pairs += fl->n_fib * d.n_trg;
+    if (subtract_self) { // fcfd.cpp:203-210; the first N_f targets are the fiber nodes themselves
+        if (d.n_trg < fl->n_fib)
+            return set_error(SKB_ERR_INVALID, "fiber flow with subtract_self needs the fiber nodes as the first "
+                                              "%lld targets (n_trg = %lld)", fl->n_fib, d.n_trg);
+        const size_t smem = (size_t)fl->max_fiber_nodes * 6 * sizeof(double);
+        fiber_self_subtract_kernel<<<fl->n_fibers, 128, smem, fl->stream>>>(
+            (const double *)fl->r_fib.ptr, (const double *)d.src[SKB_STOKESLET].f_packed.ptr,
+            (const long long *)fl->fiber_offset.ptr, 1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps, d_vel);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        fl->launches += 1;
+    }
+    return SKB_OK;
+}
+
+static int periphery_dev(skb_flow *fl, skb_ctx *ctx, const double *d_density, double eta, double *d_vel,
+                         int accumulate) {
+    DeviceState &d = ctx->devs[0];
+    if (d.n_trg == 0)
+        return SKB_OK;
+    if (fl->n_shell == 0) { // periphery.cpp:57-58
+        if (!accumulate)
+            CUDA_TRY(cudaMemsetAsync(d_vel, 0, (size_t)d.n_trg * 24, fl->stream));
+        return SKB_OK;
+    }
+    // f_dl = 2 eta n (x) rho formed on the device, stresslet, / eta  (periphery.cpp:68-74, kernels.cpp:358)
+    SKB_TRY(eval_on_device(ctx, d, SKB_STRESSLET, kNormalDensity, d_density, 2.0 * eta, d_vel, accumulate, fl->stream,
+                           false, &fl->launches, nullptr, 1.0 / eta));
+    fl->pairs += fl->n_shell * d.n_trg;
+    return SKB_OK;
+}
+
+static int bodies_dev(skb_flow *fl, skb_ctx *ctx, const double *d_density, const double *d_force,
+                      const double *d_torque, double eta, double *d_vel, int accumulate) {
+    DeviceState &d = ctx->devs[0];
+    if (d.n_trg == 0)
+        return SKB_OK;
+    if (fl->n_bodies == 0) { // body_container.cpp:273-276
+        if (!accumulate)
+            CUDA_TRY(cudaMemsetAsync(d_vel, 0, (size_t)d.n_trg * 24, fl->stream));
+        return SKB_OK;
+    }
+    // stresslet of the surface nodes (body_container.cpp:296-305)
+    SKB_TRY(eval_on_device(ctx, d, SKB_STRESSLET, kNormalDensity, d_density, 2.0 * eta, d_vel, accumulate, fl->stream,
+                           false, &fl->launches, nullptr, 1.0 / eta));
+    // Stokeslet of the net forces at the centres (:327)
+    SKB_TRY(eval_on_device(ctx, d, SKB_STOKESLET, kRaw, d_force, 0.0, d_vel, 1, fl->stream, false, &fl->launches,
+                           nullptr, 1.0 / eta));
+    // rotlet of the net torques at the centres (:335, kernels.cpp:206-242)
+    const int bs = 128;
+    rotlet_add_kernel<<<(unsigned)((d.n_trg + bs - 1) / bs), bs, 0, fl->stream>>>(
+        (const double *)fl->centers.ptr, d_torque, fl->n_bodies, (const double *)d.r_trg.ptr, d.n_trg,
+        1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps * kEps, d_vel);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    fl->launches += 1;
+    fl->pairs += (fl->n_body + 2 * (long long)fl->n_bodies) * d.n_trg;
+    return SKB_OK;
+}
+
+static int upload(skb_flow *fl, DevBuf &buf, const double *h, size_t n_doubles) {
+    if (n_doubles == 0)
+        return SKB_OK;
+    SKB_TRY(buf.ensure(n_doubles * 8));
+    CUDA_TRY(cudaMemcpyAsync(buf.ptr, h, n_doubles * 8, cudaMemcpyHostToDevice, fl->stream));
+    return SKB_OK;
+}
+
+static int set_targets_cached(skb_ctx *ctx, TargetCache &tc, const double *r_trg, long long n_trg) {
+    if (tc.same(r_trg, n_trg) && ctx->n_trg == n_trg)
+        return SKB_OK;
+    SKB_TRY(skb_set_targets(ctx, r_trg, n_trg));
+    tc.store(r_trg, n_trg);
+    return SKB_OK;
+}
+
+static void split_forces_torques(const double *ft, int n_bodies, std::vector<double> &f, std::vector<double> &t) {
+    f.resize(3 * (size_t)n_bodies);
+    t.resize(3 * (size_t)n_bodies);
+    for (int b = 0; b < n_bodies; ++b)
+        for (int k = 0; k < 3; ++k) {
+            f[3 * b + k] = ft[6 * b + k];     // forces_torques.block(0,0,3,n)  body_container.cpp:134
+            t[3 * b + k] = ft[6 * b + 3 + k]; // forces_torques.block(3,0,3,n)
+        }
+}
+
+static void begin_stats(skb_flow *fl) {
+    fl->launches = 0;
+    fl->pairs = 0;
+}
+static int finish_stats(skb_flow *fl) {
+    CUDA_TRY(cudaStreamSynchronize(fl->stream));
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, fl->ev0, fl->ev1);
+    cudaEventElapsedTime(&b, fl->evt0, fl->evt1);
+    fl->stats.device_ms = a;
+    fl->stats.total_ms = b;
+    fl->stats.n_pairs = fl->pairs;
+    fl->stats.launches = fl->launches;
+    return SKB_OK;
+}
+
+extern "C" {
+
+int skb_flow_create(int device, skb_flow **out) {
+    if (!out)
+        return set_error(SKB_ERR_INVALID, "skb_flow_create: out == NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return set_error(SKB_ERR_NO_DEVICE, "no CUDA device available; this library has no CPU fallback");
+    if (device < 0 || device >= n_dev)
+        return set_error(SKB_ERR_INVALID, "skb_flow_create: device %d out of range (%d visible)", device, n_dev);
+    std::unique_ptr<skb_flow> fl(new skb_flow);
+    fl->dev = device;
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&fl->stream, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreate(&fl->ev0));
+    CUDA_TRY(cudaEventCreate(&fl->ev1));
+    CUDA_TRY(cudaEventCreate(&fl->evt0));
+    CUDA_TRY(cudaEventCreate(&fl->evt1));
+    for (int k = 0; k < 2; ++k) {
+        SKB_TRY(ensure_ctx(fl.get(), &fl->fib[k]));
+        SKB_TRY(ensure_ctx(fl.get(), &fl->shell[k]));
+        SKB_TRY(ensure_ctx(fl.get(), &fl->body[k]));
+    }
+    // empty classes until set_* is called
+    for (int k = 0; k < 2; ++k) {
+        SKB_TRY(skb_set_sources(fl->fib[k], SKB_STOKESLET, nullptr, 0));
+        SKB_TRY(skb_set_sources(fl->shell[k], SKB_STRESSLET, nullptr, 0));
+        SKB_TRY(skb_set_sources(fl->body[k], SKB_STRESSLET, nullptr, 0));
+        SKB_TRY(skb_set_sources(fl->body[k], SKB_STOKESLET, nullptr, 0));
+    }
+    *out = fl.release();
+    return SKB_OK;
+}
+
+int skb_flow_destroy(skb_flow *fl) {
+    if (!fl)
+        return SKB_OK;
+    cudaSetDevice(fl->dev);
+    if (fl->stream)
+        cudaStreamSynchronize(fl->stream);
+    for (int k = 0; k < 2; ++k) {
+        skb_ctx_destroy(fl->fib[k]);
+        skb_ctx_destroy(fl->shell[k]);
+        skb_ctx_destroy(fl->body[k]);
+    }
+    DevBuf *bufs[] = {&fl->fiber_offset, &fl->fiber_length, &fl->r_fib, &fl->r_shell, &fl->r_body, &fl->centers,
+                      &fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel, &fl->tmp};
+    for (DevBuf *b : bufs)
+        b->release();
+    if (fl->ev0) cudaEventDestroy(fl->ev0);
+    if (fl->ev1) cudaEventDestroy(fl->ev1);
+    if (fl->evt0) cudaEventDestroy(fl->evt0);
+    if (fl->evt1) cudaEventDestroy(fl->evt1);
+    if (fl->stream) cudaStreamDestroy(fl->stream);
+    delete fl;
+    return SKB_OK;
+}
+
+int skb_flow_set_fibers(skb_flow *fl, const double *r_fib, const int *n_nodes, const double *length, int n_fibers) {
+    if (!fl || n_fibers < 0 || (n_fibers > 0 && (!r_fib || !n_nodes || !length)))
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_fibers: bad arguments");
+    std::vector<long long> off((size_t)n_fibers + 1, 0);
+    int max_n = 0;
+    for (int f = 0; f < n_fibers; ++f) {
+        if (n_nodes[f] < 2)
+            return set_error(SKB_ERR_INVALID, "fiber %d has %d nodes (need >= 2)", f, n_nodes[f]);
+        off[f + 1] = off[f] + n_nodes[f];
+        max_n = std::max(max_n, n_nodes[f]);
+    }
+    if ((size_t)max_n * 48 > 200 * 1024)
+        return set_error(SKB_ERR_INVALID, "fiber with %d nodes exceeds the shared-memory self-term kernel", max_n);
+    fl->n_fibers = n_fibers;
+    fl->n_fib = off[n_fibers];
+    fl->max_fiber_nodes = max_n;
+    fl->h_r_fib.assign(r_fib, r_fib + 3 * fl->n_fib);
+    fl->mv_dirty = true;
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    for (int k = 0; k < 2; ++k)
+        SKB_TRY(skb_set_sources(fl->fib[k], SKB_STOKESLET, r_fib, fl->n_fib));
+    if (n_fibers == 0)
+        return SKB_OK;
+    SKB_TRY(fl->fiber_offset.ensure(off.size() * 8));
+    SKB_TRY(fl->fiber_length.ensure((size_t)n_fibers * 8));
+    SKB_TRY(fl->r_fib.ensure((size_t)fl->n_fib * 24));
+    CUDA_TRY(cudaMemcpyAsync(fl->fiber_offset.ptr, off.data(), off.size() * 8, cudaMemcpyHostToDevice, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(fl->fiber_length.ptr, length, (size_t)n_fibers * 8, cudaMemcpyHostToDevice, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(fl->r_fib.ptr, r_fib, (size_t)fl->n_fib * 24, cudaMemcpyHostToDevice, fl->stream));
+    if (max_n * 48 > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(fiber_self_subtract_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      max_n * 48));
+    // trapezoid weights straight into both Stokeslet source sets
+    for (int k = 0; k < 2; ++k) {
+        SourceSet &s = fl->fib[k]->devs[0].src[SKB_STOKESLET];
+        SKB_TRY(s.weights.ensure((size_t)fl->n_fib * 8));
+        fiber_weights_kernel<<<n_fibers, 64, 0, fl->stream>>>((const long long *)fl->fiber_offset.ptr,
+                                                              (const double *)fl->fiber_length.ptr, n_fibers,
+                                                              (double *)s.weights.ptr);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        s.has_weights = true;
+    }
+    CUDA_TRY(cudaStreamSynchronize(fl->stream));
+    return SKB_OK;
+}
+
+int skb_flow_set_periphery(skb_flow *fl, const double *node_pos, const double *node_normal, int64_t n_nodes) {
+    if (!fl || n_nodes < 0 || (n_nodes > 0 && (!node_pos || !node_normal)))
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_periphery: bad arguments");
+    fl->n_shell = n_nodes;
+    fl->h_r_shell.assign(node_pos, node_pos + 3 * n_nodes);
+    fl->mv_dirty = true;
+    for (int k = 0; k < 2; ++k) {
+        SKB_TRY(skb_set_sources(fl->shell[k], SKB_STRESSLET, node_pos, n_nodes));
+        SKB_TRY(skb_set_source_normals(fl->shell[k], node_normal, n_nodes));
+    }
+    return SKB_OK;
+}
+
+int skb_flow_set_bodies(skb_flow *fl, const double *node_pos, const double *node_normal, int64_t n_nodes,
+                        const double *centers, int n_bodies) {
+    if (!fl || n_nodes < 0 || n_bodies < 0 || (n_nodes > 0 && (!node_pos || !node_normal)) ||
+        (n_bodies > 0 && !centers) || (n_bodies == 0 && n_nodes > 0))
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_bodies: bad arguments");
+    fl->n_body = n_nodes;
+    fl->n_bodies = n_bodies;
+    fl->h_r_body.assign(node_pos, node_pos + 3 * n_nodes);
+    fl->mv_dirty = true;
+    for (int k = 0; k < 2; ++k) {
+        SKB_TRY(skb_set_sources(fl->body[k], SKB_STRESSLET, node_pos, n_nodes));
+        SKB_TRY(skb_set_source_normals(fl->body[k], node_normal, n_nodes));
+        SKB_TRY(skb_set_sources(fl->body[k], SKB_STOKESLET, centers, n_bodies));
+    }
+    if (n_bodies > 0) {
+        CUDA_TRY(cudaSetDevice(fl->dev));
+        SKB_TRY(fl->centers.ensure((size_t)n_bodies * 24));
+        CUDA_TRY(cudaMemcpyAsync(fl->centers.ptr, centers, (size_t)n_bodies * 24, cudaMemcpyHostToDevice, fl->stream));
+        CUDA_TRY(cudaStreamSynchronize(fl->stream));
+    }
+    return SKB_OK;
+}
+
+int skb_flow_fibers(skb_flow *fl, const double *r_trg, int64_t n_trg, const double *fib_forces, double eta,
+                    int subtract_self, double *vel) {
+    if (!fl || n_trg < 0 || (n_trg > 0 && (!r_trg || !vel)) || (fl->n_fib > 0 && !fib_forces) || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_flow_fibers: bad arguments");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    begin_stats(fl);
+    SKB_TRY(set_targets_cached(fl->fib[0], fl->tc_fib, r_trg, n_trg));
+    if (n_trg == 0)
+        return SKB_OK;
+    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
+    SKB_TRY(upload(fl, fl->in_fib, fib_forces, (size_t)fl->n_fib * 3));
+    SKB_TRY(fl->vel.ensure((size_t)n_trg * 24));
+    CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    SKB_TRY(fibers_dev(fl, fl->fib[0], (const double *)fl->in_fib.ptr, eta, subtract_self, (double *)fl->vel.ptr, 0));
+    CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(vel, fl->vel.ptr, (size_t)n_trg * 24, cudaMemcpyDeviceToHost, fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+    return finish_stats(fl);
+}
+
+int skb_flow_periphery(skb_flow *fl, const double *r_trg, int64_t n_trg, const double *density, double eta,
+                       double *vel) {
+    if (!fl || n_trg < 0 || (n_trg > 0 && (!r_trg || !vel)) || (fl->n_shell > 0 && !density) || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_flow_periphery: bad arguments");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    begin_stats(fl);
+    SKB_TRY(set_targets_cached(fl->shell[0], fl->tc_shell, r_trg, n_trg));
+    if (n_trg == 0)
+        return SKB_OK;
+    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
+    SKB_TRY(upload(fl, fl->in_shell, density, (size_t)fl->n_shell * 3));
+    SKB_TRY(fl->vel.ensure((size_t)n_trg * 24));
+    CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    SKB_TRY(periphery_dev(fl, fl->shell[0], (const double *)fl->in_shell.ptr, eta, (double *)fl->vel.ptr, 0));
+    CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(vel, fl->vel.ptr, (size_t)n_trg * 24, cudaMemcpyDeviceToHost, fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+    return finish_stats(fl);
+}
+
+int skb_flow_bodies(skb_flow *fl, const double *r_trg, int64_t n_trg, const double *densities,
+                    const double *forces_torques, double eta, double *vel) {
+    if (!fl || n_trg < 0 || (n_trg > 0 && (!r_trg || !vel)) || (fl->n_body > 0 && !densities) ||
+        (fl->n_bodies > 0 && !forces_torques) || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_flow_bodies: bad arguments");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    begin_stats(fl);
+    SKB_TRY(set_targets_cached(fl->body[0], fl->tc_body, r_trg, n_trg));
+    if (n_trg == 0)
+        return SKB_OK;
+    std::vector<double> f, t;
+    split_forces_torques(forces_torques, fl->n_bodies, f, t);
+    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
+    SKB_TRY(upload(fl, fl->in_body, densities, (size_t)fl->n_body * 3));
+    SKB_TRY(upload(fl, fl->in_force, f.data(), f.size()));
+    SKB_TRY(upload(fl, fl->in_torque, t.data(), t.size()));
+    SKB_TRY(fl->vel.ensure((size_t)n_trg * 24));
+    CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    SKB_TRY(bodies_dev(fl, fl->body[0], (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
+                       (const double *)fl->in_torque.ptr, eta, (double *)fl->vel.ptr, 0));
+    CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(vel, fl->vel.ptr, (size_t)n_trg * 24, cudaMemcpyDeviceToHost, fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+    CUDA_TRY(cudaStreamSynchronize(fl->stream)); // f, t are stack-owned staging
+    return finish_stats(fl);
+}
+
+int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double *shell_density, const double *body_densities,
+                    const double *body_forces_torques, double eta, double *v_all) {
+    if (!fl || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_flow_matvec: bad arguments");
+    const long long nf = fl->n_fib, ns = fl->n_shell, nb = fl->n_body, n_all = nf + ns + nb;
+    if ((nf > 0 && !fib_forces) || (ns > 0 && !shell_density) || (nb > 0 && !body_densities) ||
+        (fl->n_bodies > 0 && !body_forces_torques) || (n_all > 0 && !v_all))
+        return set_error(SKB_ERR_INVALID, "skb_flow_matvec: NULL input for a non-empty class");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    begin_stats(fl);
+    if (n_all == 0)
+        return SKB_OK;
+    if (fl->mv_dirty) {
+        // target lists of apply_matvec: r_all = [fibers | shell | bodies] (system.cpp:284-291),
+        // r_fibbody = [fibers | bodies] (system.cpp:301-303)
+        std::vector<double> r_all((size_t)n_all * 3), r_fb((size_t)(nf + nb) * 3);
+        std::copy(fl->h_r_fib.begin(), fl->h_r_fib.end(), r_all.begin());
+        std::copy(fl->h_r_shell.begin(), fl->h_r_shell.end(), r_all.begin() + 3 * nf);
+        std::copy(fl->h_r_body.begin(), fl->h_r_body.end(), r_all.begin() + 3 * (nf + ns));
+        std::copy(fl->h_r_fib.begin(), fl->h_r_fib.end(), r_fb.begin());
+        std::copy(fl->h_r_body.begin(), fl->h_r_body.end(), r_fb.begin() + 3 * nf);
+        SKB_TRY(skb_set_targets(fl->fib[1], r_all.data(), n_all));
+        SKB_TRY(skb_set_targets(fl->body[1], r_all.data(), n_all));
+        SKB_TRY(skb_set_targets(fl->shell[1], r_fb.data(), nf + nb));
+        fl->mv_dirty = false;
+    }
+    std::vector<double> f, t;
+    if (fl->n_bodies > 0)
+        split_forces_torques(body_forces_torques, fl->n_bodies, f, t);
+    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
+    SKB_TRY(upload(fl, fl->in_fib, fib_forces, (size_t)nf * 3));
+    SKB_TRY(upload(fl, fl->in_shell, shell_density, (size_t)ns * 3));
+    SKB_TRY(upload(fl, fl->in_body, body_densities, (size_t)nb * 3));
+    SKB_TRY(upload(fl, fl->in_force, f.data(), f.size()));
+    SKB_TRY(upload(fl, fl->in_torque, t.data(), t.size()));
+    SKB_TRY(fl->vel.ensure((size_t)n_all * 24));
+    SKB_TRY(fl->tmp.ensure((size_t)(nf + nb) * 24 + 8));
+    double *d_v = (double *)fl->vel.ptr, *d_tmp = (double *)fl->tmp.ptr;
+    CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    // v_all = fc.flow(r_all, fw, eta)                                  system.cpp:299
+    SKB_TRY(fibers_dev(fl, fl->fib[1], (const double *)fl->in_fib.ptr, eta, 1, d_v, 0));
+    // v_fibers, v_bodies += shell.flow(r_fibbody, x_shell, eta)         system.cpp:304,313-315
+    if (ns > 0 && nf + nb > 0) {
+        SKB_TRY(periphery_dev(fl, fl->shell[1], (const double *)fl->in_shell.ptr, eta, d_tmp, 0));
+        const int bs = 256;
+        if (nf > 0) {
+            add_inplace_kernel<<<(unsigned)((3 * nf + bs - 1) / bs), bs, 0, fl->stream>>>(d_v, d_tmp, 3 * nf);
+            count_launch(1);
+            fl->launches += 1;
+        }
+        if (nb > 0) {
+            add_inplace_kernel<<<(unsigned)((3 * nb + bs - 1) / bs), bs, 0, fl->stream>>>(d_v + 3 * (nf + ns),
+                                                                                         d_tmp + 3 * nf, 3 * nb);
+            count_launch(1);
+            fl->launches += 1;
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    // v_all += bc.flow(r_all, x_bodies, body_link_conditions, eta)     system.cpp:316
+    SKB_TRY(bodies_dev(fl, fl->body[1], (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
+                       (const double *)fl->in_torque.ptr, eta, d_v, 1));
+    CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(v_all, d_v, (size_t)n_all * 24, cudaMemcpyDeviceToHost, fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+    return finish_stats(fl);
+}
+
+int skb_flow_last_stats(const skb_flow *fl, skb_flow_stats *out) {
+    if (!fl || !out)
+        return set_error(SKB_ERR_INVALID, "skb_flow_last_stats: NULL");
+    *out = fl->stats;
+    return SKB_OK;
+}
+
+} // extern "C"

@@ -239,34 +239,6 @@ using namespace skb;
 // ------------------------------------------------------------------------------------------------
 // context
 // ------------------------------------------------------------------------------------------------
-struct SourceSet {
-    long long n = -1; // -1 = never set
-    long long n_pad = 0;
-    bool has_normals = false;
-    DevBuf r;       // padded positions
-    DevBuf normals; // optional (double layer formed on device)
-    DevBuf f_raw;   // strengths as shipped by the caller (3 or 9 per source; all-gather landing zone)
-    DevBuf f_packed;
-};
-
-struct DeviceState {
-    DeviceInfo info;
-    cudaStream_t stream = nullptr;
-    cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
-    long long trg_begin = 0, n_trg = 0; // this device's block of the global target list
-    DevBuf r_trg, u, partial, scratch;
-    SourceSet src[2];
-};
-
-struct skb_ctx {
-    std::vector<DeviceState> devs;
-    long long n_trg = -1;
-    int force_T = 0, force_S = 0;
-    skb_eval_stats stats{};
-    bool kernel_events_pending = false; // device-pointer path: kernel_ms is read back lazily
-    void *nccl = nullptr; // NcclGroup*, multi-device contexts only
-};
-
 static int check_kind(int kind) {
     if (kind != SKB_STOKESLET && kind != SKB_STRESSLET)
         return set_error(SKB_ERR_INVALID, "unknown kernel kind %d", kind);
@@ -348,6 +320,7 @@ int skb_ctx_destroy(skb_ctx *ctx) {
         for (auto &s : d.src) {
             s.r.release();
             s.normals.release();
+            s.weights.release();
             s.f_raw.release();
             s.f_packed.release();
         }
@@ -461,6 +434,7 @@ static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long lo
         s.n = n_src;
         s.n_pad = n_pad;
         s.has_normals = false;
+        s.has_weights = false;
         if (n_src == 0)
             continue;
         CUDA_TRY(cudaSetDevice(d.info.dev));
@@ -491,12 +465,12 @@ static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long lo
 // ------------------------------------------------------------------------------------------------
 // evaluation
 // ------------------------------------------------------------------------------------------------
-enum StrengthMode { kRaw = 0, kNormalDensity = 1 };
 
 // device-side part for one device: pack -> pair kernel -> reduce into d_u_out.  f_raw already resident.
-static int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, const double *d_f_raw,
-                          double two_eta, double *d_u_out, int accumulate, cudaStream_t st, bool record_events,
-                          int *launches, LaunchPlan *plan_out) {
+namespace skb {
+int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, const double *d_f_raw, double two_eta,
+                   double *d_u_out, int accumulate, cudaStream_t st, bool record_events, int *launches,
+                   LaunchPlan *plan_out, double scale_mul) {
     SourceSet &s = d.src[kind];
     const int bs = 256;
     if (d.n_trg == 0)
@@ -508,8 +482,8 @@ static int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode m
     }
     // 1. strengths -> packed, padded layout
     if (kind == SKB_STOKESLET) {
-        pack_sl_kernel<<<(unsigned)((s.n_pad * 3 + bs - 1) / bs), bs, 0, st>>>(d_f_raw, nullptr,
-                                                                                (double *)s.f_packed.ptr, s.n, s.n_pad);
+        pack_sl_kernel<<<(unsigned)((s.n_pad * 3 + bs - 1) / bs), bs, 0, st>>>(
+            d_f_raw, s.has_weights ? (const double *)s.weights.ptr : nullptr, (double *)s.f_packed.ptr, s.n, s.n_pad);
     } else if (mode == kRaw) {
         pack_dl9_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(d_f_raw, (double *)s.f_packed.ptr, s.n,
                                                                              s.n_pad);
@@ -529,7 +503,7 @@ static int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode m
     if (record_events)
         CUDA_TRY(cudaEventRecord(d.ev_k1, st));
     // 3. combine splits, scale: 1/(8 pi) (kernels.cu:59) or -3/(8 pi) (kernels.cu:26,51)
-    const double scale = (kind == SKB_STOKESLET ? 1.0 : -3.0) / (8.0 * M_PI);
+    const double scale = scale_mul * (kind == SKB_STOKESLET ? 1.0 : -3.0) / (8.0 * M_PI);
     SKB_TRY(launch_reduce((const double *)d.partial.ptr, d_u_out, d.n_trg, plan.n_splits, scale, accumulate, st));
     if (launches)
         *launches += 3;
@@ -537,6 +511,7 @@ static int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode m
         *plan_out = plan;
     return SKB_OK;
 }
+} // namespace skb
 
 // host-pointer evaluation over all devices of the context
 static int eval_host(skb_ctx *ctx, int kind, StrengthMode mode, const double *f_src, double eta, double *u_trg,
@@ -592,7 +567,7 @@ static int eval_host(skb_ctx *ctx, int kind, StrengthMode mode, const double *f_
             CUDA_TRY(cudaMemcpyAsync(d.u.ptr, u_trg + 3 * d.trg_begin, (size_t)d.n_trg * 24, cudaMemcpyHostToDevice,
                                      d.stream));
         SKB_TRY(eval_on_device(ctx, d, kind, mode, (const double *)d.src[kind].f_raw.ptr, 2.0 * eta,
-                               (double *)d.u.ptr, accumulate, d.stream, true, &launches, g == 0 ? &plan : nullptr));
+                               (double *)d.u.ptr, accumulate, d.stream, true, &launches, g == 0 ? &plan : nullptr, 1.0));
         CUDA_TRY(cudaMemcpyAsync(u_trg + 3 * d.trg_begin, d.u.ptr, (size_t)d.n_trg * 24, cudaMemcpyDeviceToHost,
                                  d.stream));
         CUDA_TRY(cudaEventRecord(d.ev_t1, d.stream));
@@ -737,7 +712,7 @@ int skb_eval_device(skb_ctx *ctx, int kind, const double *d_f_src, double *d_u_t
     cudaStream_t st = (cudaStream_t)stream; // verbatim: 0 is CUDA's legacy default stream
     int launches = 0;
     LaunchPlan plan{};
-    SKB_TRY(eval_on_device(ctx, d, kind, kRaw, d_f_src, 0.0, d_u_trg, accumulate, st, true, &launches, &plan));
+    SKB_TRY(eval_on_device(ctx, d, kind, kRaw, d_f_src, 0.0, d_u_trg, accumulate, st, true, &launches, &plan, 1.0));
     ctx->kernel_events_pending = d.src[kind].n > 0 && d.n_trg > 0;
     ctx->stats.kernel_ms = 0;
     ctx->stats.total_ms = 0;

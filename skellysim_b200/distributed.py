@@ -1,0 +1,50 @@
+"""One-rank-per-GPU sharding of the pair-kernel path (used by bench.py; CPU-testable with gloo).
+
+Targets are independent (each u_t is a private sum over all sources; the reference already exploits this across
+OpenMP threads, kernels.cpp:58-65), so targets AND sources are block-partitioned over ranks and the only exchange
+is ONE all-gather of the source strengths per evaluation.  Positions are all-gathered once per
+timestep.  This module only moves strengths between ranks; it computes no velocities."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+
+def block_range(n: int, world: int, rank: int):
+    """Contiguous block [b, e) of rank `rank` when n items are split into `world` blocks of ceil(n/world)."""
+    chunk = -(-n // world) if world > 0 else n
+    b = min(n, rank * chunk)
+    e = min(n, (rank + 1) * chunk)
+    return b, e
+
+
+@dataclass
+class RankPartition:
+    n_src: int
+    n_trg: int
+    world: int
+    rank: int
+
+    @property
+    def src_chunk(self) -> int:  # all-gather slot size (equal on every rank)
+        return -(-self.n_src // self.world)
+
+    @property
+    def src_range(self):
+        return block_range(self.n_src, self.world, self.rank)
+
+    @property
+    def trg_range(self):
+        return block_range(self.n_trg, self.world, self.rank)
+
+    @property
+    def gathered_rows(self) -> int:
+        return self.src_chunk * self.world
+
+
+def allgather_strengths(gathered, mine, group=None):
+    """In-place all-gather of this rank's strength slot into `gathered` ((world*src_chunk, d) tensor; `mine` must be
+    the view gathered[rank*src_chunk:(rank+1)*src_chunk]).  NCCL on GPUs, gloo on CPU."""
+    import torch.distributed as dist
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_gather_into_tensor(gathered, mine, group=group)
+    return gathered

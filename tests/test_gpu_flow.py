@@ -1,0 +1,138 @@
+"""GPU parity tests of the flow() layer (include/skelly_b200_flow.h) against the oracle's restatement of
+FiberContainerFiniteDifference::flow, Periphery::flow, BodyContainer::flow and the hydrodynamic part of
+System::apply_matvec.  Tolerance <= 1e-12 relative (max-norm and l2)."""
+import numpy as np
+import pytest
+
+import oracle as orc
+import skellysim_b200 as skb
+from conftest import rel_l2, rel_max
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _check(u, ref, tol=TOL):
+    assert np.isfinite(u).all()
+    assert rel_max(u, ref) < tol, rel_max(u, ref)
+    assert rel_l2(u, ref) < tol, rel_l2(u, ref)
+
+
+def make_system(seed, n_fibers, n_shell, n_body_nodes, n_bodies, nodes=(8, 16, 24, 32, 48, 64)):
+    rng = np.random.default_rng(seed)
+    n_nodes = rng.choice(nodes, size=n_fibers) if n_fibers else np.zeros(0, dtype=int)
+    lengths = rng.uniform(0.5, 2.0, n_fibers)
+    pos = []
+    for n, L in zip(n_nodes, lengths):
+        x0 = rng.uniform(-3, 3, 3)
+        nh = rng.normal(size=3)
+        nh /= np.linalg.norm(nh)
+        pos.append(x0 + np.linspace(0, L, n)[:, None] * nh)
+    r_fib = np.concatenate(pos) if pos else np.zeros((0, 3))
+    d = rng.normal(size=(n_shell, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None] if n_shell else 1
+    r_shell = d * np.array([7.8, 4.16, 4.16])
+    n_shell_ = -d
+    centers = rng.uniform(-2, 2, (n_bodies, 3))
+    per = n_body_nodes // max(n_bodies, 1)
+    r_body, n_body = [], []
+    for b in range(n_bodies):
+        e = rng.normal(size=(per, 3))
+        e /= np.linalg.norm(e, axis=1)[:, None]
+        r_body.append(centers[b] + 0.4 * e)
+        n_body.append(e)
+    r_body = np.concatenate(r_body) if r_body else np.zeros((0, 3))
+    n_body = np.concatenate(n_body) if n_body else np.zeros((0, 3))
+    fib = dict(pos=r_fib, n_nodes=list(n_nodes), lengths=list(lengths), forces=rng.uniform(-1, 1, r_fib.shape))
+    shell = dict(pos=r_shell, normals=n_shell_, density=rng.uniform(-1, 1, r_shell.shape))
+    body = dict(pos=r_body, normals=n_body, density=rng.uniform(-1, 1, r_body.shape), centers=centers,
+                forces=rng.uniform(-1, 1, (n_bodies, 3)), torques=rng.uniform(-1, 1, (n_bodies, 3)))
+    return fib, shell, body
+
+
+def load(fl, fib, shell, body):
+    fl.set_fibers(fib["pos"], fib["n_nodes"], fib["lengths"])
+    fl.set_periphery(shell["pos"], shell["normals"])
+    fl.set_bodies(body["pos"], body["normals"], body["centers"])
+
+
+def ft_of(body):
+    return np.concatenate([body["forces"], body["torques"]], axis=1)
+
+
+@pytest.mark.parametrize("eta", [1.0, 0.37])
+def test_fiber_flow_with_self_subtraction(eta):
+    fib, shell, body = make_system(1, 37, 300, 0, 0)
+    r_all = np.concatenate([fib["pos"], shell["pos"]])
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        v = fl.fiber_flow(r_all, fib["forces"], eta, subtract_self=True)
+        v_ns = fl.fiber_flow(r_all, fib["forces"], eta, subtract_self=False)
+    _check(v, orc.fiber_flow(r_all, fib["pos"], fib["n_nodes"], fib["lengths"], fib["forces"], eta, True))
+    _check(v_ns, orc.fiber_flow(r_all, fib["pos"], fib["n_nodes"], fib["lengths"], fib["forces"], eta, False))
+
+
+def test_periphery_and_body_flows():
+    fib, shell, body = make_system(2, 10, 1500, 800, 2)
+    rng = np.random.default_rng(9)
+    r_trg = rng.uniform(-2, 2, (777, 3))
+    eta = 1.3
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        vs = fl.periphery_flow(r_trg, shell["density"], eta)
+        vb = fl.body_flow(r_trg, body["density"], ft_of(body), eta)
+        # cached targets: second call with the same r_trg must give the same answer without re-upload
+        vs2 = fl.periphery_flow(r_trg, shell["density"], eta)
+    _check(vs, orc.periphery_flow(r_trg, shell["pos"], shell["normals"], shell["density"], eta))
+    _check(vb, orc.body_flow(r_trg, body["pos"], body["normals"], body["density"], body["centers"], body["forces"],
+                             body["torques"], eta))
+    assert np.array_equal(vs, vs2)
+
+
+@pytest.mark.parametrize("shape", [(16, 0, 0, 0), (16, 200, 0, 0), (20, 500, 400, 1), (0, 300, 400, 2),
+                                   (12, 0, 600, 3), (0, 0, 0, 0), (60, 1000, 800, 2)])
+def test_fused_matvec_flow(shape):
+    n_fibers, n_shell, n_body_nodes, n_bodies = shape
+    fib, shell, body = make_system(7 + sum(shape), n_fibers, n_shell, n_body_nodes, n_bodies)
+    eta = 0.9
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        v = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+        st = fl.stats()
+        # GMRES: same geometry, new strengths
+        rng = np.random.default_rng(0)
+        fib2 = dict(fib, forces=rng.normal(size=fib["forces"].shape))
+        v2 = fl.matvec(fib2["forces"], shell["density"], body["density"], ft_of(body), eta)
+    ref = orc.matvec_flow(fib, shell, body, eta)
+    assert v.shape == ref.shape
+    if ref.size == 0:
+        return
+    if np.abs(ref).max() == 0.0:
+        assert np.abs(v).max() == 0.0
+        return
+    _check(v, ref)
+    _check(v2, orc.matvec_flow(fib2, shell, body, eta))
+    assert st["launches"] > 0 and st["n_pairs"] > 0
+
+
+def test_c1_plumbing_config_16x32():
+    # BASELINE configs[0]: 16 fibers x 32 nodes, direct kernel, targets == sources
+    fib, shell, body = make_system(4, 16, 0, 0, 0, nodes=(32,))
+    eta = 1.0
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        v = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+    _check(v, orc.matvec_flow(fib, shell, body, eta))
+
+
+def test_geometry_update_between_timesteps():
+    fib, shell, body = make_system(11, 8, 100, 0, 0)
+    eta = 1.0
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        v0 = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+        fib2 = dict(fib, pos=fib["pos"] + 0.01)  # System::step moves the fibers (system.cpp:486-489)
+        fl.set_fibers(fib2["pos"], fib2["n_nodes"], fib2["lengths"])
+        v1 = fl.matvec(fib2["forces"], shell["density"], body["density"], ft_of(body), eta)
+    _check(v0, orc.matvec_flow(fib, shell, body, eta))
+    _check(v1, orc.matvec_flow(fib2, shell, body, eta))

@@ -275,3 +275,16 @@ def test_launches_are_counted(ctx):
     n0 = capi.launch_count()
     ctx.eval(SL, f3)
     assert capi.launch_count() - n0 == 3  # pack + pair sums + split reduction
+
+
+@pytest.mark.parametrize("kernel", ["stokeslet", "stresslet"])
+@pytest.mark.parametrize("driver", ["gpu", "gpu_cached", "impl"])
+def test_cpp_kernel_test_clone(kernel, driver):
+    # tests/cpp/kernel_test.cpp == SkellySim tests/core/kernel_test.cpp re-created against the drop-in library:
+    # C++ host code -> skelly_b200/kernels.hpp -> C ABI, plus the reference-named kernels::*_gpu_impl symbols
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "kernel_test")
+    assert os.path.exists(exe), "tests/cpp/kernel_test not built (run __graft_entry__.build())"
+    r = subprocess.run([exe, f"--kernel={kernel}", f"--driver={driver}"], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
