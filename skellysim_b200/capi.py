@@ -15,7 +15,7 @@ KERNEL_STOKESLET = 0
 KERNEL_STRESSLET = 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB = os.path.join(_HERE, "lib", "libskelly_b200.so")
+_LIB = os.environ.get("SKB_LIBRARY") or os.path.join(_HERE, "lib", "libskelly_b200.so")  # override: tuning A/B only
 _dp = C.POINTER(C.c_double)
 _lib = None
 

@@ -27,8 +27,13 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#ifndef SKB_SRC_UNROLL
+#define SKB_SRC_UNROLL 1 // source-pair iterations unrolled in the hot loop (tuning knob, see profiles/)
+#endif
+
 namespace skb {
 
+constexpr int kSrcUnroll = SKB_SRC_UNROLL;
 constexpr int kSrcTile = 128;       // sources per shared-memory stage
 constexpr int kStages = 4;          // TMA ring depth
 constexpr int kPrefetch = 2;        // tiles in flight ahead of the one being consumed (< kStages - 1)
@@ -479,7 +484,9 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
         // pairs of sources to walk in this tile (the padded tail of the last tile is skipped)
         long long left = a.n_src - (long long)(first_tile + k) * kSrcTile;
         const int jmax = left >= kSrcTile ? kSrcTile / 2 : (int)((left + 1) >> 1);
-#pragma unroll 1
+        // the stresslet's longer body gains ~2 % from exposing the next sources' LDS early (profiles/)
+        constexpr int kUnroll = (KIND == kStresslet && T <= 4) ? 2 * kSrcUnroll : kSrcUnroll;
+#pragma unroll kUnroll
         for (int j = 0; j < jmax; ++j) {
             // two sources per iteration: 48 B of positions = 3 x LDS.128 (warp-wide broadcast)
             const double2 p0 = ps[3 * j + 0], p1 = ps[3 * j + 1], p2 = ps[3 * j + 2];
