@@ -204,6 +204,101 @@ def workload_name(w, n_fib, n_shell):
 
 
 # ------------------------------------------------------------------------------------------------
+# second half of BASELINE's metric: GMRES matvec (hydrodynamic part) at N = 1e5 nodes, strong-scaled over the ranks
+# ------------------------------------------------------------------------------------------------
+def make_c3_system(seed=2):
+    """BASELINE C3 / SURVEY.md 8d S4: 3000 fibers x 32 + 6000 shell nodes + 1 body x 400 nodes = 102 400 nodes."""
+    fib, shell, nrm = make_suspension(3000, 6000, seed=seed)
+    rng = np.random.default_rng(seed)
+    e = rng.normal(size=(400, 3))
+    e /= np.linalg.norm(e, axis=1)[:, None]
+    centers = np.zeros((1, 3))
+    body_pos = centers + 0.5 * e
+    return dict(fib=fib, n_nodes=np.full(3000, 32, dtype=np.int32), lengths=np.ones(3000), shell=shell,
+                shell_n=nrm, body=np.ascontiguousarray(body_pos), body_n=np.ascontiguousarray(e), centers=centers,
+                ff=rng.uniform(-1, 1, fib.shape), sd=rng.uniform(-1, 1, shell.shape),
+                bd=rng.uniform(-1, 1, body_pos.shape), force=rng.uniform(-1, 1, (1, 3)),
+                torque=rng.uniform(-1, 1, (1, 3)))
+
+
+def matvec_leg(torch, dist, skb, dev, local_rank, rank, world, steps=20, warmup=3):
+    from skellysim_b200.distributed import allgather_strengths, block_range
+    g = make_c3_system()
+    nf, ns, nb = g["fib"].shape[0], g["shell"].shape[0], g["body"].shape[0]
+    n_all = nf + ns + nb
+    eta = 1.0
+    fl = skb.Flow(local_rank)
+    fl.set_fibers(g["fib"], g["n_nodes"], g["lengths"])
+    fl.set_periphery(g["shell"], g["shell_n"])
+    fl.set_bodies(g["body"], g["body_n"], g["centers"])
+    w0, w1 = block_range(n_all, world, rank)
+    fl.set_target_window(w0, w1)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    chunk = -(-nf // world)
+    d_ff = torch.zeros((chunk * world, 3), dtype=torch.float64, device=dev)
+    b, e = block_range(nf, world, rank)
+    d_mine = d_ff[rank * chunk:(rank + 1) * chunk]
+    d_mine[:e - b] = t(g["ff"][b:e])  # each rank owns the forces of its own fibers
+    d_sd, d_bd, d_f, d_t = t(g["sd"]), t(g["bd"]), t(g["force"]), t(g["torque"])
+    d_v = torch.empty((max(w1 - w0, 1), 3), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step():
+        allgather_strengths(d_ff, d_mine)
+        fl.matvec_device(d_ff.data_ptr(), d_sd.data_ptr(), d_bd.data_ptr(), d_f.data_ptr(), d_t.data_ptr(), eta,
+                         d_v.data_ptr(), stream)
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+    if world > 1:
+        dist.barrier()
+    for a, bb in evs:
+        flush.zero_()
+        a.record()
+        step()
+        bb.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(bb) for a, bb in evs) / steps
+    tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms = float(tt.item())
+    out = None
+    if rank == 0:
+        import oracle as orc
+        # accuracy gate on shell rows (fiber flow + body flow act there; the shell's own flow does not, system.cpp:301-315)
+        st = fl.stats()
+        res = {"workload": "c3: 3000 fibers x 32 + 6000 periphery nodes + 1 body x 400 nodes (102400 nodes); "
+                           "hydrodynamic part of System::apply_matvec (SL fibers->all, DL shell->fibers+bodies, "
+                           "DL body->all, SL+rotlet centres->all, self-term subtraction)",
+               "n_nodes": n_all, "ms": ms, "scaling": "strong", "steps": steps,
+               "pairs": float(nf) * n_all + float(ns) * (nf + nb) + float(nb + 2) * n_all,
+               "launches_per_matvec_rank0": st["launches"]}
+        if world == 1:
+            v = d_v.cpu().numpy()
+            idx = nf + np.random.default_rng(1).choice(ns, 64, replace=False)
+            r_all = np.concatenate([g["fib"], g["shell"], g["body"]])
+            w = np.tile(orc.trapezoid_weights(32, 1.0), 3000)
+            ref = orc.stokeslet_direct_cpu(g["fib"], g["ff"] * w[:, None], r_all[idx], eta)
+            ref += orc.body_flow(r_all[idx], g["body"], g["body_n"], g["bd"], g["centers"], g["force"], g["torque"],
+                                 eta)
+            res["max_rel_err_vs_oracle_shell_rows"] = float(np.abs(v[idx] - ref).max() / np.abs(ref).max())
+            # end to end through the host-pointer C ABI (H2D of all strengths + D2H of v_all inside)
+            ft = np.concatenate([g["force"], g["torque"]], axis=1)
+            fl.matvec(g["ff"], g["sd"], g["bd"], ft, eta)
+            t0 = time.perf_counter()
+            for _ in range(5):
+                fl.matvec(g["ff"], g["sd"], g["bd"], ft, eta)
+            res["e2e_ms"] = 1e3 * (time.perf_counter() - t0) / 5
+        out = res
+    fl.close()
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -214,6 +309,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-matvec", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -396,8 +492,13 @@ def main():
             out["error"] = f"accuracy gate failed: {acc}"
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg(r_src_all, f_all, r_trg_all)
-        print(json.dumps(out))
     ctx.close()
+    del flush
+    mv = None if args.no_matvec else matvec_leg(torch, dist, skb, dev, local_rank, rank, world)
+    if rank == 0:
+        if mv is not None:
+            out["matvec"] = mv
+        print(json.dumps(out))
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

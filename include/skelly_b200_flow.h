@@ -65,6 +65,18 @@ SKB_API int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double
                             const double *body_densities, const double *body_forces_torques, double eta,
                             double *v_all);
 
+/* Restrict the matvec to rows [begin, end) of the target list [fibers | periphery | bodies] (end < 0: all).
+ * For one-rank-per-GPU hosts: every rank loads the full geometry, all-gathers the strengths, and evaluates its own
+ * block of targets; v_all / d_v_window then has (end - begin) rows.  The self-term subtraction is applied to the
+ * fiber rows inside the window. */
+SKB_API int skb_flow_set_target_window(skb_flow *fl, int64_t begin, int64_t end);
+
+/* Device-pointer form of skb_flow_matvec: all inputs and the output already on this flow's device; asynchronous on
+ * `stream` (cudaStream_t as void*, used verbatim).  d_body_forces / d_body_torques are 3 x n_bodies each. */
+SKB_API int skb_flow_matvec_device(skb_flow *fl, const double *d_fib_forces, const double *d_shell_density,
+                                   const double *d_body_densities, const double *d_body_forces,
+                                   const double *d_body_torques, double eta, double *d_v_window, void *stream);
+
 typedef struct skb_flow_stats {
     double device_ms;   /* CUDA-event time of the last call, first launch to last kernel (copies excluded) */
     double total_ms;    /* including H2D / D2H */

@@ -94,6 +94,8 @@ def library() -> C.CDLL:
         "skb_flow_bodies": ([ctxp, _dp, C.c_int64, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_matvec": ([ctxp, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_last_stats": ([ctxp, C.POINTER(FlowStats)], C.c_int),
+        "skb_flow_set_target_window": ([ctxp, C.c_int64, C.c_int64], C.c_int),
+        "skb_flow_matvec_device": ([ctxp] + [C.c_void_p] * 5 + [C.c_double, C.c_void_p, C.c_void_p], C.c_int),
     }
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
@@ -328,10 +330,27 @@ class Flow:
                                          _p(vel)))
         return vel
 
+    def set_target_window(self, begin: int, end: int = -1):
+        """Evaluate only rows [begin, end) of [fibers | periphery | bodies] in matvec() (one rank's block)."""
+        _check(library().skb_flow_set_target_window(self._h, int(begin), int(end)))
+        n_all = self.n_fib + self.n_shell + self.n_body
+        self._window = (min(begin, n_all), n_all if end < 0 else min(end, n_all))
+
+    def matvec_device(self, d_fib_forces: int, d_shell_density: int, d_body_densities: int, d_body_forces: int,
+                      d_body_torques: int, eta: float, d_v_window: int, stream: int = 0):
+        """Device-pointer matvec (addresses as ints); asynchronous on `stream`."""
+        _check(library().skb_flow_matvec_device(self._h, C.c_void_p(d_fib_forces), C.c_void_p(d_shell_density),
+                                                C.c_void_p(d_body_densities), C.c_void_p(d_body_forces),
+                                                C.c_void_p(d_body_torques), float(eta), C.c_void_p(d_v_window),
+                                                C.c_void_p(stream)))
+
     def matvec(self, fib_forces, shell_density, body_densities, body_forces_torques, eta):
         a, b, c = _arr(fib_forces, 3), _arr(shell_density, 3), _arr(body_densities, 3)
         ft = _arr(body_forces_torques, 6)
-        v = np.empty((self.n_fib + self.n_shell + self.n_body, 3))
+        n_all = self.n_fib + self.n_shell + self.n_body
+        w0, w1 = getattr(self, "_window", (0, n_all))
+        w1 = min(w1, n_all)
+        v = np.empty((max(w1 - w0, 0), 3))
         _check(library().skb_flow_matvec(self._h, _p(a), _p(b), _p(c), _p(ft), float(eta), _p(v)))
         return v
 

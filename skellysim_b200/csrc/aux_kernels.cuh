@@ -13,10 +13,15 @@ namespace skb {
 // `wf` are the trapezoid-weighted forces, i.e. the packed Stokeslet strengths.
 __global__ void fiber_self_subtract_kernel(const double *__restrict__ r_fib, const double *__restrict__ wf,
                                            const long long *__restrict__ fiber_offset, double inv_8pi_eta,
-                                           double reg2, double eps, double *__restrict__ vel) {
+                                           double reg2, double eps, double *__restrict__ vel, long long node_begin,
+                                           long long node_end) {
+    // only fiber nodes in [node_begin, node_end) are targets of this launch (target window of a rank);
+    // vel is indexed window-locally: row (node - node_begin)
     extern __shared__ double sh[]; // [n*3 positions][n*3 strengths]
     const long long off = fiber_offset[blockIdx.x];
     const int n = (int)(fiber_offset[blockIdx.x + 1] - off);
+    if (off + n <= node_begin || off >= node_end)
+        return;
     double *xs = sh, *fs = sh + 3 * n;
     for (int i = threadIdx.x; i < 3 * n; i += blockDim.x) {
         xs[i] = r_fib[3 * off + i];
@@ -24,6 +29,8 @@ __global__ void fiber_self_subtract_kernel(const double *__restrict__ r_fib, con
     }
     __syncthreads();
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        if (off + i < node_begin || off + i >= node_end)
+            continue;
         const double x = xs[3 * i], y = xs[3 * i + 1], z = xs[3 * i + 2];
         double a0 = 0, a1 = 0, a2 = 0;
         for (int j = 0; j < n; ++j) {
@@ -47,9 +54,10 @@ __global__ void fiber_self_subtract_kernel(const double *__restrict__ r_fib, con
             a1 += fr * d1 + dy * dot;
             a2 += fr * d2 + dz * dot;
         }
-        vel[3 * (off + i) + 0] -= a0;
-        vel[3 * (off + i) + 1] -= a1;
-        vel[3 * (off + i) + 2] -= a2;
+        const long long row = off + i - node_begin;
+        vel[3 * row + 0] -= a0;
+        vel[3 * row + 1] -= a1;
+        vel[3 * row + 2] -= a2;
     }
 }
 

@@ -58,6 +58,9 @@ struct skb_flow {
     skb_ctx *fib[2] = {nullptr, nullptr}, *shell[2] = {nullptr, nullptr}, *body[2] = {nullptr, nullptr};
     TargetCache tc_fib, tc_shell, tc_body;
     bool mv_dirty = true;
+    long long win_begin = 0, win_end = -1; // target window of the matvec in [fibers|shell|bodies] rows; -1 = all
+    long long fa = 0, fb = 0, ba = 0, bb = 0, w0 = 0, w1 = 0; // resolved window pieces (fiber rows, body rows)
+    cudaStream_t cur = nullptr;            // stream of the call in flight (own stream or the caller's)
     // staging
     DevBuf in_fib, in_shell, in_body, in_force, in_torque, vel, tmp;
     skb_flow_stats stats{};
@@ -72,28 +75,30 @@ static int ensure_ctx(skb_flow *fl, skb_ctx **slot) {
 }
 
 // ---- device-side flows: ctx already has its targets and sources ------------------------------------------------
+// subtract_self: the first (node_end - node_begin) targets are the fiber nodes [node_begin, node_end)
 static int fibers_dev(skb_flow *fl, skb_ctx *ctx, const double *d_forces, double eta, int subtract_self,
-                      double *d_vel, int accumulate) {
+                      double *d_vel, int accumulate, long long node_begin, long long node_end) {
     DeviceState &d = ctx->devs[0];
     if (d.n_trg == 0)
         return SKB_OK;
     if (fl->n_fibers == 0) { // fiber_container_finite_difference.cpp:178-179
         if (!accumulate)
-            CUDA_TRY(cudaMemsetAsync(d_vel, 0, (size_t)d.n_trg * 24, fl->stream));
+            CUDA_TRY(cudaMemsetAsync(d_vel, 0, (size_t)d.n_trg * 24, fl->cur));
         return SKB_OK;
     }
     // weighted forces -> Stokeslet all-to-all, / eta  (fcfd.cpp:185-199, kernels.cpp:365)
-    SKB_TRY(eval_on_device(ctx, d, SKB_STOKESLET, kRaw, d_forces, 0.0, d_vel, accumulate, fl->stream, false,
+    SKB_TRY(eval_on_device(ctx, d, SKB_STOKESLET, kRaw, d_forces, 0.0, d_vel, accumulate, fl->cur, false,
                            &fl->launches, nullptr, 1.0 / eta));
     fl->pairs += fl->n_fib * d.n_trg;
     if (subtract_self) { // fcfd.cpp:203-210; the first N_f targets are the fiber nodes themselves
-        if (d.n_trg < fl->n_fib)
+        if (d.n_trg < node_end - node_begin)
             return set_error(SKB_ERR_INVALID, "fiber flow with subtract_self needs the fiber nodes as the first "
-                                              "%lld targets (n_trg = %lld)", fl->n_fib, d.n_trg);
+                                              "%lld targets (n_trg = %lld)", node_end - node_begin, d.n_trg);
         const size_t smem = (size_t)fl->max_fiber_nodes * 6 * sizeof(double);
-        fiber_self_subtract_kernel<<<fl->n_fibers, 128, smem, fl->stream>>>(
+        fiber_self_subtract_kernel<<<fl->n_fibers, 128, smem, fl->cur>>>(
             (const double *)fl->r_fib.ptr, (const double *)d.src[SKB_STOKESLET].f_packed.ptr,
-            (const long long *)fl->fiber_offset.ptr, 1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps, d_vel);
+            (const long long *)fl->fiber_offset.ptr, 1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps, d_vel, node_begin,
+            node_end);
         CUDA_TRY(cudaGetLastError());
         count_launch(1);
         fl->launches += 1;
@@ -108,11 +113,11 @@ static int periphery_dev(skb_flow *fl, skb_ctx *ctx, const double *d_density, do
         return SKB_OK;
     if (fl->n_shell == 0) { // periphery.cpp:57-58
         if (!accumulate)
-            CUDA_TRY(cudaMemsetAsync(d_vel, 0, (size_t)d.n_trg * 24, fl->stream));
+            CUDA_TRY(cudaMemsetAsync(d_vel, 0, (size_t)d.n_trg * 24, fl->cur));
         return SKB_OK;
     }
     // f_dl = 2 eta n (x) rho formed on the device, stresslet, / eta  (periphery.cpp:68-74, kernels.cpp:358)
-    SKB_TRY(eval_on_device(ctx, d, SKB_STRESSLET, kNormalDensity, d_density, 2.0 * eta, d_vel, accumulate, fl->stream,
+    SKB_TRY(eval_on_device(ctx, d, SKB_STRESSLET, kNormalDensity, d_density, 2.0 * eta, d_vel, accumulate, fl->cur,
                            false, &fl->launches, nullptr, 1.0 / eta));
     fl->pairs += fl->n_shell * d.n_trg;
     return SKB_OK;
@@ -125,18 +130,18 @@ static int bodies_dev(skb_flow *fl, skb_ctx *ctx, const double *d_density, const
         return SKB_OK;
     if (fl->n_bodies == 0) { // body_container.cpp:273-276
         if (!accumulate)
-            CUDA_TRY(cudaMemsetAsync(d_vel, 0, (size_t)d.n_trg * 24, fl->stream));
+            CUDA_TRY(cudaMemsetAsync(d_vel, 0, (size_t)d.n_trg * 24, fl->cur));
         return SKB_OK;
     }
     // stresslet of the surface nodes (body_container.cpp:296-305)
-    SKB_TRY(eval_on_device(ctx, d, SKB_STRESSLET, kNormalDensity, d_density, 2.0 * eta, d_vel, accumulate, fl->stream,
+    SKB_TRY(eval_on_device(ctx, d, SKB_STRESSLET, kNormalDensity, d_density, 2.0 * eta, d_vel, accumulate, fl->cur,
                            false, &fl->launches, nullptr, 1.0 / eta));
     // Stokeslet of the net forces at the centres (:327)
-    SKB_TRY(eval_on_device(ctx, d, SKB_STOKESLET, kRaw, d_force, 0.0, d_vel, 1, fl->stream, false, &fl->launches,
+    SKB_TRY(eval_on_device(ctx, d, SKB_STOKESLET, kRaw, d_force, 0.0, d_vel, 1, fl->cur, false, &fl->launches,
                            nullptr, 1.0 / eta));
     // rotlet of the net torques at the centres (:335, kernels.cpp:206-242)
     const int bs = 128;
-    rotlet_add_kernel<<<(unsigned)((d.n_trg + bs - 1) / bs), bs, 0, fl->stream>>>(
+    rotlet_add_kernel<<<(unsigned)((d.n_trg + bs - 1) / bs), bs, 0, fl->cur>>>(
         (const double *)fl->centers.ptr, d_torque, fl->n_bodies, (const double *)d.r_trg.ptr, d.n_trg,
         1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps * kEps, d_vel);
     CUDA_TRY(cudaGetLastError());
@@ -343,7 +348,9 @@ int skb_flow_fibers(skb_flow *fl, const double *r_trg, int64_t n_trg, const doub
     SKB_TRY(upload(fl, fl->in_fib, fib_forces, (size_t)fl->n_fib * 3));
     SKB_TRY(fl->vel.ensure((size_t)n_trg * 24));
     CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
-    SKB_TRY(fibers_dev(fl, fl->fib[0], (const double *)fl->in_fib.ptr, eta, subtract_self, (double *)fl->vel.ptr, 0));
+    fl->cur = fl->stream;
+    SKB_TRY(fibers_dev(fl, fl->fib[0], (const double *)fl->in_fib.ptr, eta, subtract_self, (double *)fl->vel.ptr, 0, 0,
+                       fl->n_fib));
     CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
     CUDA_TRY(cudaMemcpyAsync(vel, fl->vel.ptr, (size_t)n_trg * 24, cudaMemcpyDeviceToHost, fl->stream));
     CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
@@ -363,6 +370,7 @@ int skb_flow_periphery(skb_flow *fl, const double *r_trg, int64_t n_trg, const d
     SKB_TRY(upload(fl, fl->in_shell, density, (size_t)fl->n_shell * 3));
     SKB_TRY(fl->vel.ensure((size_t)n_trg * 24));
     CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    fl->cur = fl->stream;
     SKB_TRY(periphery_dev(fl, fl->shell[0], (const double *)fl->in_shell.ptr, eta, (double *)fl->vel.ptr, 0));
     CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
     CUDA_TRY(cudaMemcpyAsync(vel, fl->vel.ptr, (size_t)n_trg * 24, cudaMemcpyDeviceToHost, fl->stream));
@@ -388,6 +396,7 @@ int skb_flow_bodies(skb_flow *fl, const double *r_trg, int64_t n_trg, const doub
     SKB_TRY(upload(fl, fl->in_torque, t.data(), t.size()));
     SKB_TRY(fl->vel.ensure((size_t)n_trg * 24));
     CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    fl->cur = fl->stream;
     SKB_TRY(bodies_dev(fl, fl->body[0], (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
                        (const double *)fl->in_torque.ptr, eta, (double *)fl->vel.ptr, 0));
     CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
@@ -395,6 +404,82 @@ int skb_flow_bodies(skb_flow *fl, const double *r_trg, int64_t n_trg, const doub
     CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
     CUDA_TRY(cudaStreamSynchronize(fl->stream)); // f, t are stack-owned staging
     return finish_stats(fl);
+}
+
+// resolve the target window into its fiber / body pieces and (re)build the matvec target lists
+static int prepare_matvec_targets(skb_flow *fl) {
+    const long long nf = fl->n_fib, ns = fl->n_shell, nb = fl->n_body, n_all = nf + ns + nb;
+    if (!fl->mv_dirty)
+        return SKB_OK;
+    long long w0 = fl->win_begin, w1 = fl->win_end < 0 ? n_all : fl->win_end;
+    w0 = std::min(std::max(w0, 0LL), n_all);
+    w1 = std::min(std::max(w1, w0), n_all);
+    auto clampi = [](long long x, long long lo, long long hi) { return std::min(std::max(x, lo), hi); };
+    fl->w0 = w0;
+    fl->w1 = w1;
+    fl->fa = clampi(w0, 0, nf);
+    fl->fb = clampi(w1, 0, nf);
+    fl->ba = clampi(w0 - nf - ns, 0, nb);
+    fl->bb = clampi(w1 - nf - ns, 0, nb);
+    // target lists of apply_matvec: r_all = [fibers | shell | bodies] (system.cpp:284-291),
+    // r_fibbody = [fibers | bodies] (system.cpp:301-303), both restricted to the window
+    std::vector<double> r_all((size_t)n_all * 3);
+    std::copy(fl->h_r_fib.begin(), fl->h_r_fib.end(), r_all.begin());
+    std::copy(fl->h_r_shell.begin(), fl->h_r_shell.end(), r_all.begin() + 3 * nf);
+    std::copy(fl->h_r_body.begin(), fl->h_r_body.end(), r_all.begin() + 3 * (nf + ns));
+    std::vector<double> r_fb;
+    r_fb.insert(r_fb.end(), fl->h_r_fib.begin() + 3 * fl->fa, fl->h_r_fib.begin() + 3 * fl->fb);
+    r_fb.insert(r_fb.end(), fl->h_r_body.begin() + 3 * fl->ba, fl->h_r_body.begin() + 3 * fl->bb);
+    SKB_TRY(skb_set_targets(fl->fib[1], r_all.data() + 3 * w0, w1 - w0));
+    SKB_TRY(skb_set_targets(fl->body[1], r_all.data() + 3 * w0, w1 - w0));
+    SKB_TRY(skb_set_targets(fl->shell[1], r_fb.data(), (long long)r_fb.size() / 3));
+    fl->mv_dirty = false;
+    return SKB_OK;
+}
+
+// device-side matvec flow on fl->cur: all strengths resident, d_v = window rows of v_all
+static int matvec_core(skb_flow *fl, const double *d_ff, const double *d_sd, const double *d_bd, const double *d_f,
+                       const double *d_t, double eta, double *d_v) {
+    const long long nf = fl->n_fib, ns = fl->n_shell;
+    const long long n_win = fl->w1 - fl->w0, n_fw = fl->fb - fl->fa, n_bw = fl->bb - fl->ba;
+    if (n_win == 0)
+        return SKB_OK;
+    // v_all = fc.flow(r_all, fw, eta)                                  system.cpp:299
+    // (the window's fiber rows come first, so the self term applies to targets [0, n_fw) of the window)
+    SKB_TRY(fibers_dev(fl, fl->fib[1], d_ff, eta, n_fw > 0, d_v, 0, fl->fa, fl->fb));
+    // v_fibers, v_bodies += shell.flow(r_fibbody, x_shell, eta)         system.cpp:304,313-315
+    if (ns > 0 && n_fw + n_bw > 0) {
+        SKB_TRY(fl->tmp.ensure((size_t)(n_fw + n_bw) * 24 + 8));
+        double *d_tmp = (double *)fl->tmp.ptr;
+        SKB_TRY(periphery_dev(fl, fl->shell[1], d_sd, eta, d_tmp, 0));
+        const int bs = 256;
+        if (n_fw > 0) {
+            add_inplace_kernel<<<(unsigned)((3 * n_fw + bs - 1) / bs), bs, 0, fl->cur>>>(d_v + 3 * (fl->fa - fl->w0),
+                                                                                        d_tmp, 3 * n_fw);
+            count_launch(1);
+            fl->launches += 1;
+        }
+        if (n_bw > 0) {
+            add_inplace_kernel<<<(unsigned)((3 * n_bw + bs - 1) / bs), bs, 0, fl->cur>>>(
+                d_v + 3 * (nf + ns + fl->ba - fl->w0), d_tmp + 3 * n_fw, 3 * n_bw);
+            count_launch(1);
+            fl->launches += 1;
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    // v_all += bc.flow(r_all, x_bodies, body_link_conditions, eta)     system.cpp:316
+    SKB_TRY(bodies_dev(fl, fl->body[1], d_bd, d_f, d_t, eta, d_v, 1));
+    return SKB_OK;
+}
+
+int skb_flow_set_target_window(skb_flow *fl, int64_t begin, int64_t end) {
+    if (!fl || begin < 0 || (end >= 0 && end < begin))
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_target_window: bad window [%lld, %lld)", (long long)begin,
+                         (long long)end);
+    fl->win_begin = begin;
+    fl->win_end = end;
+    fl->mv_dirty = true;
+    return SKB_OK;
 }
 
 int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double *shell_density, const double *body_densities,
@@ -409,59 +494,55 @@ int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double *shell_
     begin_stats(fl);
     if (n_all == 0)
         return SKB_OK;
-    if (fl->mv_dirty) {
-        // target lists of apply_matvec: r_all = [fibers | shell | bodies] (system.cpp:284-291),
-        // r_fibbody = [fibers | bodies] (system.cpp:301-303)
-        std::vector<double> r_all((size_t)n_all * 3), r_fb((size_t)(nf + nb) * 3);
-        std::copy(fl->h_r_fib.begin(), fl->h_r_fib.end(), r_all.begin());
-        std::copy(fl->h_r_shell.begin(), fl->h_r_shell.end(), r_all.begin() + 3 * nf);
-        std::copy(fl->h_r_body.begin(), fl->h_r_body.end(), r_all.begin() + 3 * (nf + ns));
-        std::copy(fl->h_r_fib.begin(), fl->h_r_fib.end(), r_fb.begin());
-        std::copy(fl->h_r_body.begin(), fl->h_r_body.end(), r_fb.begin() + 3 * nf);
-        SKB_TRY(skb_set_targets(fl->fib[1], r_all.data(), n_all));
-        SKB_TRY(skb_set_targets(fl->body[1], r_all.data(), n_all));
-        SKB_TRY(skb_set_targets(fl->shell[1], r_fb.data(), nf + nb));
-        fl->mv_dirty = false;
-    }
+    SKB_TRY(prepare_matvec_targets(fl));
+    const long long n_win = fl->w1 - fl->w0;
+    if (n_win == 0)
+        return SKB_OK;
     std::vector<double> f, t;
     if (fl->n_bodies > 0)
         split_forces_torques(body_forces_torques, fl->n_bodies, f, t);
+    fl->cur = fl->stream;
     CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
     SKB_TRY(upload(fl, fl->in_fib, fib_forces, (size_t)nf * 3));
     SKB_TRY(upload(fl, fl->in_shell, shell_density, (size_t)ns * 3));
     SKB_TRY(upload(fl, fl->in_body, body_densities, (size_t)nb * 3));
     SKB_TRY(upload(fl, fl->in_force, f.data(), f.size()));
     SKB_TRY(upload(fl, fl->in_torque, t.data(), t.size()));
-    SKB_TRY(fl->vel.ensure((size_t)n_all * 24));
-    SKB_TRY(fl->tmp.ensure((size_t)(nf + nb) * 24 + 8));
-    double *d_v = (double *)fl->vel.ptr, *d_tmp = (double *)fl->tmp.ptr;
+    SKB_TRY(fl->vel.ensure((size_t)n_win * 24));
     CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
-    // v_all = fc.flow(r_all, fw, eta)                                  system.cpp:299
-    SKB_TRY(fibers_dev(fl, fl->fib[1], (const double *)fl->in_fib.ptr, eta, 1, d_v, 0));
-    // v_fibers, v_bodies += shell.flow(r_fibbody, x_shell, eta)         system.cpp:304,313-315
-    if (ns > 0 && nf + nb > 0) {
-        SKB_TRY(periphery_dev(fl, fl->shell[1], (const double *)fl->in_shell.ptr, eta, d_tmp, 0));
-        const int bs = 256;
-        if (nf > 0) {
-            add_inplace_kernel<<<(unsigned)((3 * nf + bs - 1) / bs), bs, 0, fl->stream>>>(d_v, d_tmp, 3 * nf);
-            count_launch(1);
-            fl->launches += 1;
-        }
-        if (nb > 0) {
-            add_inplace_kernel<<<(unsigned)((3 * nb + bs - 1) / bs), bs, 0, fl->stream>>>(d_v + 3 * (nf + ns),
-                                                                                         d_tmp + 3 * nf, 3 * nb);
-            count_launch(1);
-            fl->launches += 1;
-        }
-        CUDA_TRY(cudaGetLastError());
-    }
-    // v_all += bc.flow(r_all, x_bodies, body_link_conditions, eta)     system.cpp:316
-    SKB_TRY(bodies_dev(fl, fl->body[1], (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
-                       (const double *)fl->in_torque.ptr, eta, d_v, 1));
+    SKB_TRY(matvec_core(fl, (const double *)fl->in_fib.ptr, (const double *)fl->in_shell.ptr,
+                        (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
+                        (const double *)fl->in_torque.ptr, eta, (double *)fl->vel.ptr));
     CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
-    CUDA_TRY(cudaMemcpyAsync(v_all, d_v, (size_t)n_all * 24, cudaMemcpyDeviceToHost, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(v_all, fl->vel.ptr, (size_t)n_win * 24, cudaMemcpyDeviceToHost, fl->stream));
     CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
     return finish_stats(fl);
+}
+
+int skb_flow_matvec_device(skb_flow *fl, const double *d_fib_forces, const double *d_shell_density,
+                           const double *d_body_densities, const double *d_body_forces, const double *d_body_torques,
+                           double eta, double *d_v_window, void *stream) {
+    if (!fl || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_flow_matvec_device: bad arguments");
+    const long long nf = fl->n_fib, ns = fl->n_shell, nb = fl->n_body, n_all = nf + ns + nb;
+    if ((nf > 0 && !d_fib_forces) || (ns > 0 && !d_shell_density) || (nb > 0 && !d_body_densities) ||
+        (fl->n_bodies > 0 && (!d_body_forces || !d_body_torques)))
+        return set_error(SKB_ERR_INVALID, "skb_flow_matvec_device: NULL input for a non-empty class");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    begin_stats(fl);
+    if (n_all == 0)
+        return SKB_OK;
+    SKB_TRY(prepare_matvec_targets(fl));
+    if (fl->w1 - fl->w0 > 0 && !d_v_window)
+        return set_error(SKB_ERR_INVALID, "skb_flow_matvec_device: NULL output");
+    fl->cur = (cudaStream_t)stream;
+    SKB_TRY(matvec_core(fl, d_fib_forces, d_shell_density, d_body_densities, d_body_forces, d_body_torques, eta,
+                        d_v_window));
+    fl->stats.device_ms = 0;
+    fl->stats.total_ms = 0;
+    fl->stats.n_pairs = fl->pairs;
+    fl->stats.launches = fl->launches;
+    return SKB_OK;
 }
 
 int skb_flow_last_stats(const skb_flow *fl, skb_flow_stats *out) {

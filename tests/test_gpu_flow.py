@@ -136,3 +136,43 @@ def test_geometry_update_between_timesteps():
         v1 = fl.matvec(fib2["forces"], shell["density"], body["density"], ft_of(body), eta)
     _check(v0, orc.matvec_flow(fib, shell, body, eta))
     _check(v1, orc.matvec_flow(fib2, shell, body, eta))
+
+
+def test_target_windows_tile_the_full_matvec():
+    # one-rank-per-GPU sharding of apply_matvec: every rank evaluates a block of [fibers | shell | bodies] rows;
+    # blocks cut through fibers, the shell and the body on purpose
+    fib, shell, body = make_system(21, 25, 333, 450, 1)
+    eta = 1.1
+    ref = orc.matvec_flow(fib, shell, body, eta)
+    n_all = ref.shape[0]
+    cuts = [0, 37, 200, n_all // 2, n_all - 100, n_all]
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        full = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+        parts = []
+        for a, b in zip(cuts[:-1], cuts[1:]):
+            fl.set_target_window(a, b)
+            parts.append(fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta))
+    _check(full, ref)
+    tiled = np.concatenate(parts)
+    assert tiled.shape == ref.shape
+    _check(tiled, ref)
+
+
+def test_matvec_device_pointers_with_torch():
+    import torch
+    fib, shell, body = make_system(23, 30, 400, 300, 2)
+    eta = 0.8
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_ff, d_sd, d_bd = t(fib["forces"]), t(shell["density"]), t(body["density"])
+    d_f, d_t = t(body["forces"]), t(body["torques"])
+    n_all = fib["pos"].shape[0] + shell["pos"].shape[0] + body["pos"].shape[0]
+    d_v = torch.empty((n_all, 3), dtype=torch.float64, device=dev)
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        st = torch.cuda.current_stream().cuda_stream
+        fl.matvec_device(d_ff.data_ptr(), d_sd.data_ptr(), d_bd.data_ptr(), d_f.data_ptr(), d_t.data_ptr(), eta,
+                         d_v.data_ptr(), st)
+        torch.cuda.synchronize()
+    _check(d_v.cpu().numpy(), orc.matvec_flow(fib, shell, body, eta))
