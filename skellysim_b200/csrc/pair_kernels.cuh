@@ -34,6 +34,10 @@
 namespace skb {
 
 constexpr int kSrcUnroll = SKB_SRC_UNROLL;
+#ifndef SKB_CHAIN_GROUP
+#define SKB_CHAIN_GROUP 4 // independent pair chains evaluated stage-wise together when T >= 4 (tuning knob)
+#endif
+constexpr int kChainGroup = SKB_CHAIN_GROUP;
 constexpr int kSrcTile = 128;       // sources per shared-memory stage
 constexpr int kStages = 4;          // TMA ring depth
 constexpr int kPrefetch = 2;        // tiles in flight ahead of the one being consumed (< kStages - 1)
@@ -317,23 +321,24 @@ __device__ __forceinline__ void stokeslet_two_sources(const double (&tx)[T], con
             uz[t] = fma(y[c], vz[c], uz[t]);
         }
     } else {
+        constexpr int G = (T % kChainGroup == 0) ? kChainGroup : 4;
 #pragma unroll
         for (int src = 0; src < 2; ++src) {
 #pragma unroll
-            for (int g = 0; g < T / 4; ++g) {
-                double cx[4], cy[4], cz[4], sx[4], sy[4], sz[4], fx[4], fy[4], fz[4], y[4], vx[4], vy[4], vz[4];
+            for (int g = 0; g < T / G; ++g) {
+                double cx[G], cy[G], cz[G], sx[G], sy[G], sz[G], fx[G], fy[G], fz[G], y[G], vx[G], vy[G], vz[G];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    cx[c] = tx[4 * g + c], cy[c] = ty[4 * g + c], cz[c] = tz[4 * g + c];
+                for (int c = 0; c < G; ++c) {
+                    cx[c] = tx[G * g + c], cy[c] = ty[G * g + c], cz[c] = tz[G * g + c];
                     sx[c] = src ? sb[0] : sa[0], sy[c] = src ? sb[1] : sa[1], sz[c] = src ? sb[2] : sa[2];
                     fx[c] = src ? fb[0] : fa[0], fy[c] = src ? fb[1] : fa[1], fz[c] = src ? fb[2] : fa[2];
                 }
-                stokeslet_chains<4>(cx, cy, cz, sx, sy, sz, fx, fy, fz, y, vx, vy, vz);
+                stokeslet_chains<G>(cx, cy, cz, sx, sy, sz, fx, fy, fz, y, vx, vy, vz);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    ux[4 * g + c] = fma(y[c], vx[c], ux[4 * g + c]);
-                    uy[4 * g + c] = fma(y[c], vy[c], uy[4 * g + c]);
-                    uz[4 * g + c] = fma(y[c], vz[c], uz[4 * g + c]);
+                for (int c = 0; c < G; ++c) {
+                    ux[G * g + c] = fma(y[c], vx[c], ux[G * g + c]);
+                    uy[G * g + c] = fma(y[c], vy[c], uy[G * g + c]);
+                    uz[G * g + c] = fma(y[c], vz[c], uz[G * g + c]);
                 }
             }
         }
@@ -368,25 +373,26 @@ __device__ __forceinline__ void stresslet_two_sources(const double (&tx)[T], con
             uz[t] = fma(dz[c], co[c], uz[t]);
         }
     } else {
+        constexpr int G = (T % kChainGroup == 0) ? kChainGroup : 4;
 #pragma unroll
         for (int src = 0; src < 2; ++src) {
 #pragma unroll
-            for (int g = 0; g < T / 4; ++g) {
-                double cx[4], cy[4], cz[4], sx[4], sy[4], sz[4], s0[4], s1[4], s2[4], s3[4], s4[4], s5[4];
-                double dx[4], dy[4], dz[4], co[4];
+            for (int g = 0; g < T / G; ++g) {
+                double cx[G], cy[G], cz[G], sx[G], sy[G], sz[G], s0[G], s1[G], s2[G], s3[G], s4[G], s5[G];
+                double dx[G], dy[G], dz[G], co[G];
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    cx[c] = tx[4 * g + c], cy[c] = ty[4 * g + c], cz[c] = tz[4 * g + c];
+                for (int c = 0; c < G; ++c) {
+                    cx[c] = tx[G * g + c], cy[c] = ty[G * g + c], cz[c] = tz[G * g + c];
                     sx[c] = src ? sb[0] : sa[0], sy[c] = src ? sb[1] : sa[1], sz[c] = src ? sb[2] : sa[2];
                     s0[c] = src ? fb[0] : fa[0], s1[c] = src ? fb[1] : fa[1], s2[c] = src ? fb[2] : fa[2];
                     s3[c] = src ? fb[3] : fa[3], s4[c] = src ? fb[4] : fa[4], s5[c] = src ? fb[5] : fa[5];
                 }
-                stresslet_chains<4>(cx, cy, cz, sx, sy, sz, s0, s1, s2, s3, s4, s5, dx, dy, dz, co);
+                stresslet_chains<G>(cx, cy, cz, sx, sy, sz, s0, s1, s2, s3, s4, s5, dx, dy, dz, co);
 #pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    ux[4 * g + c] = fma(dx[c], co[c], ux[4 * g + c]);
-                    uy[4 * g + c] = fma(dy[c], co[c], uy[4 * g + c]);
-                    uz[4 * g + c] = fma(dz[c], co[c], uz[4 * g + c]);
+                for (int c = 0; c < G; ++c) {
+                    ux[G * g + c] = fma(dx[c], co[c], ux[G * g + c]);
+                    uy[G * g + c] = fma(dy[c], co[c], uy[G * g + c]);
+                    uz[G * g + c] = fma(dz[c], co[c], uz[G * g + c]);
                 }
             }
         }
