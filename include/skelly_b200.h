@@ -132,6 +132,13 @@ SKB_API int64_t skb_launch_count(void);
 /* tuning overrides (0 = automatic): targets per thread in {1,2,4,8}, source splits >= 1 */
 SKB_API int skb_ctx_set_tuning(skb_ctx *ctx, int targets_per_thread, int source_splits);
 
+/* Stokeslet self-interaction with Newton's third law: when the sources are bit-identical to the leading targets
+ * (the fiber -> fiber block of System::apply_matvec, system.cpp:284-299) each pair's geometry is evaluated once
+ * for both directions.  mode: -1 automatic (default: on for >= 4096 such sources on single-GPU contexts),
+ * 0 never, 1 whenever applicable.  Results stay within the same 1e-12 gate; summation order differs from the
+ * plain kernel, and stays bitwise reproducible run to run. */
+SKB_API int skb_ctx_set_symmetric(skb_ctx *ctx, int mode);
+
 /* Pure DFMA micro-benchmark on the context's first device: returns achieved FP64 FMA/s * 2 (flop/s).
  * SURVEY.md section 8d asks for the measured FP64 roofline denominator next to the datasheet value. */
 SKB_API int skb_measure_fp64_peak(skb_ctx *ctx, double *flops_per_s);

@@ -42,12 +42,19 @@ def main():
             for kind, fdim, flop, name in ((0, 3, 28, "SL"), (1, 9, 40, "DL")):
                 ctx.set_sources(kind, rs)
                 f = rng.uniform(-1, 1, (ns, fdim))
-                for T in (0, 1, 2, 4, 8):
-                    for S in ((0,) if (T == 0 or QUICK) else (0, 4, 8, 16)):
-                        ctx.set_tuning(T, S)
+                for T in (-1, 0, 1, 2, 4, 8):
+                    for S in ((0,) if (T <= 0 or QUICK) else (0, 4, 8, 16)):
+                        if T == -1:  # symmetric (Newton's third law) kernel, Stokeslet self-interaction only
+                            if kind != 0 or nt < ns:
+                                continue
+                            ctx.set_symmetric(1)
+                            ctx.set_tuning(0, 0)
+                        else:
+                            ctx.set_symmetric(0)
+                            ctx.set_tuning(T, S)
                         k, t, st = run(ctx, kind, f)
                         pairs = ns * nt
-                        rec = dict(kind=name, n_src=ns, n_trg=nt, T=st["targets_per_thread"], S=st["source_splits"],
+                        rec = dict(kind=name + ("_sym" if T == -1 else ""), n_src=ns, n_trg=nt, T=st["targets_per_thread"], S=st["source_splits"],
                                    ctas=st["grid_ctas"], forced=(T, S), kernel_ms=round(k, 4), total_ms=round(t, 4),
                                    gpairs_s=round(pairs / k / 1e6, 1), tflops=round(flop * pairs / k / 1e9, 2),
                                    frac_probe=round(flop * pairs / (k * 1e-3) / peak, 3))

@@ -83,6 +83,7 @@ def library() -> C.CDLL:
         "skb_launch_count": ([], C.c_int64),
         "skb_ctx_set_tuning": ([ctxp, C.c_int, C.c_int], C.c_int),
         "skb_measure_fp64_peak": ([ctxp, C.POINTER(C.c_double)], C.c_int),
+        "skb_ctx_set_symmetric": ([ctxp, C.c_int], C.c_int),
         # include/skelly_b200_flow.h
         "skb_flow_create": ([C.c_int, C.POINTER(ctxp)], C.c_int),
         "skb_flow_destroy": ([ctxp], C.c_int),
@@ -256,6 +257,10 @@ class Context:
 
     def set_tuning(self, targets_per_thread=0, source_splits=0):
         _check(library().skb_ctx_set_tuning(self._h, int(targets_per_thread), int(source_splits)))
+
+    def set_symmetric(self, mode: int):
+        """-1 auto, 0 off, 1 on: Newton's-third-law kernel for sources that are the leading targets."""
+        _check(library().skb_ctx_set_symmetric(self._h, int(mode)))
 
     def measure_fp64_peak(self) -> float:
         v = C.c_double(0)

@@ -56,8 +56,10 @@ struct PairArgs {
     double *partial;       // [n_splits][n_trg*3]
     long long n_trg;
     long long n_src;       // valid sources (the last tile is only walked up to here, rounded up to even)
-    int n_src_tiles;       // n_src_pad / kSrcTile
+    int n_src_tiles;       // ceil(n_src / kSrcTile)
     int tiles_per_split;   // source tiles handled by one blockIdx.y
+    int diag_tiles;        // 0: off.  >0: block-diagonal mode -- target tile b only meets source tiles
+                           // [b*diag_tiles, (b+1)*diag_tiles) (the diagonal blocks the symmetric kernel leaves out)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -428,9 +430,10 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const long long t_base = (long long)blockIdx.x * kTileT;
-    const int first_tile = blockIdx.y * a.tiles_per_split;
+    const int per_cta = a.diag_tiles > 0 ? a.diag_tiles : a.tiles_per_split;
+    const int first_tile = a.diag_tiles > 0 ? (int)blockIdx.x * a.diag_tiles : (int)blockIdx.y * a.tiles_per_split;
     int n_tiles = a.n_src_tiles - first_tile;
-    n_tiles = n_tiles < a.tiles_per_split ? n_tiles : a.tiles_per_split;
+    n_tiles = n_tiles < per_cta ? n_tiles : per_cta;
     if (n_tiles < 0)
         n_tiles = 0;
     const char *gp = reinterpret_cast<const char *>(a.r_src) + (size_t)first_tile * L::pos_stage_bytes;

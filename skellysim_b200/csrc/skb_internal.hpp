@@ -39,7 +39,7 @@ DeviceInfo query_device(int dev);
 LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_src_tiles, int force_T, int force_S);
 int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const double *d_f_packed, long long n_src,
                     long long n_src_pad, const double *d_r_trg, long long n_trg, double *d_partial,
-                    const LaunchPlan &plan, cudaStream_t st);
+                    const LaunchPlan &plan, cudaStream_t st, int diag_tiles = 0);
 int launch_reduce(const double *d_partial, double *d_u, long long n_trg, int n_splits, double scale, int accumulate,
                   cudaStream_t st);
 
@@ -58,6 +58,11 @@ struct SourceSet {
     skb::DevBuf weights; // optional per-source quadrature weight folded into the Stokeslet strengths
     skb::DevBuf f_raw;   // strengths as shipped by the caller (3 or 9 per source; all-gather landing zone)
     skb::DevBuf f_packed;
+    // symmetric (Newton's third law) path of the Stokeslet self-interaction, sym_kernels.cuh
+    int self_state = -1;       // -1 unknown, 0 targets do not start with these sources, 1 they do
+    bool sym_plan_valid = false;
+    int sym_T = 0, sym_nb = 0, sym_items = 0;
+    skb::DevBuf sym_item_buf, sym_row_begin, sym_P, sym_F, sym_diag, sym_flag;
 };
 
 struct DeviceState {
@@ -73,6 +78,7 @@ struct skb_ctx {
     std::vector<DeviceState> devs;
     long long n_trg = -1;
     int force_T = 0, force_S = 0;
+    int sym_mode = -1; // -1 auto, 0 never, 1 whenever the sources are the leading targets
     skb_eval_stats stats{};
     bool kernel_events_pending = false; // device-pointer path: kernel_ms is read back lazily
     void *nccl = nullptr; // NcclGroup*, multi-device contexts only

@@ -5,6 +5,7 @@
 //
 // No CPU fallback exists here: every path ends in a CUDA launch or an error code.
 #include "pair_kernels.cuh"
+#include "sym_kernels.cuh"
 #include "skb_internal.hpp"
 
 #include <algorithm>
@@ -154,7 +155,7 @@ LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_sr
 
 int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const double *d_f_packed, long long n_src,
                     long long n_src_pad, const double *d_r_trg, long long n_trg, double *d_partial,
-                    const LaunchPlan &plan, cudaStream_t st) {
+                    const LaunchPlan &plan, cudaStream_t st, int diag_tiles) {
     PairArgs a;
     a.r_src = d_r_src;
     a.f_src = d_f_packed;
@@ -162,8 +163,10 @@ int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const
     a.partial = d_partial;
     a.n_trg = n_trg;
     a.n_src = n_src;
-    a.n_src_tiles = (int)(n_src_pad / kSrcTile);
+    a.n_src_tiles = (int)((n_src + kSrcTile - 1) / kSrcTile);
     a.tiles_per_split = plan.tiles_per_split;
+    a.diag_tiles = diag_tiles;
+    (void)n_src_pad;
     dim3 grid(plan.grid_x, plan.n_splits, 1);
     cudaError_t e = cudaSuccess;
 #define LAUNCH_CALL(KIND, T, MINB) e = launch_variant<KIND, T, MINB>(a, grid, st)
@@ -257,6 +260,8 @@ static int ctx_create_impl(const int *ids, int n, skb_ctx **out) {
     if (n < 1 || n > n_dev)
         return set_error(SKB_ERR_INVALID, "skb_ctx_create: n_gpus=%d but %d device(s) visible", n, n_dev);
     std::unique_ptr<skb_ctx> ctx(new skb_ctx);
+    if (const char *e = getenv("SKB_SYMMETRIC")) // default of skb_ctx_set_symmetric for contexts created from now on
+        ctx->sym_mode = std::max(-1, std::min(1, atoi(e)));
     ctx->devs.resize(n);
     for (int g = 0; g < n; ++g) {
         DeviceState &d = ctx->devs[g];
@@ -321,6 +326,12 @@ int skb_ctx_destroy(skb_ctx *ctx) {
             s.r.release();
             s.normals.release();
             s.weights.release();
+            s.sym_item_buf.release();
+            s.sym_row_begin.release();
+            s.sym_P.release();
+            s.sym_F.release();
+            s.sym_diag.release();
+            s.sym_flag.release();
             s.f_raw.release();
             s.f_packed.release();
         }
@@ -350,6 +361,13 @@ int skb_ctx_set_tuning(skb_ctx *ctx, int T, int S) {
         return set_error(SKB_ERR_INVALID, "tuning: targets_per_thread must be 0/1/2/4/8, source_splits >= 0");
     ctx->force_T = T;
     ctx->force_S = S;
+    return SKB_OK;
+}
+
+int skb_ctx_set_symmetric(skb_ctx *ctx, int mode) {
+    if (!ctx || mode < -1 || mode > 1)
+        return set_error(SKB_ERR_INVALID, "skb_ctx_set_symmetric: mode must be -1 (auto), 0 (off) or 1 (on)");
+    ctx->sym_mode = mode;
     return SKB_OK;
 }
 
@@ -396,6 +414,8 @@ static int set_targets_impl(skb_ctx *ctx, const double *r_trg, long long n_trg, 
         return set_error(SKB_ERR_INVALID, "device-pointer entry points need a single-GPU context");
     partition_targets(ctx, n_trg);
     for (auto &d : ctx->devs) {
+        d.src[0].self_state = -1;
+        d.src[1].self_state = -1;
         if (d.n_trg == 0)
             continue;
         CUDA_TRY(cudaSetDevice(d.info.dev));
@@ -424,7 +444,8 @@ static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long lo
         return set_error(SKB_ERR_INVALID, "set_sources: n_src=%lld exceeds the supported range", n_src);
     if (on_device && ctx->devs.size() != 1)
         return set_error(SKB_ERR_INVALID, "device-pointer entry points need a single-GPU context");
-    const long long n_pad = ((n_src + kSrcTile - 1) / kSrcTile) * kSrcTile;
+    const long long kPadTo = 1024; // multiple of every source tile / symmetric block size in use
+    const long long n_pad = ((n_src + kPadTo - 1) / kPadTo) * kPadTo;
     const int fdim_raw = kind == SKB_STOKESLET ? 3 : 9;
     const int fdim_packed = kind == SKB_STOKESLET ? 3 : 6;
     const long long P = (long long)ctx->devs.size();
@@ -435,6 +456,8 @@ static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long lo
         s.n_pad = n_pad;
         s.has_normals = false;
         s.has_weights = false;
+        s.self_state = -1;
+        s.sym_plan_valid = false;
         if (n_src == 0)
             continue;
         CUDA_TRY(cudaSetDevice(d.info.dev));
@@ -467,6 +490,159 @@ static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long lo
 // ------------------------------------------------------------------------------------------------
 
 // device-side part for one device: pack -> pair kernel -> reduce into d_u_out.  f_raw already resident.
+
+// ------------------------------------------------------------------------------------------------
+// symmetric Stokeslet self-interaction (sym_kernels.cuh)
+// ------------------------------------------------------------------------------------------------
+namespace skb {
+
+__global__ void self_check_kernel(const double *__restrict__ a, const double *__restrict__ b, long long n,
+                                  int *__restrict__ differs) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n && __double_as_longlong(a[i]) != __double_as_longlong(b[i]))
+        *differs = 1;
+}
+
+template <int T, int MINB> static cudaError_t launch_sym(const SymArgs &a, int n_items, cudaStream_t st) {
+    using L = SymSmem<T>;
+    auto kern = pair_sym_kernel<T, MINB>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total_bytes);
+        if (e != cudaSuccess)
+            return e;
+        attr_set[dev] = true;
+    }
+    kern<<<n_items, kSymThreads, L::total_bytes, st>>>(a);
+    return cudaGetLastError();
+}
+
+static long long sym_mem_budget() {
+    const char *e = getenv("SKB_SYM_MAX_BYTES");
+    return e ? atoll(e) : (8LL << 30);
+}
+
+// Decide whether the symmetric path applies and make sure its plan / buffers exist.
+static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) {
+    *use = 0;
+    SourceSet &s = d.src[SKB_STOKESLET];
+    const int T = 4;
+    const long long block = (long long)kSymThreads * T;
+    if (s.n < 8 * block && ctx->sym_mode != 1)
+        return SKB_OK; // too small to matter
+    if (s.n < 2 * block || d.n_trg < s.n)
+        return SKB_OK;
+    const long long nb = s.n_pad / block; // n_pad is a multiple of 1024
+    if ((long long)nb * s.n_pad * 24 > sym_mem_budget())
+        return SKB_OK;
+    if (s.self_state < 0) { // positions changed: are the first n_src targets bit-identical to the sources?
+        SKB_TRY(s.sym_flag.ensure(sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(s.sym_flag.ptr, 0, sizeof(int), st));
+        const long long n3 = 3 * s.n;
+        self_check_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>((const double *)d.r_trg.ptr,
+                                                                        (const double *)s.r.ptr, n3,
+                                                                        (int *)s.sym_flag.ptr);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        int differs = 1;
+        CUDA_TRY(cudaMemcpyAsync(&differs, s.sym_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        s.self_state = differs ? 0 : 1;
+    }
+    if (s.self_state != 1)
+        return SKB_OK;
+    if (!s.sym_plan_valid || s.sym_T != T || s.sym_nb != (int)nb) {
+        // work items: (I, [J0,J1)) over the strict upper triangle of blocks, rows cut into near-equal chunks
+        int occ = 3;
+        const long long pairs = nb * (nb - 1) / 2;
+        const long long slots = (long long)d.info.num_sms * occ;
+        long long chunk = std::max<long long>(1, pairs / (slots * 6));
+        std::vector<SymItem> items;
+        std::vector<int> row_begin(nb + 1, 0);
+        for (int I = 0; I < nb; ++I) {
+            row_begin[I] = (int)items.size();
+            const int len = (int)nb - 1 - I;
+            if (len <= 0)
+                continue;
+            const int n_chunks = (int)((len + chunk - 1) / chunk);
+            for (int c = 0; c < n_chunks; ++c) {
+                SymItem it;
+                it.I = I;
+                it.J0 = I + 1 + (int)((long long)len * c / n_chunks);
+                it.J1 = I + 1 + (int)((long long)len * (c + 1) / n_chunks);
+                it.slot = (int)items.size();
+                items.push_back(it);
+            }
+        }
+        row_begin[nb] = (int)items.size();
+        // launch the large items first (slot keeps the row-major position for the reduction)
+        std::vector<SymItem> order = items;
+        std::stable_sort(order.begin(), order.end(),
+                         [](const SymItem &a, const SymItem &b) { return (a.J1 - a.J0) > (b.J1 - b.J0); });
+        SKB_TRY(s.sym_item_buf.ensure(order.size() * sizeof(SymItem) + 16));
+        SKB_TRY(s.sym_row_begin.ensure(row_begin.size() * sizeof(int)));
+        SKB_TRY(s.sym_P.ensure((size_t)nb * (size_t)s.n_pad * 24));
+        SKB_TRY(s.sym_F.ensure(order.size() * (size_t)block * 24 + 16));
+        SKB_TRY(s.sym_diag.ensure((size_t)s.n_pad * 24));
+        CUDA_TRY(cudaMemcpyAsync(s.sym_item_buf.ptr, order.data(), order.size() * sizeof(SymItem),
+                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(s.sym_row_begin.ptr, row_begin.data(), row_begin.size() * sizeof(int),
+                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st)); // host vectors go out of scope
+        s.sym_T = T;
+        s.sym_nb = (int)nb;
+        s.sym_items = (int)order.size();
+        s.sym_plan_valid = true;
+    }
+    *use = 1;
+    return SKB_OK;
+}
+
+// u[0 : 3 n_src] (=|+=) scale * sum over the square block, using the plan above.  Strengths are packed already.
+static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulate, cudaStream_t st, double scale_mul,
+                    int *launches) {
+    SourceSet &s = d.src[SKB_STOKESLET];
+    const int T = s.sym_T;
+    const long long block = (long long)kSymThreads * T;
+    SymArgs a;
+    a.r = (const double *)s.r.ptr;
+    a.f = (const double *)s.f_packed.ptr;
+    a.items = (const SymItem *)s.sym_item_buf.ptr;
+    a.P = (double *)s.sym_P.ptr;
+    a.F = (double *)s.sym_F.ptr;
+    a.n_pad = s.n_pad;
+    a.nb = s.sym_nb;
+    cudaError_t e = launch_sym<4, 3>(a, s.sym_items, st);
+    if (e != cudaSuccess)
+        return set_error(SKB_ERR_CUDA, "pair_sym_kernel launch failed: %s", cudaGetErrorString(e));
+    count_launch(1);
+    // block diagonal with the plain kernel: target tile b (128*T nodes) x its own T source tiles
+    LaunchPlan dp;
+    dp.T = T;
+    dp.n_splits = 1;
+    dp.tiles_per_split = T;
+    dp.grid_x = (unsigned)((s.n + block - 1) / block);
+    SKB_TRY(launch_pair_sum(d.info, SKB_STOKESLET, (const double *)s.r.ptr, (const double *)s.f_packed.ptr, s.n,
+                            s.n_pad, (const double *)s.r.ptr, s.n, (double *)s.sym_diag.ptr, dp, st, T));
+    const long long n3 = 3 * s.n;
+    const double scale = scale_mul / (8.0 * M_PI);
+    sym_reduce_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(
+        (const double *)s.sym_diag.ptr, (const double *)s.sym_P.ptr, (const double *)s.sym_F.ptr,
+        (const int *)s.sym_row_begin.ptr, (int)block, s.n_pad, n3, scale, accumulate, d_u_out);
+    e = cudaGetLastError();
+    if (e != cudaSuccess)
+        return set_error(SKB_ERR_CUDA, "sym_reduce_kernel launch failed: %s", cudaGetErrorString(e));
+    count_launch(1);
+    if (launches)
+        *launches += 3;
+    (void)ctx;
+    return SKB_OK;
+}
+
+} // namespace skb
+
 namespace skb {
 int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, const double *d_f_raw, double two_eta,
                    double *d_u_out, int accumulate, cudaStream_t st, bool record_events, int *launches,
@@ -493,21 +669,46 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
     }
     CUDA_TRY(cudaGetLastError());
     count_launch(1);
-    // 2. pair sums
-    LaunchPlan plan = plan_launch(d.info, kind, d.n_trg, (int)(s.n_pad / kSrcTile), ctx->force_T, ctx->force_S);
-    SKB_TRY(d.partial.ensure((size_t)plan.n_splits * (size_t)d.n_trg * 24));
     if (record_events)
         CUDA_TRY(cudaEventRecord(d.ev_k0, st));
+    // 2. pair sums
+    // ---- symmetric path: sources are the leading targets (fiber -> fiber block of apply_matvec) ----
+    long long n_sym = 0;
+    if (kind == SKB_STOKESLET && ctx->devs.size() == 1 && ctx->sym_mode != 0) {
+        int use = 0;
+        SKB_TRY(sym_prepare(ctx, d, st, &use));
+        if (use) {
+            SKB_TRY(sym_eval(ctx, d, d_u_out, accumulate, st, scale_mul, launches));
+            n_sym = s.n;
+            if (plan_out) {
+                plan_out->T = s.sym_T;
+                plan_out->n_splits = 1;
+                plan_out->grid_x = (unsigned)s.sym_items;
+                plan_out->tiles_per_split = 0;
+            }
+            if (d.n_trg == n_sym) {
+                if (record_events)
+                    CUDA_TRY(cudaEventRecord(d.ev_k1, st));
+                return SKB_OK;
+            }
+        }
+    }
+    const long long n_trg_std = d.n_trg - n_sym; // targets beyond the square block go through the plain kernel
+    const double *d_r_trg_std = (const double *)d.r_trg.ptr + 3 * n_sym;
+    double *d_u_std = d_u_out + 3 * n_sym;
+    LaunchPlan plan = plan_launch(d.info, kind, n_trg_std, (int)((s.n + kSrcTile - 1) / kSrcTile), ctx->force_T,
+                                  ctx->force_S);
+    SKB_TRY(d.partial.ensure((size_t)plan.n_splits * (size_t)n_trg_std * 24));
     SKB_TRY(launch_pair_sum(d.info, kind, (const double *)s.r.ptr, (const double *)s.f_packed.ptr, s.n, s.n_pad,
-                            (const double *)d.r_trg.ptr, d.n_trg, (double *)d.partial.ptr, plan, st));
+                            d_r_trg_std, n_trg_std, (double *)d.partial.ptr, plan, st));
     if (record_events)
         CUDA_TRY(cudaEventRecord(d.ev_k1, st));
     // 3. combine splits, scale: 1/(8 pi) (kernels.cu:59) or -3/(8 pi) (kernels.cu:26,51)
     const double scale = scale_mul * (kind == SKB_STOKESLET ? 1.0 : -3.0) / (8.0 * M_PI);
-    SKB_TRY(launch_reduce((const double *)d.partial.ptr, d_u_out, d.n_trg, plan.n_splits, scale, accumulate, st));
+    SKB_TRY(launch_reduce((const double *)d.partial.ptr, d_u_std, n_trg_std, plan.n_splits, scale, accumulate, st));
     if (launches)
         *launches += 3;
-    if (plan_out)
+    if (plan_out && n_sym == 0)
         *plan_out = plan;
     return SKB_OK;
 }
