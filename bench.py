@@ -310,6 +310,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-matvec", action="store_true")
+    ap.add_argument("--no-symmetric", action="store_true", help="plain kernel only (A/B)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -340,19 +341,32 @@ def main():
     r_src_all = fib
     r_trg_all = np.concatenate([fib, shell])
     n_src, n_trg = r_src_all.shape[0], r_trg_all.shape[0]
-    from skellysim_b200.distributed import RankPartition, allgather_strengths
+    from skellysim_b200.distributed import RankPartition, allgather_strengths, block_range
     part = RankPartition(n_src, n_trg, world, rank)
     src_chunk = part.src_chunk
-    (s0, s1), (t0_, t1_) = part.src_range, part.trg_range
+    s0, s1 = part.src_range
     if part.gathered_rows != n_src:
         raise SystemExit("bench workloads keep n_src divisible by the rank count")
-    my_trg = np.ascontiguousarray(r_trg_all[t0_:t1_])
+    # Target list of a rank: ALL fiber nodes first (the self-interaction block, evaluated with the symmetric kernel:
+    # each rank owns a serpentine set of block rows and produces partial sums for every fiber node), then the rank's
+    # block of the remaining (shell) targets.  Partial sums are combined by one all-reduce per step.
+    sym_layout = not args.no_symmetric
+    if sym_layout:
+        n_rem = n_trg - n_src
+        rb, re_ = block_range(n_rem, world, rank)
+        my_trg = np.ascontiguousarray(np.concatenate([r_src_all, r_trg_all[n_src + rb:n_src + re_]]))
+    else:  # plain kernel: every rank owns a block of the whole target list, no reduction needed
+        tb, te = part.trg_range
+        my_trg = np.ascontiguousarray(r_trg_all[tb:te])
     n_my_trg = my_trg.shape[0]
     rng = np.random.default_rng(7)
     f_all = rng.uniform(-1, 1, (n_src, 3))  # trapezoid-weighted forces, U[-1,1]
 
     # device state: positions once ("per timestep"); strengths per step
     ctx = skb.Context(1, device_ids=[local_rank])
+    if args.no_symmetric:
+        ctx.set_symmetric(0)
+    ctx.set_sym_partition(rank, world)
     stream = torch.cuda.current_stream().cuda_stream  # kernels are launched on torch's current stream
     d_rsrc = torch.from_numpy(r_src_all).to(dev)
     d_rtrg = torch.from_numpy(my_trg).to(dev)
@@ -364,6 +378,7 @@ def main():
     h_f_mine[:s1 - s0] = torch.from_numpy(f_all[s0:s1])
     d_f_mine.copy_(h_f_mine, non_blocking=True)
     d_u = torch.empty((max(n_my_trg, 1), 3), dtype=torch.float64, device=dev)
+    d_u_fib = d_u[:n_src]
     h_u = torch.empty((max(n_my_trg, 1), 3), dtype=torch.float64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     torch.cuda.synchronize()
@@ -375,6 +390,8 @@ def main():
     def step_device():
         allgather_strengths(d_f_gather, d_f_mine)  # ONE NCCL all-gather per step (no-op at world == 1)
         ctx.eval_device(skb.KERNEL_STOKESLET, d_f_gather.data_ptr(), d_u.data_ptr(), False, stream)
+        if world > 1 and sym_layout:  # fiber rows are per-rank partial sums of the symmetric block rows
+            dist.all_reduce(d_u_fib)
 
     def step_e2e():
         d_f_mine.copy_(h_f_mine, non_blocking=True)
@@ -411,6 +428,9 @@ def main():
     for _ in range(args.warmup):
         step_device()
     torch.cuda.synchronize()
+    if sym_layout and not ctx.last_eval_was_symmetric():
+        raise SystemExit("symmetric layout requested but the symmetric kernel was not used (problem too small?); "
+                         "run with --no-symmetric")
     acc = None
     if rank == 0:
         import oracle as orc
@@ -428,7 +448,8 @@ def main():
     e2e_ms, _, _ = timed(step_e2e, args.steps)
 
     pairs_total = float(n_src) * float(n_trg)
-    pairs_rank = float(n_src) * float(n_my_trg)
+    pairs_rank = (float(n_src) * float(n_src) / world + float(n_src) * float(n_my_trg - n_src)) if sym_layout \
+        else float(n_src) * float(n_my_trg)
     ms_per_step = tot_ms / args.steps
     value = pairs_total / (ms_per_step * 1e-3)
     e2e_val = pairs_total / (e2e_ms / args.steps * 1e-3)
@@ -453,12 +474,14 @@ def main():
         # + positions 24 B/source + targets 24 B read + 24 B written per target
         alg_bytes = 24.0 * n_src + 24.0 * n_src + 48.0 * n_my_trg
         roofline = {
-            "bound": "fp64", "kernel": f"pair_sum_kernel<stokeslet,T={stats['targets_per_thread']}>",
+            "bound": "fp64",
+            "kernel": ("pair_sym_kernel<T=4> (self block, 16 FP64 instr/pair) + pair_sum_kernel (remainder)"
+                       if sym_layout else f"pair_sum_kernel<stokeslet,T={stats['targets_per_thread']}>"),
             "achieved": achieved / 1e12, "peak": peak / 1e12, "unit": "TFLOP/s", "frac": achieved / peak,
             "peak_source": "measured on this GPU by skb_measure_fp64_peak (register-resident DFMA loop)",
             "peak_nominal": NOMINAL_FP64_TFLOPS, "frac_of_nominal": achieved / 1e12 / NOMINAL_FP64_TFLOPS,
             "flop_per_pair": SL_FLOP_PER_PAIR, "kernel_ms": k_ms,
-            "fp64_instr_per_pair": 22,
+            "fp64_instr_per_pair": 16 if sym_layout else 22,
             "hbm": {"achieved": alg_bytes / (k_ms * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
                     "frac": alg_bytes / (k_ms * 1e-3) / 1e9 / hbm_peak, "peak_source": hbm_src,
                     "algorithmic_bytes_per_launch": alg_bytes},
@@ -472,14 +495,20 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": workload_name(args.workload, n_fib, n_shell), "n_src": n_src, "n_trg": n_trg,
-                       "pairs_per_step": pairs_total, "parallelism": f"targets+sources block-partitioned x{world}"
-                       + (", 1 NCCL all-gather of strengths per step" if world > 1 else ""),
+                       "pairs_per_step": pairs_total,
+                       "parallelism": (f"symmetric block rows (serpentine) + remainder targets partitioned x{world}"
+                                       + (", 1 NCCL all-gather of strengths + 1 all-reduce of fiber velocities per step"
+                                          if world > 1 else "")) if sym_layout else
+                       (f"targets+sources block-partitioned x{world}"
+                        + (", 1 NCCL all-gather of strengths per step" if world > 1 else "")),
+                       "kernel": "Newton's-third-law symmetric kernel on the fiber-fiber block" if sym_layout
+                       else "plain kernel",
                        "l2": "flushed between timed steps (256 MiB memset, untimed)",
                        "timing": "per-step CUDA events on the launch stream, summed; max over ranks",
                        "positions": "device-resident across steps (constant within a timestep, system.cpp:486-489)"},
             "e2e": {"value": e2e_val, "unit": "pairs/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(h_f_mine.numel() * 8 * world),
-                    "d2h_bytes_per_step": int(n_trg * 24),
+                    "d2h_bytes_per_step": int((world * n_src + (n_trg - n_src)) * 24 if sym_layout else n_trg * 24),
                     "path": "pinned host strengths -> H2D -> (all-gather) -> skb_eval_device -> D2H velocities"},
             "gpu_launches": launches_all,
             "launches_per_step": launches_all / args.steps / world,

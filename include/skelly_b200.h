@@ -138,6 +138,13 @@ SKB_API int skb_ctx_set_tuning(skb_ctx *ctx, int targets_per_thread, int source_
  * 0 never, 1 whenever applicable.  Results stay within the same 1e-12 gate; summation order differs from the
  * plain kernel, and stays bitwise reproducible run to run. */
 SKB_API int skb_ctx_set_symmetric(skb_ctx *ctx, int mode);
+/* One rank per GPU with the symmetric kernel: this context evaluates only the block rows of the self-interaction
+ * owned by `part` (of `n_parts`, serpentine over rows).  The leading n_src rows of the result are then PARTIAL sums:
+ * the caller adds the parts (one all-reduce of 24 B x n_src per evaluation); rows beyond n_src are complete.  With
+ * n_parts == 1 (default) nothing changes.  Only takes effect when the symmetric kernel is used. */
+SKB_API int skb_ctx_set_sym_partition(skb_ctx *ctx, int part, int n_parts);
+/* 1 if the last Stokeslet evaluation of this context went through the symmetric kernel, else 0 */
+SKB_API int skb_ctx_last_eval_was_symmetric(const skb_ctx *ctx, int *yes);
 
 /* Pure DFMA micro-benchmark on the context's first device: returns achieved FP64 FMA/s * 2 (flop/s).
  * SURVEY.md section 8d asks for the measured FP64 roofline denominator next to the datasheet value. */

@@ -84,6 +84,8 @@ def library() -> C.CDLL:
         "skb_ctx_set_tuning": ([ctxp, C.c_int, C.c_int], C.c_int),
         "skb_measure_fp64_peak": ([ctxp, C.POINTER(C.c_double)], C.c_int),
         "skb_ctx_set_symmetric": ([ctxp, C.c_int], C.c_int),
+        "skb_ctx_set_sym_partition": ([ctxp, C.c_int, C.c_int], C.c_int),
+        "skb_ctx_last_eval_was_symmetric": ([ctxp, C.POINTER(C.c_int)], C.c_int),
         # include/skelly_b200_flow.h
         "skb_flow_create": ([C.c_int, C.POINTER(ctxp)], C.c_int),
         "skb_flow_destroy": ([ctxp], C.c_int),
@@ -261,6 +263,16 @@ class Context:
     def set_symmetric(self, mode: int):
         """-1 auto, 0 off, 1 on: Newton's-third-law kernel for sources that are the leading targets."""
         _check(library().skb_ctx_set_symmetric(self._h, int(mode)))
+
+    def set_sym_partition(self, part: int, n_parts: int):
+        """One rank per GPU: evaluate only the block rows of the self-interaction owned by `part`; the leading
+        n_src rows of the result are partial sums to be all-reduced over the parts."""
+        _check(library().skb_ctx_set_sym_partition(self._h, int(part), int(n_parts)))
+
+    def last_eval_was_symmetric(self) -> bool:
+        y = C.c_int(0)
+        _check(library().skb_ctx_last_eval_was_symmetric(self._h, C.byref(y)))
+        return bool(y.value)
 
     def measure_fp64_peak(self) -> float:
         v = C.c_double(0)

@@ -61,13 +61,15 @@ struct SourceSet {
     // symmetric (Newton's third law) path of the Stokeslet self-interaction, sym_kernels.cuh
     int self_state = -1;       // -1 unknown, 0 targets do not start with these sources, 1 they do
     bool sym_plan_valid = false;
-    int sym_T = 0, sym_nb = 0, sym_items = 0;
+    int sym_T = 0, sym_nb = 0, sym_items = 0, sym_part = 0, sym_parts = 1;
     skb::DevBuf sym_item_buf, sym_row_begin, sym_P, sym_F, sym_diag, sym_flag;
 };
 
 struct DeviceState {
     skb::DeviceInfo info;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;              // remainder targets run beside the symmetric kernel
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     long long trg_begin = 0, n_trg = 0; // this device's block of the global target list
     skb::DevBuf r_trg, u, partial, scratch;
@@ -79,6 +81,8 @@ struct skb_ctx {
     long long n_trg = -1;
     int force_T = 0, force_S = 0;
     int sym_mode = -1; // -1 auto, 0 never, 1 whenever the sources are the leading targets
+    bool last_was_sym = false;
+    int sym_part = 0, sym_parts = 1; // this context evaluates block rows owned by part `sym_part` of `sym_parts`
     skb_eval_stats stats{};
     bool kernel_events_pending = false; // device-pointer path: kernel_ms is read back lazily
     void *nccl = nullptr; // NcclGroup*, multi-device contexts only

@@ -274,6 +274,9 @@ static int ctx_create_impl(const int *ids, int n, skb_ctx **out) {
             return set_error(SKB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
                              d.info.cc_major, d.info.cc_minor);
         CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.aux_stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreate(&d.ev_t0));
         CUDA_TRY(cudaEventCreate(&d.ev_t1));
         CUDA_TRY(cudaEventCreate(&d.ev_k0));
@@ -339,6 +342,9 @@ int skb_ctx_destroy(skb_ctx *ctx) {
         if (d.ev_t1) cudaEventDestroy(d.ev_t1);
         if (d.ev_k0) cudaEventDestroy(d.ev_k0);
         if (d.ev_k1) cudaEventDestroy(d.ev_k1);
+        if (d.ev_fork) cudaEventDestroy(d.ev_fork);
+        if (d.ev_join) cudaEventDestroy(d.ev_join);
+        if (d.aux_stream) cudaStreamDestroy(d.aux_stream);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
     if (ctx->nccl)
@@ -368,6 +374,23 @@ int skb_ctx_set_symmetric(skb_ctx *ctx, int mode) {
     if (!ctx || mode < -1 || mode > 1)
         return set_error(SKB_ERR_INVALID, "skb_ctx_set_symmetric: mode must be -1 (auto), 0 (off) or 1 (on)");
     ctx->sym_mode = mode;
+    return SKB_OK;
+}
+
+int skb_ctx_last_eval_was_symmetric(const skb_ctx *ctx, int *yes) {
+    if (!ctx || !yes)
+        return set_error(SKB_ERR_INVALID, "skb_ctx_last_eval_was_symmetric: NULL");
+    *yes = ctx->last_was_sym ? 1 : 0;
+    return SKB_OK;
+}
+
+int skb_ctx_set_sym_partition(skb_ctx *ctx, int part, int n_parts) {
+    if (!ctx || n_parts < 1 || part < 0 || part >= n_parts)
+        return set_error(SKB_ERR_INVALID, "skb_ctx_set_sym_partition: need 0 <= part < n_parts");
+    if (ctx->devs.size() != 1)
+        return set_error(SKB_ERR_INVALID, "skb_ctx_set_sym_partition: single-GPU contexts only");
+    ctx->sym_part = part;
+    ctx->sym_parts = n_parts;
     return SKB_OK;
 }
 
@@ -553,10 +576,11 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
     }
     if (s.self_state != 1)
         return SKB_OK;
-    if (!s.sym_plan_valid || s.sym_T != T || s.sym_nb != (int)nb) {
+    if (!s.sym_plan_valid || s.sym_T != T || s.sym_nb != (int)nb || s.sym_part != ctx->sym_part ||
+        s.sym_parts != ctx->sym_parts) {
         // work items: (I, [J0,J1)) over the strict upper triangle of blocks, rows cut into near-equal chunks
         int occ = 3;
-        const long long pairs = nb * (nb - 1) / 2;
+        const long long pairs = nb * (nb - 1) / 2 / ctx->sym_parts;
         const long long slots = (long long)d.info.num_sms * occ;
         long long chunk = std::max<long long>(1, pairs / (slots * 6));
         std::vector<SymItem> items;
@@ -564,7 +588,7 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
         for (int I = 0; I < nb; ++I) {
             row_begin[I] = (int)items.size();
             const int len = (int)nb - 1 - I;
-            if (len <= 0)
+            if (len <= 0 || sym_row_owner(I, ctx->sym_parts) != ctx->sym_part)
                 continue;
             const int n_chunks = (int)((len + chunk - 1) / chunk);
             for (int c = 0; c < n_chunks; ++c) {
@@ -594,6 +618,8 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
         s.sym_T = T;
         s.sym_nb = (int)nb;
         s.sym_items = (int)order.size();
+        s.sym_part = ctx->sym_part;
+        s.sym_parts = ctx->sym_parts;
         s.sym_plan_valid = true;
     }
     *use = 1;
@@ -614,10 +640,13 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
     a.F = (double *)s.sym_F.ptr;
     a.n_pad = s.n_pad;
     a.nb = s.sym_nb;
-    cudaError_t e = launch_sym<4, 3>(a, s.sym_items, st);
-    if (e != cudaSuccess)
-        return set_error(SKB_ERR_CUDA, "pair_sym_kernel launch failed: %s", cudaGetErrorString(e));
-    count_launch(1);
+    cudaError_t e = cudaSuccess;
+    if (s.sym_items > 0) {
+        e = launch_sym<4, 3>(a, s.sym_items, st);
+        if (e != cudaSuccess)
+            return set_error(SKB_ERR_CUDA, "pair_sym_kernel launch failed: %s", cudaGetErrorString(e));
+        count_launch(1);
+    }
     // block diagonal with the plain kernel: target tile b (128*T nodes) x its own T source tiles
     LaunchPlan dp;
     dp.T = T;
@@ -630,7 +659,8 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
     const double scale = scale_mul / (8.0 * M_PI);
     sym_reduce_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(
         (const double *)s.sym_diag.ptr, (const double *)s.sym_P.ptr, (const double *)s.sym_F.ptr,
-        (const int *)s.sym_row_begin.ptr, (int)block, s.n_pad, n3, scale, accumulate, d_u_out);
+        (const int *)s.sym_row_begin.ptr, (int)block, s.n_pad, n3, scale, accumulate, d_u_out, s.sym_part,
+        s.sym_parts);
     e = cudaGetLastError();
     if (e != cudaSuccess)
         return set_error(SKB_ERR_CUDA, "sym_reduce_kernel launch failed: %s", cudaGetErrorString(e));
@@ -677,38 +707,51 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
     if (kind == SKB_STOKESLET && ctx->devs.size() == 1 && ctx->sym_mode != 0) {
         int use = 0;
         SKB_TRY(sym_prepare(ctx, d, st, &use));
-        if (use) {
-            SKB_TRY(sym_eval(ctx, d, d_u_out, accumulate, st, scale_mul, launches));
+        if (use)
             n_sym = s.n;
-            if (plan_out) {
-                plan_out->T = s.sym_T;
-                plan_out->n_splits = 1;
-                plan_out->grid_x = (unsigned)s.sym_items;
-                plan_out->tiles_per_split = 0;
-            }
-            if (d.n_trg == n_sym) {
-                if (record_events)
-                    CUDA_TRY(cudaEventRecord(d.ev_k1, st));
-                return SKB_OK;
-            }
-        }
     }
     const long long n_trg_std = d.n_trg - n_sym; // targets beyond the square block go through the plain kernel
     const double *d_r_trg_std = (const double *)d.r_trg.ptr + 3 * n_sym;
     double *d_u_std = d_u_out + 3 * n_sym;
-    LaunchPlan plan = plan_launch(d.info, kind, n_trg_std, (int)((s.n + kSrcTile - 1) / kSrcTile), ctx->force_T,
-                                  ctx->force_S);
-    SKB_TRY(d.partial.ensure((size_t)plan.n_splits * (size_t)n_trg_std * 24));
-    SKB_TRY(launch_pair_sum(d.info, kind, (const double *)s.r.ptr, (const double *)s.f_packed.ptr, s.n, s.n_pad,
-                            d_r_trg_std, n_trg_std, (double *)d.partial.ptr, plan, st));
+    const double scale = scale_mul * (kind == SKB_STOKESLET ? 1.0 : -3.0) / (8.0 * M_PI);
+    cudaStream_t st_std = st;
+    if (n_sym > 0 && n_trg_std > 0) { // fork: the remainder fills the SMs the symmetric kernel's tail leaves idle
+        CUDA_TRY(cudaEventRecord(d.ev_fork, st));
+        CUDA_TRY(cudaStreamWaitEvent(d.aux_stream, d.ev_fork, 0));
+        st_std = d.aux_stream;
+    }
+    LaunchPlan plan{};
+    // the long symmetric kernel is launched first so that the remainder's CTAs are dispatched into its tail
+    if (n_sym > 0)
+        SKB_TRY(sym_eval(ctx, d, d_u_out, accumulate, st, scale_mul, launches));
+    if (n_trg_std > 0) {
+        plan = plan_launch(d.info, kind, n_trg_std, (int)((s.n + kSrcTile - 1) / kSrcTile), ctx->force_T, ctx->force_S);
+        SKB_TRY(d.partial.ensure((size_t)plan.n_splits * (size_t)n_trg_std * 24));
+        SKB_TRY(launch_pair_sum(d.info, kind, (const double *)s.r.ptr, (const double *)s.f_packed.ptr, s.n, s.n_pad,
+                                d_r_trg_std, n_trg_std, (double *)d.partial.ptr, plan, st_std));
+        // 3. combine splits, scale: 1/(8 pi) (kernels.cu:59) or -3/(8 pi) (kernels.cu:26,51)
+        SKB_TRY(launch_reduce((const double *)d.partial.ptr, d_u_std, n_trg_std, plan.n_splits, scale, accumulate,
+                              st_std));
+        if (launches)
+            *launches += 2;
+    }
+    if (kind == SKB_STOKESLET)
+        ctx->last_was_sym = n_sym > 0;
+    if (n_sym > 0) {
+        if (n_trg_std > 0) { // join
+            CUDA_TRY(cudaEventRecord(d.ev_join, d.aux_stream));
+            CUDA_TRY(cudaStreamWaitEvent(st, d.ev_join, 0));
+        }
+        plan.T = s.sym_T;
+        plan.n_splits = 1;
+        plan.grid_x = (unsigned)s.sym_items;
+        plan.tiles_per_split = 0;
+    }
     if (record_events)
         CUDA_TRY(cudaEventRecord(d.ev_k1, st));
-    // 3. combine splits, scale: 1/(8 pi) (kernels.cu:59) or -3/(8 pi) (kernels.cu:26,51)
-    const double scale = scale_mul * (kind == SKB_STOKESLET ? 1.0 : -3.0) / (8.0 * M_PI);
-    SKB_TRY(launch_reduce((const double *)d.partial.ptr, d_u_std, n_trg_std, plan.n_splits, scale, accumulate, st));
     if (launches)
-        *launches += 3;
-    if (plan_out && n_sym == 0)
+        *launches += 1; // the pack kernel
+    if (plan_out)
         *plan_out = plan;
     return SKB_OK;
 }

@@ -237,20 +237,29 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
     }
 }
 
+// Block row I of the upper triangle belongs to part owner(I): serpentine assignment, so that every part gets the
+// same number of long and short rows (one rank per GPU: each rank evaluates its rows, partial sums are all-reduced).
+__host__ __device__ inline int sym_row_owner(int I, int n_parts) {
+    const int k = I / n_parts, m = I % n_parts;
+    return (k & 1) ? n_parts - 1 - m : m;
+}
+
 // Fixed-order combination for the symmetric path, one thread per velocity component of node `n` (block b):
 //   u = (acc ? u : 0) + scale * ( diag[n] + sum_{I < b} P[I][n] + sum_{items of row b} F[item][n - b*block] )
 __global__ void sym_reduce_kernel(const double *__restrict__ diag, const double *__restrict__ P,
                                   const double *__restrict__ F, const int *__restrict__ row_item_begin, int block,
                                   long long n_pad, long long n_valid3, double scale, int accumulate,
-                                  double *__restrict__ u) {
+                                  double *__restrict__ u, int part, int n_parts) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // component index 3*n + k
     if (i >= n_valid3)
         return;
     const long long node = i / 3;
     const int b = (int)(node / block);
-    double acc = diag[i];
+    // only rows owned by this part were evaluated here (n_parts == 1: all of them)
+    double acc = (sym_row_owner(b, n_parts) == part) ? diag[i] : 0.0;
     for (int I = 0; I < b; ++I)
-        acc += P[((size_t)I * n_pad) * 3 + i];
+        if (sym_row_owner(I, n_parts) == part)
+            acc += P[((size_t)I * n_pad) * 3 + i];
     const long long local = i - (long long)b * block * 3;
     for (int it = row_item_begin[b]; it < row_item_begin[b + 1]; ++it)
         acc += F[(size_t)it * block * 3 + local];

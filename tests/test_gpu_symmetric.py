@@ -113,3 +113,27 @@ def test_auto_mode_large_self_interaction():
         u = c.eval(SL, f)
     sub = rng.choice(rt.shape[0], 300, replace=False)
     _check(u[sub], orc.stokeslet_direct_cpu(rs, f, rt[sub], 1.0))
+
+
+@pytest.mark.parametrize("n_parts", [2, 3, 8])
+def test_row_partition_parts_sum_to_the_full_result(n_parts):
+    # one rank per GPU with the symmetric kernel: every part evaluates its block rows; the leading n_src rows are
+    # partial sums that add up to the full self-interaction; remainder targets are complete per part
+    rng = np.random.default_rng(40 + n_parts)
+    n_src = 6000
+    rs = rng.uniform(-2, 2, (n_src, 3))
+    f = rng.uniform(-1, 1, (n_src, 3))
+    extra = rng.uniform(-2, 2, (n_parts * 50, 3))
+    total = np.zeros((n_src, 3))
+    for p in range(n_parts):
+        mine = extra[p * 50:(p + 1) * 50]
+        with skb.Context(1) as c:
+            c.set_symmetric(1)
+            c.set_sym_partition(p, n_parts)
+            c.set_targets(np.concatenate([rs, mine]))
+            c.set_sources(SL, rs)
+            u = c.eval(SL, f)
+            assert c.last_eval_was_symmetric()
+        total += u[:n_src]
+        _check(u[n_src:], orc.stokeslet_direct_cpu(rs, f, mine, 1.0))
+    _check(total, orc.stokeslet_direct_cpu(rs, f, rs, 1.0))
