@@ -59,7 +59,8 @@ struct PairArgs {
     int n_src_tiles;       // ceil(n_src / kSrcTile)
     int tiles_per_split;   // source tiles handled by one blockIdx.y
     int diag_tiles;        // 0: off.  >0: block-diagonal mode -- target tile b only meets source tiles
-                           // [b*diag_tiles, (b+1)*diag_tiles) (the diagonal blocks the symmetric kernel leaves out)
+                           // [b*diag_tiles, (b+1)*diag_tiles), one per blockIdx.y (the diagonal blocks the
+                           // symmetric kernel leaves out)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -430,8 +431,10 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const long long t_base = (long long)blockIdx.x * kTileT;
-    const int per_cta = a.diag_tiles > 0 ? a.diag_tiles : a.tiles_per_split;
-    const int first_tile = a.diag_tiles > 0 ? (int)blockIdx.x * a.diag_tiles : (int)blockIdx.y * a.tiles_per_split;
+    // block-diagonal mode: CTA (b, y) meets source tile b*diag_tiles + y only (gridDim.y == diag_tiles)
+    const int per_cta = a.diag_tiles > 0 ? 1 : a.tiles_per_split;
+    const int first_tile = a.diag_tiles > 0 ? (int)blockIdx.x * a.diag_tiles + (int)blockIdx.y
+                                            : (int)blockIdx.y * a.tiles_per_split;
     int n_tiles = a.n_src_tiles - first_tile;
     n_tiles = n_tiles < per_cta ? n_tiles : per_cta;
     if (n_tiles < 0)

@@ -69,7 +69,7 @@ struct DeviceState {
     skb::DeviceInfo info;
     cudaStream_t stream = nullptr;
     cudaStream_t aux_stream = nullptr;              // remainder targets run beside the symmetric kernel
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     long long trg_begin = 0, n_trg = 0; // this device's block of the global target list
     skb::DevBuf r_trg, u, partial, scratch;

@@ -277,6 +277,8 @@ static int ctx_create_impl(const int *ids, int n, skb_ctx **out) {
         CUDA_TRY(cudaStreamCreateWithFlags(&d.aux_stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.ev_fork2, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&d.ev_join2, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreate(&d.ev_t0));
         CUDA_TRY(cudaEventCreate(&d.ev_t1));
         CUDA_TRY(cudaEventCreate(&d.ev_k0));
@@ -344,6 +346,8 @@ int skb_ctx_destroy(skb_ctx *ctx) {
         if (d.ev_k1) cudaEventDestroy(d.ev_k1);
         if (d.ev_fork) cudaEventDestroy(d.ev_fork);
         if (d.ev_join) cudaEventDestroy(d.ev_join);
+        if (d.ev_fork2) cudaEventDestroy(d.ev_fork2);
+        if (d.ev_join2) cudaEventDestroy(d.ev_join2);
         if (d.aux_stream) cudaStreamDestroy(d.aux_stream);
         if (d.stream) cudaStreamDestroy(d.stream);
     }
@@ -609,7 +613,7 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
         SKB_TRY(s.sym_row_begin.ensure(row_begin.size() * sizeof(int)));
         SKB_TRY(s.sym_P.ensure((size_t)nb * (size_t)s.n_pad * 24));
         SKB_TRY(s.sym_F.ensure(order.size() * (size_t)block * 24 + 16));
-        SKB_TRY(s.sym_diag.ensure((size_t)s.n_pad * 24));
+        SKB_TRY(s.sym_diag.ensure((size_t)T * (size_t)s.n_pad * 24));
         CUDA_TRY(cudaMemcpyAsync(s.sym_item_buf.ptr, order.data(), order.size() * sizeof(SymItem),
                                  cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(s.sym_row_begin.ptr, row_begin.data(), row_begin.size() * sizeof(int),
@@ -641,26 +645,31 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
     a.n_pad = s.n_pad;
     a.nb = s.sym_nb;
     cudaError_t e = cudaSuccess;
+    CUDA_TRY(cudaEventRecord(d.ev_fork2, st)); // strengths are packed: the diagonal blocks may start from here
     if (s.sym_items > 0) {
         e = launch_sym<4, 3>(a, s.sym_items, st);
         if (e != cudaSuccess)
             return set_error(SKB_ERR_CUDA, "pair_sym_kernel launch failed: %s", cudaGetErrorString(e));
         count_launch(1);
     }
-    // block diagonal with the plain kernel: target tile b (128*T nodes) x its own T source tiles
+    // block diagonal with the plain kernel, beside the symmetric kernel on the auxiliary stream: target tile b
+    // (128*T nodes) x its own T source tiles, one CTA per (block, source tile)
     LaunchPlan dp;
     dp.T = T;
-    dp.n_splits = 1;
-    dp.tiles_per_split = T;
+    dp.n_splits = T;
+    dp.tiles_per_split = 1;
     dp.grid_x = (unsigned)((s.n + block - 1) / block);
+    CUDA_TRY(cudaStreamWaitEvent(d.aux_stream, d.ev_fork2, 0)); // recorded before the symmetric launch
     SKB_TRY(launch_pair_sum(d.info, SKB_STOKESLET, (const double *)s.r.ptr, (const double *)s.f_packed.ptr, s.n,
-                            s.n_pad, (const double *)s.r.ptr, s.n, (double *)s.sym_diag.ptr, dp, st, T));
+                            s.n_pad, (const double *)s.r.ptr, s.n, (double *)s.sym_diag.ptr, dp, d.aux_stream, T));
+    CUDA_TRY(cudaEventRecord(d.ev_join2, d.aux_stream));
+    CUDA_TRY(cudaStreamWaitEvent(st, d.ev_join2, 0));
     const long long n3 = 3 * s.n;
     const double scale = scale_mul / (8.0 * M_PI);
     sym_reduce_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(
         (const double *)s.sym_diag.ptr, (const double *)s.sym_P.ptr, (const double *)s.sym_F.ptr,
         (const int *)s.sym_row_begin.ptr, (int)block, s.n_pad, n3, scale, accumulate, d_u_out, s.sym_part,
-        s.sym_parts);
+        s.sym_parts, T, s.n);
     e = cudaGetLastError();
     if (e != cudaSuccess)
         return set_error(SKB_ERR_CUDA, "sym_reduce_kernel launch failed: %s", cudaGetErrorString(e));

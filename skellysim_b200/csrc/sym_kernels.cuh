@@ -249,14 +249,17 @@ __host__ __device__ inline int sym_row_owner(int I, int n_parts) {
 __global__ void sym_reduce_kernel(const double *__restrict__ diag, const double *__restrict__ P,
                                   const double *__restrict__ F, const int *__restrict__ row_item_begin, int block,
                                   long long n_pad, long long n_valid3, double scale, int accumulate,
-                                  double *__restrict__ u, int part, int n_parts) {
+                                  double *__restrict__ u, int part, int n_parts, int n_diag, long long n_valid) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // component index 3*n + k
     if (i >= n_valid3)
         return;
     const long long node = i / 3;
     const int b = (int)(node / block);
     // only rows owned by this part were evaluated here (n_parts == 1: all of them)
-    double acc = (sym_row_owner(b, n_parts) == part) ? diag[i] : 0.0;
+    double acc = 0.0;
+    if (sym_row_owner(b, n_parts) == part)
+        for (int y = 0; y < n_diag; ++y) // diagonal block, one slab per source tile of the block
+            acc += diag[(size_t)y * n_valid * 3 + i];
     for (int I = 0; I < b; ++I)
         if (sym_row_owner(I, n_parts) == part)
             acc += P[((size_t)I * n_pad) * 3 + i];
