@@ -198,6 +198,14 @@ def run_reference_arm(args, rank, world):
     }))
 
 
+_T0 = time.perf_counter()
+
+
+def _log(msg):
+    if os.environ.get("BENCH_VERBOSE"):
+        print(f"[bench +{time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def workload_name(w, n_fib, n_shell):
     return (f"{w}: ellipsoid periphery ({n_shell} nodes) + {n_fib} fibers x 32 nodes; Stokeslet call of "
             f"FiberContainer::flow (fiber nodes -> fiber+shell nodes), FP64 direct kernel")
@@ -299,6 +307,40 @@ def matvec_leg(torch, dist, skb, dev, local_rank, rank, world, steps=20, warmup=
 
 
 # ------------------------------------------------------------------------------------------------
+# "next" row N1: the periphery's dense operator (HBM-bound GEMV), N_s = 6000 nodes -> 18000 x 18000 FP64
+# ------------------------------------------------------------------------------------------------
+def dense_leg(skb, hbm_peak_gbs, n_nodes=6000, reps=10):
+    n = 3 * n_nodes
+    rng = np.random.default_rng(4)
+    _log("dense: generating matrix")
+    A = rng.random((n, n))  # 2.6 GB
+    _log("dense: matrix ready")
+    x = rng.random(n)
+    v = rng.random(n)
+    with skb.Dense(1) as dn:
+        dn.set_matrix(skb.DENSE_STRESSLET_PLUS_COMPLEMENTARY, A)
+        _log("dense: uploaded")
+        y = dn.apply(skb.DENSE_STRESSLET_PLUS_COMPLEMENTARY, x, v)
+        ks, ts = [], []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            y = dn.apply(skb.DENSE_STRESSLET_PLUS_COMPLEMENTARY, x, v)
+            ts.append(1e3 * (time.perf_counter() - t0))
+            ks.append(dn.stats()["kernel_ms"])
+        bytes_ = dn.stats()["bytes"]
+    _log("dense: timed")
+    rows = np.random.default_rng(0).choice(n, 32, replace=False)
+    ref = A[rows] @ x + v[rows]
+    err = float(np.max(np.abs(y[rows] - ref) / (np.abs(A[rows]) @ np.abs(x) + np.abs(v[rows]))))
+    k = float(np.median(ks))
+    return {"workload": f"Periphery::matvec dense operator, {n_nodes} nodes: {n} x {n} FP64 row-major GEMV (+v)",
+            "kernel_ms": k, "e2e_ms": float(np.median(ts)), "bytes": int(bytes_),
+            "roofline": {"bound": "hbm", "achieved": bytes_ / (k * 1e-3) / 1e9, "peak": hbm_peak_gbs, "unit": "GB/s",
+                         "frac": bytes_ / (k * 1e-3) / 1e9 / hbm_peak_gbs},
+            "max_backward_err": err}
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -310,6 +352,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-matvec", action="store_true")
+    ap.add_argument("--no-dense", action="store_true")
     ap.add_argument("--no-symmetric", action="store_true", help="plain kernel only (A/B)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -323,8 +366,10 @@ def main():
         args.gpus = world
     args.warmup = max(args.warmup, 3)
 
+    _log("importing torch")
     import torch
     import torch.distributed as dist
+    _log("torch imported")
 
     import skellysim_b200 as skb
     from skellysim_b200 import capi
@@ -439,6 +484,7 @@ def main():
         got = d_u.cpu().numpy()[idx]
         acc = float(np.abs(got - ref).max() / np.abs(ref).max())
 
+    _log("warm-up + accuracy gate done")
     with ClockSampler(local_rank) as clk:
         n0 = capi.launch_count()
         tot_ms, wall, kms = timed(step_device, args.steps)
@@ -521,12 +567,16 @@ def main():
             out["error"] = f"accuracy gate failed: {acc}"
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline_leg(r_src_all, f_all, r_trg_all)
+    _log("headline + e2e + cpu baseline done")
     ctx.close()
     del flush
     mv = None if args.no_matvec else matvec_leg(torch, dist, skb, dev, local_rank, rank, world)
     if rank == 0:
         if mv is not None:
             out["matvec"] = mv
+        _log("matvec leg done")
+        if world == 1 and not args.no_dense:
+            out["periphery_dense"] = dense_leg(skb, out["roofline"]["hbm"]["peak"])
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

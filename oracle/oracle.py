@@ -229,6 +229,16 @@ def body_flow(r_trg, node_pos, node_normal, densities, centers, forces, torques,
     return v
 
 
+def periphery_dense_apply(A, x, v_add=None):
+    """Periphery::matvec `stresslet_plus_complementary_ * x_shell + v_local` (periphery.cpp:38-47) and
+    Periphery::apply_preconditioner `M_inv_ * x_shell` (periphery.cpp:21-30); A row-major as the precompute .npz
+    stores it (precompute.py:113-148)."""
+    y = np.asarray(A, dtype=np.float64) @ np.asarray(x, dtype=np.float64).reshape(-1)
+    if v_add is not None:
+        y = y + np.asarray(v_add, dtype=np.float64).reshape(-1)
+    return y
+
+
 def matvec_flow(fib, shell, body, eta):
     """Hydrodynamic part of System::apply_matvec (system.cpp:284-316): v_all over targets
     [fibers | shell | bodies]; shell sources act on fiber and body targets only (system.cpp:301-315).

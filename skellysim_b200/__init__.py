@@ -5,8 +5,10 @@ The product is the C-ABI shared library ``skellysim_b200/lib/libskelly_b200.so``
 ctypes binding used by the tests and bench.py.  There is no CPU fallback: importing works without a
 GPU (so the C-ABI export test can run), every compute call needs a B200.
 """
-from .capi import (KERNEL_STOKESLET, KERNEL_STRESSLET, Context, Flow, SkbError, build_library, library, library_path,
+from .capi import (DENSE_M_INV, DENSE_STRESSLET_PLUS_COMPLEMENTARY, KERNEL_STOKESLET, KERNEL_STRESSLET, Context, Dense,
+                   Flow, SkbError, build_library, library, library_path,
                    stokeslet_direct, stresslet_direct)
 
-__all__ = ["KERNEL_STOKESLET", "KERNEL_STRESSLET", "Context", "Flow", "SkbError", "build_library", "library",
+__all__ = ["DENSE_M_INV", "DENSE_STRESSLET_PLUS_COMPLEMENTARY", "KERNEL_STOKESLET", "KERNEL_STRESSLET", "Context",
+           "Dense", "Flow", "SkbError", "build_library", "library",
            "library_path", "stokeslet_direct", "stresslet_direct"]

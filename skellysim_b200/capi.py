@@ -34,6 +34,10 @@ class FlowStats(C.Structure):
     _fields_ = [("device_ms", C.c_double), ("total_ms", C.c_double), ("n_pairs", C.c_int64), ("launches", C.c_int32)]
 
 
+class DenseStats(C.Structure):
+    _fields_ = [("kernel_ms", C.c_double), ("total_ms", C.c_double), ("bytes", C.c_int64)]
+
+
 def library_path() -> str:
     return _LIB
 
@@ -98,6 +102,12 @@ def library() -> C.CDLL:
         "skb_flow_matvec": ([ctxp, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_last_stats": ([ctxp, C.POINTER(FlowStats)], C.c_int),
         "skb_flow_set_target_window": ([ctxp, C.c_int64, C.c_int64], C.c_int),
+        # include/skelly_b200_dense.h
+        "skb_dense_create": ([C.c_int, C.POINTER(ctxp)], C.c_int),
+        "skb_dense_destroy": ([ctxp], C.c_int),
+        "skb_dense_set_matrix": ([ctxp, C.c_int, _dp, C.c_int64, C.c_int64], C.c_int),
+        "skb_dense_apply": ([ctxp, C.c_int, _dp, _dp, _dp], C.c_int),
+        "skb_dense_last_stats": ([ctxp, C.POINTER(DenseStats)], C.c_int),
         "skb_flow_matvec_device": ([ctxp] + [C.c_void_p] * 5 + [C.c_double, C.c_void_p, C.c_void_p], C.c_int),
     }
     for name, (args, res) in sig.items():
@@ -375,3 +385,57 @@ class Flow:
         s = FlowStats()
         _check(library().skb_flow_last_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in FlowStats._fields_}
+
+
+DENSE_STRESSLET_PLUS_COMPLEMENTARY = 0
+DENSE_M_INV = 1
+
+
+class Dense:
+    """The periphery's dense operators on the GPU (include/skelly_b200_dense.h): Periphery::matvec and
+    Periphery::apply_preconditioner (periphery.cpp:21-47) as row-partitioned GEMVs."""
+
+    def __init__(self, n_gpus: int = 1):
+        self._h = C.c_void_p()
+        _check(library().skb_dense_create(int(n_gpus), C.byref(self._h)))
+        self.shape = {}
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            library().skb_dense_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_matrix(self, op: int, A):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        assert A.ndim == 2
+        _check(library().skb_dense_set_matrix(self._h, int(op), _p(A), A.shape[0], A.shape[1]))
+        self.shape[int(op)] = A.shape
+
+    def apply(self, op: int, x, v_add=None):
+        rows, cols = self.shape[int(op)]
+        x = np.ascontiguousarray(x, dtype=np.float64).reshape(-1)
+        assert x.shape[0] == cols
+        y = np.empty(rows)
+        v = None
+        if v_add is not None:
+            v = np.ascontiguousarray(v_add, dtype=np.float64).reshape(-1)
+            assert v.shape[0] == rows
+        _check(library().skb_dense_apply(self._h, int(op), _p(x), _p(v) if v is not None else None, _p(y)))
+        return y
+
+    def stats(self) -> dict:
+        s = DenseStats()
+        _check(library().skb_dense_last_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in DenseStats._fields_}

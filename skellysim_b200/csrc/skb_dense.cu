@@ -1,0 +1,248 @@
+// skb_dense.cu -- the periphery's dense operators (Periphery::matvec / apply_preconditioner,
+// SkellySim src/core/periphery.cpp:21-47) as an HBM-bound row-major GEMV on B200.  include/skelly_b200_dense.h.
+#include "skb_internal.hpp"
+#include "../../include/skelly_b200_dense.h"
+
+#include <algorithm>
+#include <memory>
+#include <vector>
+
+using namespace skb;
+
+#define CUDA_TRY(expr)                                                                                                \
+    do {                                                                                                              \
+        cudaError_t _e = (expr);                                                                                      \
+        if (_e != cudaSuccess)                                                                                        \
+            return set_error(SKB_ERR_CUDA, "%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,                      \
+                             cudaGetErrorString(_e));                                                                 \
+    } while (0)
+#define SKB_TRY(expr)                                                                                                 \
+    do {                                                                                                              \
+        int _rc = (expr);                                                                                             \
+        if (_rc != SKB_OK)                                                                                            \
+            return _rc;                                                                                               \
+    } while (0)
+
+namespace {
+
+// 128-bit streaming load of the matrix (read once, keep it out of L1)
+__device__ __forceinline__ double2 ldg_stream(const double2 *p) {
+    double2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p));
+    return v;
+}
+
+// y[r] = sum_c A[r][c] x[c] (+ v[r]).  One warp per row, rows strided over the grid; each lane walks the row in
+// 16-byte pieces (512 B per warp-load, fully coalesced) with kUnroll independent loads in flight; x (<= 240 KB)
+// lives in L1/L2.  Per-lane partial sums are combined by a fixed shuffle tree: bitwise reproducible.
+constexpr int kGemvUnroll = 8;
+__global__ void __launch_bounds__(256) dense_gemv_kernel(const double *__restrict__ A, const double *__restrict__ x,
+                                                         const double *__restrict__ v, double *__restrict__ y,
+                                                         long long n_rows, long long n_cols, int vec_ok) {
+    const int lane = threadIdx.x & 31;
+    const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
+    for (long long r = warp; r < n_rows; r += n_warps) {
+        const double *row = A + r * n_cols;
+        double acc[kGemvUnroll];
+#pragma unroll
+        for (int u = 0; u < kGemvUnroll; ++u)
+            acc[u] = 0.0;
+        long long c = 0;
+        if (vec_ok) {
+            const double2 *row2 = reinterpret_cast<const double2 *>(row);
+            const double2 *x2 = reinterpret_cast<const double2 *>(x);
+            const long long n2 = n_cols >> 1;
+            long long j = lane;
+            for (; j + 32 * (kGemvUnroll - 1) < n2; j += 32 * kGemvUnroll) {
+                double2 a[kGemvUnroll];
+#pragma unroll
+                for (int u = 0; u < kGemvUnroll; ++u)
+                    a[u] = ldg_stream(row2 + j + 32 * u);
+#pragma unroll
+                for (int u = 0; u < kGemvUnroll; ++u) {
+                    const double2 xv = x2[j + 32 * u];
+                    acc[u] = fma(a[u].x, xv.x, acc[u]);
+                    acc[u] = fma(a[u].y, xv.y, acc[u]);
+                }
+            }
+            for (; j < n2; j += 32) {
+                const double2 a = ldg_stream(row2 + j);
+                const double2 xv = x2[j];
+                acc[0] = fma(a.x, xv.x, acc[0]);
+                acc[0] = fma(a.y, xv.y, acc[0]);
+            }
+            c = n2 << 1;
+            if ((n_cols & 1) && lane == 0)
+                acc[1] = fma(row[c], x[c], acc[1]);
+        } else {
+            for (c = lane; c < n_cols; c += 32)
+                acc[0] = fma(__ldg(row + c), x[c], acc[0]);
+        }
+        double s = 0.0;
+#pragma unroll
+        for (int u = 0; u < kGemvUnroll; ++u)
+            s += acc[u];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+        if (lane == 0)
+            y[r] = v ? s + v[r] : s;
+    }
+}
+
+struct DenseDev {
+    int dev = 0, num_sms = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t e0 = nullptr, e1 = nullptr, t0 = nullptr, t1 = nullptr;
+    long long row_begin[2] = {0, 0}, n_rows[2] = {0, 0};
+    DevBuf A[2], x, v, y;
+};
+
+} // namespace
+
+struct skb_dense {
+    std::vector<DenseDev> devs;
+    long long rows[2] = {-1, -1}, cols[2] = {0, 0};
+    skb_dense_stats stats{};
+};
+
+extern "C" {
+
+int skb_dense_create(int n_gpus, skb_dense **out) {
+    if (!out)
+        return set_error(SKB_ERR_INVALID, "skb_dense_create: out == NULL");
+    *out = nullptr;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev == 0)
+        return set_error(SKB_ERR_NO_DEVICE, "no CUDA device available; this library has no CPU fallback");
+    if (n_gpus < 1 || n_gpus > n_dev)
+        return set_error(SKB_ERR_INVALID, "skb_dense_create: n_gpus=%d but %d device(s) visible", n_gpus, n_dev);
+    std::unique_ptr<skb_dense> dn(new skb_dense);
+    dn->devs.resize(n_gpus);
+    for (int g = 0; g < n_gpus; ++g) {
+        DenseDev &d = dn->devs[g];
+        d.dev = g;
+        CUDA_TRY(cudaSetDevice(g));
+        cudaDeviceProp p;
+        CUDA_TRY(cudaGetDeviceProperties(&p, g));
+        d.num_sms = p.multiProcessorCount;
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaEventCreate(&d.e0));
+        CUDA_TRY(cudaEventCreate(&d.e1));
+        CUDA_TRY(cudaEventCreate(&d.t0));
+        CUDA_TRY(cudaEventCreate(&d.t1));
+    }
+    *out = dn.release();
+    return SKB_OK;
+}
+
+int skb_dense_destroy(skb_dense *dn) {
+    if (!dn)
+        return SKB_OK;
+    for (auto &d : dn->devs) {
+        cudaSetDevice(d.dev);
+        if (d.stream)
+            cudaStreamSynchronize(d.stream);
+        d.A[0].release();
+        d.A[1].release();
+        d.x.release();
+        d.v.release();
+        d.y.release();
+        if (d.e0) cudaEventDestroy(d.e0);
+        if (d.e1) cudaEventDestroy(d.e1);
+        if (d.t0) cudaEventDestroy(d.t0);
+        if (d.t1) cudaEventDestroy(d.t1);
+        if (d.stream) cudaStreamDestroy(d.stream);
+    }
+    delete dn;
+    return SKB_OK;
+}
+
+int skb_dense_set_matrix(skb_dense *dn, int op, const double *A, int64_t n_rows, int64_t n_cols) {
+    if (!dn || (op != 0 && op != 1) || n_rows < 0 || n_cols < 0 || (n_rows * n_cols > 0 && !A))
+        return set_error(SKB_ERR_INVALID, "skb_dense_set_matrix: bad arguments");
+    const long long P = (long long)dn->devs.size();
+    const long long chunk = (n_rows + P - 1) / P; // contiguous row blocks, periphery.cpp:387-417
+    dn->rows[op] = n_rows;
+    dn->cols[op] = n_cols;
+    for (long long g = 0; g < P; ++g) {
+        DenseDev &d = dn->devs[g];
+        d.row_begin[op] = std::min<long long>(n_rows, g * chunk);
+        d.n_rows[op] = std::min<long long>(n_rows, (g + 1) * chunk) - d.row_begin[op];
+        if (d.n_rows[op] == 0 || n_cols == 0)
+            continue;
+        CUDA_TRY(cudaSetDevice(d.dev));
+        SKB_TRY(d.A[op].ensure((size_t)d.n_rows[op] * (size_t)n_cols * 8));
+        CUDA_TRY(cudaMemcpyAsync(d.A[op].ptr, A + d.row_begin[op] * n_cols, (size_t)d.n_rows[op] * n_cols * 8,
+                                 cudaMemcpyHostToDevice, d.stream));
+    }
+    for (auto &d : dn->devs) {
+        CUDA_TRY(cudaSetDevice(d.dev));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+    }
+    return SKB_OK;
+}
+
+int skb_dense_apply(skb_dense *dn, int op, const double *x, const double *v_add, double *y) {
+    if (!dn || (op != 0 && op != 1))
+        return set_error(SKB_ERR_INVALID, "skb_dense_apply: bad arguments");
+    if (dn->rows[op] < 0)
+        return set_error(SKB_ERR_STATE, "skb_dense_apply: skb_dense_set_matrix(op=%d) has not been called", op);
+    const long long n_rows = dn->rows[op], n_cols = dn->cols[op];
+    if ((n_cols > 0 && !x) || (n_rows > 0 && !y))
+        return set_error(SKB_ERR_INVALID, "skb_dense_apply: NULL x or y");
+    for (auto &d : dn->devs) {
+        if (d.n_rows[op] == 0)
+            continue;
+        CUDA_TRY(cudaSetDevice(d.dev));
+        SKB_TRY(d.x.ensure((size_t)std::max<long long>(n_cols, 1) * 8 + 16));
+        SKB_TRY(d.y.ensure((size_t)d.n_rows[op] * 8));
+        CUDA_TRY(cudaEventRecord(d.t0, d.stream));
+        if (n_cols > 0)
+            CUDA_TRY(cudaMemcpyAsync(d.x.ptr, x, (size_t)n_cols * 8, cudaMemcpyHostToDevice, d.stream));
+        const double *dv = nullptr;
+        if (v_add) {
+            SKB_TRY(d.v.ensure((size_t)d.n_rows[op] * 8));
+            CUDA_TRY(cudaMemcpyAsync(d.v.ptr, v_add + d.row_begin[op], (size_t)d.n_rows[op] * 8,
+                                     cudaMemcpyHostToDevice, d.stream));
+            dv = (const double *)d.v.ptr;
+        }
+        const int vec_ok = (n_cols % 2 == 0) ? 1 : 0; // every row then starts 16-byte aligned
+        const int blocks = d.num_sms * 8;
+        CUDA_TRY(cudaEventRecord(d.e0, d.stream));
+        dense_gemv_kernel<<<blocks, 256, 0, d.stream>>>((const double *)d.A[op].ptr, (const double *)d.x.ptr, dv,
+                                                        (double *)d.y.ptr, d.n_rows[op], n_cols, vec_ok);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        CUDA_TRY(cudaEventRecord(d.e1, d.stream));
+        CUDA_TRY(cudaMemcpyAsync(y + d.row_begin[op], d.y.ptr, (size_t)d.n_rows[op] * 8, cudaMemcpyDeviceToHost,
+                                 d.stream));
+        CUDA_TRY(cudaEventRecord(d.t1, d.stream));
+    }
+    double k = 0, t = 0;
+    for (auto &d : dn->devs) {
+        if (d.n_rows[op] == 0)
+            continue;
+        CUDA_TRY(cudaSetDevice(d.dev));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, d.e0, d.e1) == cudaSuccess)
+            k = std::max(k, (double)ms);
+        if (cudaEventElapsedTime(&ms, d.t0, d.t1) == cudaSuccess)
+            t = std::max(t, (double)ms);
+    }
+    dn->stats.kernel_ms = k;
+    dn->stats.total_ms = t;
+    dn->stats.bytes = 8 * n_rows * n_cols;
+    return SKB_OK;
+}
+
+int skb_dense_last_stats(const skb_dense *dn, skb_dense_stats *out) {
+    if (!dn || !out)
+        return set_error(SKB_ERR_INVALID, "skb_dense_last_stats: NULL");
+    *out = dn->stats;
+    return SKB_OK;
+}
+
+} // extern "C"
