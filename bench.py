@@ -424,6 +424,7 @@ def main():
     d_f_mine.copy_(h_f_mine, non_blocking=True)
     d_u = torch.empty((max(n_my_trg, 1), 3), dtype=torch.float64, device=dev)
     d_u_fib = d_u[:n_src]
+    d_u_mine = torch.empty((src_chunk, 3), dtype=torch.float64, device=dev)  # reduce-scatter output (own fibers)
     h_u = torch.empty((max(n_my_trg, 1), 3), dtype=torch.float64).pin_memory()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
     torch.cuda.synchronize()
@@ -435,8 +436,8 @@ def main():
     def step_device():
         allgather_strengths(d_f_gather, d_f_mine)  # ONE NCCL all-gather per step (no-op at world == 1)
         ctx.eval_device(skb.KERNEL_STOKESLET, d_f_gather.data_ptr(), d_u.data_ptr(), False, stream)
-        if world > 1 and sym_layout:  # fiber rows are per-rank partial sums of the symmetric block rows
-            dist.all_reduce(d_u_fib)
+        if world > 1 and sym_layout:  # fiber rows are per-rank partial sums of the symmetric block rows:
+            dist.reduce_scatter_tensor(d_u_mine, d_u_fib)  # every rank ends up with the velocities of ITS fibers
 
     def step_e2e():
         d_f_mine.copy_(h_f_mine, non_blocking=True)
@@ -479,10 +480,14 @@ def main():
     acc = None
     if rank == 0:
         import oracle as orc
-        idx = np.random.default_rng(3).choice(n_my_trg, size=min(128, n_my_trg), replace=False)
-        ref = orc.stokeslet_direct_cpu(r_src_all, f_all, my_trg[idx], 1.0)
-        got = d_u.cpu().numpy()[idx]
-        acc = float(np.abs(got - ref).max() / np.abs(ref).max())
+        if world > 1 and sym_layout:  # this rank's final rows: its own fibers (reduce-scatter) + its remainder block
+            chk_trg = np.concatenate([r_src_all[s0:s1], my_trg[n_src:]])
+            chk_val = np.concatenate([d_u_mine.cpu().numpy()[:s1 - s0], d_u.cpu().numpy()[n_src:]])
+        else:
+            chk_trg, chk_val = my_trg, d_u.cpu().numpy()
+        idx = np.random.default_rng(3).choice(chk_trg.shape[0], size=min(128, chk_trg.shape[0]), replace=False)
+        ref = orc.stokeslet_direct_cpu(r_src_all, f_all, chk_trg[idx], 1.0)
+        acc = float(np.abs(chk_val[idx] - ref).max() / np.abs(ref).max())
 
     _log("warm-up + accuracy gate done")
     with ClockSampler(local_rank) as clk:
@@ -543,7 +548,7 @@ def main():
             "config": {"workload": workload_name(args.workload, n_fib, n_shell), "n_src": n_src, "n_trg": n_trg,
                        "pairs_per_step": pairs_total,
                        "parallelism": (f"symmetric block rows (serpentine) + remainder targets partitioned x{world}"
-                                       + (", 1 NCCL all-gather of strengths + 1 all-reduce of fiber velocities per step"
+                                       + (", 1 NCCL all-gather of strengths + 1 reduce-scatter of fiber velocities per step"
                                           if world > 1 else "")) if sym_layout else
                        (f"targets+sources block-partitioned x{world}"
                         + (", 1 NCCL all-gather of strengths per step" if world > 1 else "")),

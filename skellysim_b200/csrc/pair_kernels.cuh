@@ -49,6 +49,14 @@ template <int KIND> struct KindTraits;
 template <> struct KindTraits<kStokeslet> { static constexpr int fdim = 3; };  // packed strengths / source
 template <> struct KindTraits<kStresslet> { static constexpr int fdim = 6; };  // sym6 combinations
 
+// Block row I of the symmetric path's upper triangle belongs to part owner(I): serpentine assignment, so that every
+// part gets the same number of long and short rows (one rank per GPU: each rank evaluates its rows, partial sums are
+// all-reduced).
+__host__ __device__ inline int sym_row_owner(int I, int n_parts) {
+    const int k = I / n_parts, m = I % n_parts;
+    return (k & 1) ? n_parts - 1 - m : m;
+}
+
 struct PairArgs {
     const double *r_src;   // [n_src_pad*3]   padded to a multiple of kSrcTile (pads replicate the last source)
     const double *f_src;   // [n_src_pad*fdim] padded with zeros
@@ -61,6 +69,7 @@ struct PairArgs {
     int diag_tiles;        // 0: off.  >0: block-diagonal mode -- target tile b only meets source tiles
                            // [b*diag_tiles, (b+1)*diag_tiles), one per blockIdx.y (the diagonal blocks the
                            // symmetric kernel leaves out)
+    int diag_part, diag_parts; // block-diagonal mode: only blocks owned by this part are evaluated
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -428,6 +437,8 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::bar_offset);
     uint64_t *empty_bar = full_bar + kStages;
 
+    if (a.diag_tiles > 0 && sym_row_owner((int)blockIdx.x, a.diag_parts) != a.diag_part)
+        return; // another rank's diagonal block (its slab is never read here)
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const long long t_base = (long long)blockIdx.x * kTileT;

@@ -39,7 +39,8 @@ DeviceInfo query_device(int dev);
 LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_src_tiles, int force_T, int force_S);
 int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const double *d_f_packed, long long n_src,
                     long long n_src_pad, const double *d_r_trg, long long n_trg, double *d_partial,
-                    const LaunchPlan &plan, cudaStream_t st, int diag_tiles = 0);
+                    const LaunchPlan &plan, cudaStream_t st, int diag_tiles = 0, int diag_part = 0,
+                    int diag_parts = 1);
 int launch_reduce(const double *d_partial, double *d_u, long long n_trg, int n_splits, double scale, int accumulate,
                   cudaStream_t st);
 

@@ -155,7 +155,7 @@ LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_sr
 
 int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const double *d_f_packed, long long n_src,
                     long long n_src_pad, const double *d_r_trg, long long n_trg, double *d_partial,
-                    const LaunchPlan &plan, cudaStream_t st, int diag_tiles) {
+                    const LaunchPlan &plan, cudaStream_t st, int diag_tiles, int diag_part, int diag_parts) {
     PairArgs a;
     a.r_src = d_r_src;
     a.f_src = d_f_packed;
@@ -166,6 +166,8 @@ int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const
     a.n_src_tiles = (int)((n_src + kSrcTile - 1) / kSrcTile);
     a.tiles_per_split = plan.tiles_per_split;
     a.diag_tiles = diag_tiles;
+    a.diag_part = diag_part;
+    a.diag_parts = diag_parts < 1 ? 1 : diag_parts;
     (void)n_src_pad;
     dim3 grid(plan.grid_x, plan.n_splits, 1);
     cudaError_t e = cudaSuccess;
@@ -661,7 +663,8 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
     dp.grid_x = (unsigned)((s.n + block - 1) / block);
     CUDA_TRY(cudaStreamWaitEvent(d.aux_stream, d.ev_fork2, 0)); // recorded before the symmetric launch
     SKB_TRY(launch_pair_sum(d.info, SKB_STOKESLET, (const double *)s.r.ptr, (const double *)s.f_packed.ptr, s.n,
-                            s.n_pad, (const double *)s.r.ptr, s.n, (double *)s.sym_diag.ptr, dp, d.aux_stream, T));
+                            s.n_pad, (const double *)s.r.ptr, s.n, (double *)s.sym_diag.ptr, dp, d.aux_stream, T,
+                            s.sym_part, s.sym_parts));
     CUDA_TRY(cudaEventRecord(d.ev_join2, d.aux_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, d.ev_join2, 0));
     const long long n3 = 3 * s.n;

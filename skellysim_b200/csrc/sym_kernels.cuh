@@ -237,13 +237,6 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
     }
 }
 
-// Block row I of the upper triangle belongs to part owner(I): serpentine assignment, so that every part gets the
-// same number of long and short rows (one rank per GPU: each rank evaluates its rows, partial sums are all-reduced).
-__host__ __device__ inline int sym_row_owner(int I, int n_parts) {
-    const int k = I / n_parts, m = I % n_parts;
-    return (k & 1) ? n_parts - 1 - m : m;
-}
-
 // Fixed-order combination for the symmetric path, one thread per velocity component of node `n` (block b):
 //   u = (acc ? u : 0) + scale * ( diag[n] + sum_{I < b} P[I][n] + sum_{items of row b} F[item][n - b*block] )
 __global__ void sym_reduce_kernel(const double *__restrict__ diag, const double *__restrict__ P,
