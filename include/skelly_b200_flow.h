@@ -54,6 +54,14 @@ SKB_API int skb_flow_periphery(skb_flow *fl, const double *r_trg, int64_t n_trg,
 SKB_API int skb_flow_bodies(skb_flow *fl, const double *r_trg, int64_t n_trg, const double *densities,
                             const double *forces_torques, double eta, double *vel);
 
+/* System::velocity_at_targets (system.cpp:330-384), hydrodynamic part: fiber flow WITHOUT self-term subtraction +
+ * body flow + periphery flow at arbitrary targets (system.cpp:355-359; point/background sources are analytic
+ * add-ons outside this library).  This is what the listener and the streamline integrator evaluate.  Any class may
+ * be empty; one upload of the strengths, one download of the velocities. */
+SKB_API int skb_flow_velocity_at_targets(skb_flow *fl, const double *r_trg, int64_t n_trg, const double *fib_forces,
+                                         const double *shell_density, const double *body_densities,
+                                         const double *body_forces_torques, double eta, double *vel);
+
 /* ---- fused matvec flow -------------------------------------------------------------------------------
  * v_all over targets [fibers | periphery | bodies] (get_node_maps, system.cpp:234-241):
  *   v_all  = fiber flow (all targets, self term subtracted)

@@ -101,6 +101,7 @@ def library() -> C.CDLL:
         "skb_flow_bodies": ([ctxp, _dp, C.c_int64, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_matvec": ([ctxp, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_last_stats": ([ctxp, C.POINTER(FlowStats)], C.c_int),
+        "skb_flow_velocity_at_targets": ([ctxp, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_set_target_window": ([ctxp, C.c_int64, C.c_int64], C.c_int),
         # include/skelly_b200_dense.h
         "skb_dense_create": ([C.c_int, C.POINTER(ctxp)], C.c_int),
@@ -355,6 +356,16 @@ class Flow:
         vel = np.empty((r_trg.shape[0], 3))
         _check(library().skb_flow_bodies(self._h, _p(r_trg), r_trg.shape[0], _p(densities), _p(ft), float(eta),
                                          _p(vel)))
+        return vel
+
+    def velocity_at_targets(self, r_trg, fib_forces, shell_density, body_densities, body_forces_torques, eta):
+        """System::velocity_at_targets (system.cpp:355-359): fiber (no self subtraction) + body + periphery flows."""
+        r_trg = _arr(r_trg, 3)
+        a, b, c = _arr(fib_forces, 3), _arr(shell_density, 3), _arr(body_densities, 3)
+        ft = _arr(body_forces_torques, 6)
+        vel = np.empty((r_trg.shape[0], 3))
+        _check(library().skb_flow_velocity_at_targets(self._h, _p(r_trg), r_trg.shape[0], _p(a), _p(b), _p(c), _p(ft),
+                                                      float(eta), _p(vel)))
         return vel
 
     def set_target_window(self, begin: int, end: int = -1):

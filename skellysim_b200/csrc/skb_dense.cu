@@ -38,11 +38,20 @@ __device__ __forceinline__ double2 ldg_stream(const double2 *p) {
 constexpr int kGemvUnroll = 8;
 __global__ void __launch_bounds__(256) dense_gemv_kernel(const double *__restrict__ A, const double *__restrict__ x,
                                                          const double *__restrict__ v, double *__restrict__ y,
-                                                         long long n_rows, long long n_cols, int vec_ok) {
+                                                         long long n_rows, long long n_cols, int vec_ok,
+                                                         unsigned long long *__restrict__ next_row) {
     const int lane = threadIdx.x & 31;
     const long long warp = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
     const long long n_warps = ((long long)gridDim.x * blockDim.x) >> 5;
-    for (long long r = warp; r < n_rows; r += n_warps) {
+    // rows are handed out dynamically (18 000 rows over ~9 500 warps would otherwise leave a 2-vs-1 tail); the row a
+    // warp gets does not change how that row is summed, so results stay bitwise reproducible.  The first row is
+    // static, the ticket for the following one is drawn before the current row is streamed.
+    long long r = warp;
+    while (r < n_rows) {
+        unsigned long long ticket = 0;
+        if (lane == 0)
+            ticket = atomicAdd(next_row, 1ULL);
+        const long long r_next = n_warps + (long long)__shfl_sync(0xffffffffu, ticket, 0);
         const double *row = A + r * n_cols;
         double acc[kGemvUnroll];
 #pragma unroll
@@ -88,6 +97,7 @@ __global__ void __launch_bounds__(256) dense_gemv_kernel(const double *__restric
             s += __shfl_xor_sync(0xffffffffu, s, o);
         if (lane == 0)
             y[r] = v ? s + v[r] : s;
+        r = r_next;
     }
 }
 
@@ -96,7 +106,7 @@ struct DenseDev {
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr, t0 = nullptr, t1 = nullptr;
     long long row_begin[2] = {0, 0}, n_rows[2] = {0, 0};
-    DevBuf A[2], x, v, y;
+    DevBuf A[2], x, v, y, ticket;
 };
 
 } // namespace
@@ -149,6 +159,7 @@ int skb_dense_destroy(skb_dense *dn) {
         d.x.release();
         d.v.release();
         d.y.release();
+        d.ticket.release();
         if (d.e0) cudaEventDestroy(d.e0);
         if (d.e1) cudaEventDestroy(d.e1);
         if (d.t0) cudaEventDestroy(d.t0);
@@ -209,10 +220,16 @@ int skb_dense_apply(skb_dense *dn, int op, const double *x, const double *v_add,
             dv = (const double *)d.v.ptr;
         }
         const int vec_ok = (n_cols % 2 == 0) ? 1 : 0; // every row then starts 16-byte aligned
-        const int blocks = d.num_sms * 8;
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense_gemv_kernel, 256, 0) != cudaSuccess || occ < 1)
+            occ = 2;
+        const int blocks = d.num_sms * occ; // all warps resident; further rows come from the ticket counter
+        SKB_TRY(d.ticket.ensure(8));
+        CUDA_TRY(cudaMemsetAsync(d.ticket.ptr, 0, 8, d.stream));
         CUDA_TRY(cudaEventRecord(d.e0, d.stream));
         dense_gemv_kernel<<<blocks, 256, 0, d.stream>>>((const double *)d.A[op].ptr, (const double *)d.x.ptr, dv,
-                                                        (double *)d.y.ptr, d.n_rows[op], n_cols, vec_ok);
+                                                        (double *)d.y.ptr, d.n_rows[op], n_cols, vec_ok,
+                                                        (unsigned long long *)d.ticket.ptr);
         CUDA_TRY(cudaGetLastError());
         count_launch(1);
         CUDA_TRY(cudaEventRecord(d.e1, d.stream));

@@ -406,6 +406,46 @@ int skb_flow_bodies(skb_flow *fl, const double *r_trg, int64_t n_trg, const doub
     return finish_stats(fl);
 }
 
+int skb_flow_velocity_at_targets(skb_flow *fl, const double *r_trg, int64_t n_trg, const double *fib_forces,
+                                 const double *shell_density, const double *body_densities,
+                                 const double *body_forces_torques, double eta, double *vel) {
+    if (!fl || n_trg < 0 || (n_trg > 0 && (!r_trg || !vel)) || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_flow_velocity_at_targets: bad arguments");
+    if ((fl->n_fib > 0 && !fib_forces) || (fl->n_shell > 0 && !shell_density) || (fl->n_body > 0 && !body_densities) ||
+        (fl->n_bodies > 0 && !body_forces_torques))
+        return set_error(SKB_ERR_INVALID, "skb_flow_velocity_at_targets: NULL input for a non-empty class");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    begin_stats(fl);
+    // the three "arbitrary target" evaluators share one cached target list
+    SKB_TRY(set_targets_cached(fl->fib[0], fl->tc_fib, r_trg, n_trg));
+    SKB_TRY(set_targets_cached(fl->shell[0], fl->tc_shell, r_trg, n_trg));
+    SKB_TRY(set_targets_cached(fl->body[0], fl->tc_body, r_trg, n_trg));
+    if (n_trg == 0)
+        return SKB_OK;
+    std::vector<double> f, t;
+    if (fl->n_bodies > 0)
+        split_forces_torques(body_forces_torques, fl->n_bodies, f, t);
+    fl->cur = fl->stream;
+    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
+    SKB_TRY(upload(fl, fl->in_fib, fib_forces, (size_t)fl->n_fib * 3));
+    SKB_TRY(upload(fl, fl->in_shell, shell_density, (size_t)fl->n_shell * 3));
+    SKB_TRY(upload(fl, fl->in_body, body_densities, (size_t)fl->n_body * 3));
+    SKB_TRY(upload(fl, fl->in_force, f.data(), f.size()));
+    SKB_TRY(upload(fl, fl->in_torque, t.data(), t.size()));
+    SKB_TRY(fl->vel.ensure((size_t)n_trg * 24));
+    double *d_v = (double *)fl->vel.ptr;
+    CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    // fc_->flow(r_trg, f_on_fibers, eta, /*subtract_self=*/false) + bc_.flow + shell_->flow   system.cpp:355-359
+    SKB_TRY(fibers_dev(fl, fl->fib[0], (const double *)fl->in_fib.ptr, eta, 0, d_v, 0, 0, 0));
+    SKB_TRY(bodies_dev(fl, fl->body[0], (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
+                       (const double *)fl->in_torque.ptr, eta, d_v, 1));
+    SKB_TRY(periphery_dev(fl, fl->shell[0], (const double *)fl->in_shell.ptr, eta, d_v, 1));
+    CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(vel, d_v, (size_t)n_trg * 24, cudaMemcpyDeviceToHost, fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+    return finish_stats(fl);
+}
+
 // resolve the target window into its fiber / body pieces and (re)build the matvec target lists
 static int prepare_matvec_targets(skb_flow *fl) {
     const long long nf = fl->n_fib, ns = fl->n_shell, nb = fl->n_body, n_all = nf + ns + nb;

@@ -176,3 +176,21 @@ def test_matvec_device_pointers_with_torch():
                          d_v.data_ptr(), st)
         torch.cuda.synchronize()
     _check(d_v.cpu().numpy(), orc.matvec_flow(fib, shell, body, eta))
+
+
+@pytest.mark.parametrize("n_trg", [1, 6, 1000])
+def test_velocity_at_targets(n_trg):
+    # listener / streamline path: fiber flow without self subtraction + body flow + periphery flow at free targets
+    # (system.cpp:355-359); 1-6 targets is what the Cash-Karp streamline integrator asks for per stage
+    fib, shell, body = make_system(33, 20, 600, 300, 1)
+    rng = np.random.default_rng(n_trg)
+    r_trg = rng.uniform(-2.5, 2.5, (n_trg, 3))
+    eta = 1.0
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        v = fl.velocity_at_targets(r_trg, fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+    ref = orc.fiber_flow(r_trg, fib["pos"], fib["n_nodes"], fib["lengths"], fib["forces"], eta, subtract_self=False)
+    ref += orc.body_flow(r_trg, body["pos"], body["normals"], body["density"], body["centers"], body["forces"],
+                         body["torques"], eta)
+    ref += orc.periphery_flow(r_trg, shell["pos"], shell["normals"], shell["density"], eta)
+    _check(v, ref)
