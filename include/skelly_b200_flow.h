@@ -62,6 +62,15 @@ SKB_API int skb_flow_velocity_at_targets(skb_flow *fl, const double *r_trg, int6
                                          const double *shell_density, const double *body_densities,
                                          const double *body_forces_torques, double eta, double *vel);
 
+/* Optional analytic add-ons of velocity_at_targets (system.cpp:358-359): point forces/torques
+ * (PointSourceContainer::flow, point_source.cpp:16-54: regularised Oseen contraction + rotlet; the caller passes
+ * the points that are alive at the current time) and the linear background flow (BackgroundSource::flow,
+ * background_source.cpp:15-24: u_j = uniform_j + r[components_j] * scale_factor_j).  n_points == 0 / NULL clears. */
+SKB_API int skb_flow_set_point_sources(skb_flow *fl, const double *positions, const double *forces,
+                                       const double *torques, int n_points);
+SKB_API int skb_flow_set_background(skb_flow *fl, const int *components, const double *scale_factor,
+                                    const double *uniform);
+
 /* ---- fused matvec flow -------------------------------------------------------------------------------
  * v_all over targets [fibers | periphery | bodies] (get_node_maps, system.cpp:234-241):
  *   v_all  = fiber flow (all targets, self term subtracted)

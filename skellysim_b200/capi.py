@@ -101,6 +101,8 @@ def library() -> C.CDLL:
         "skb_flow_bodies": ([ctxp, _dp, C.c_int64, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_matvec": ([ctxp, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_last_stats": ([ctxp, C.POINTER(FlowStats)], C.c_int),
+        "skb_flow_set_point_sources": ([ctxp, _dp, _dp, _dp, C.c_int], C.c_int),
+        "skb_flow_set_background": ([ctxp, C.POINTER(C.c_int), _dp, _dp], C.c_int),
         "skb_flow_velocity_at_targets": ([ctxp, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_set_target_window": ([ctxp, C.c_int64, C.c_int64], C.c_int),
         # include/skelly_b200_dense.h
@@ -357,6 +359,17 @@ class Flow:
         _check(library().skb_flow_bodies(self._h, _p(r_trg), r_trg.shape[0], _p(densities), _p(ft), float(eta),
                                          _p(vel)))
         return vel
+
+    def set_point_sources(self, positions, forces, torques):
+        positions, forces, torques = _arr(positions, 3), _arr(forces, 3), _arr(torques, 3)
+        _check(library().skb_flow_set_point_sources(self._h, _p(positions), _p(forces), _p(torques),
+                                                    positions.shape[0]))
+
+    def set_background(self, components, scale_factor, uniform):
+        comp = (C.c_int * 3)(*[int(c) for c in components])
+        sc = np.ascontiguousarray(scale_factor, dtype=np.float64)
+        un = np.ascontiguousarray(uniform, dtype=np.float64)
+        _check(library().skb_flow_set_background(self._h, comp, _p(sc), _p(un)))
 
     def velocity_at_targets(self, r_trg, fib_forces, shell_density, body_densities, body_forces_torques, eta):
         """System::velocity_at_targets (system.cpp:355-359): fiber (no self subtraction) + body + periphery flows."""

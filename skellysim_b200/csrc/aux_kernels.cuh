@@ -86,6 +86,54 @@ __global__ void rotlet_add_kernel(const double *__restrict__ r_src, const double
     u[3 * t + 2] += inv_8pi_eta * a2;
 }
 
+// kernels::oseen_tensor_contract_direct (kernels.cpp:85-131) for a handful of point forces, accumulated into u:
+// regularised for 0 < r <= eps, r == 0 skipped (point_source.cpp:42).  One thread per target.
+__global__ void oseen_contract_add_kernel(const double *__restrict__ r_src, const double *__restrict__ density,
+                                          int n_src, const double *__restrict__ r_trg, long long n_trg,
+                                          double inv_8pi_eta, double reg2, double eps, double *__restrict__ u) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trg)
+        return;
+    const double x = r_trg[3 * t], y = r_trg[3 * t + 1], z = r_trg[3 * t + 2];
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int s = 0; s < n_src; ++s) {
+        const double dx = r_src[3 * s] - x, dy = r_src[3 * s + 1] - y, dz = r_src[3 * s + 2] - z; // kernels.cpp:100-102
+        const double dr2 = dx * dx + dy * dy + dz * dz;
+        const double dr = sqrt(dr2);
+        if (dr == 0.0)
+            continue;
+        double fr, gr;
+        if (dr > eps) {
+            fr = inv_8pi_eta / dr;
+            gr = inv_8pi_eta / (dr * dr * dr);
+        } else {
+            const double di = 1.0 / sqrt(dr * dr + reg2);
+            fr = inv_8pi_eta * di;
+            gr = inv_8pi_eta * di * di * di;
+        }
+        const double d0 = density[3 * s], d1 = density[3 * s + 1], d2 = density[3 * s + 2];
+        const double dot = gr * (dx * d0 + dy * d1 + dz * d2);
+        a0 += fr * d0 + dx * dot;
+        a1 += fr * d1 + dy * dot;
+        a2 += fr * d2 + dz * dot;
+    }
+    u[3 * t + 0] += a0;
+    u[3 * t + 1] += a1;
+    u[3 * t + 2] += a2;
+}
+
+// BackgroundSource::flow (background_source.cpp:15-24): u_j += uniform_j + r[components_j] * scale_j
+__global__ void background_add_kernel(const double *__restrict__ r_trg, long long n_trg, int c0, int c1, int c2,
+                                      double s0, double s1, double s2, double u0, double u1, double u2,
+                                      double *__restrict__ u) {
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_trg)
+        return;
+    u[3 * t + 0] += u0 + r_trg[3 * t + c0] * s0;
+    u[3 * t + 1] += u1 + r_trg[3 * t + c1] * s1;
+    u[3 * t + 2] += u2 + r_trg[3 * t + c2] * s2;
+}
+
 // dst[i] += src[i]
 __global__ void add_inplace_kernel(double *__restrict__ dst, const double *__restrict__ src, long long n) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

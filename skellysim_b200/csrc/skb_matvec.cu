@@ -61,6 +61,11 @@ struct skb_flow {
     long long win_begin = 0, win_end = -1; // target window of the matvec in [fibers|shell|bodies] rows; -1 = all
     long long fa = 0, fb = 0, ba = 0, bb = 0, w0 = 0, w1 = 0; // resolved window pieces (fiber rows, body rows)
     cudaStream_t cur = nullptr;            // stream of the call in flight (own stream or the caller's)
+    int n_points = 0;
+    DevBuf pt_pos, pt_force, pt_torque;
+    bool has_background = false;
+    int bg_comp[3] = {0, 1, 2};
+    double bg_scale[3] = {0, 0, 0}, bg_uniform[3] = {0, 0, 0};
     // staging
     DevBuf in_fib, in_shell, in_body, in_force, in_torque, vel, tmp;
     skb_flow_stats stats{};
@@ -240,7 +245,7 @@ int skb_flow_destroy(skb_flow *fl) {
         skb_ctx_destroy(fl->body[k]);
     }
     DevBuf *bufs[] = {&fl->fiber_offset, &fl->fiber_length, &fl->r_fib, &fl->r_shell, &fl->r_body, &fl->centers,
-                      &fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel, &fl->tmp};
+                      &fl->pt_pos, &fl->pt_force, &fl->pt_torque, &fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel, &fl->tmp};
     for (DevBuf *b : bufs)
         b->release();
     if (fl->ev0) cudaEventDestroy(fl->ev0);
@@ -406,6 +411,42 @@ int skb_flow_bodies(skb_flow *fl, const double *r_trg, int64_t n_trg, const doub
     return finish_stats(fl);
 }
 
+int skb_flow_set_point_sources(skb_flow *fl, const double *positions, const double *forces, const double *torques,
+                               int n_points) {
+    if (!fl || n_points < 0 || (n_points > 0 && (!positions || !forces || !torques)))
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_point_sources: bad arguments");
+    fl->n_points = n_points;
+    if (n_points == 0)
+        return SKB_OK;
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    SKB_TRY(fl->pt_pos.ensure((size_t)n_points * 24));
+    SKB_TRY(fl->pt_force.ensure((size_t)n_points * 24));
+    SKB_TRY(fl->pt_torque.ensure((size_t)n_points * 24));
+    CUDA_TRY(cudaMemcpyAsync(fl->pt_pos.ptr, positions, (size_t)n_points * 24, cudaMemcpyHostToDevice, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(fl->pt_force.ptr, forces, (size_t)n_points * 24, cudaMemcpyHostToDevice, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(fl->pt_torque.ptr, torques, (size_t)n_points * 24, cudaMemcpyHostToDevice, fl->stream));
+    CUDA_TRY(cudaStreamSynchronize(fl->stream));
+    return SKB_OK;
+}
+
+int skb_flow_set_background(skb_flow *fl, const int *components, const double *scale_factor, const double *uniform) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_background: NULL");
+    if (!components || !scale_factor || !uniform) {
+        fl->has_background = false;
+        return SKB_OK;
+    }
+    for (int j = 0; j < 3; ++j) {
+        if (components[j] < 0 || components[j] > 2)
+            return set_error(SKB_ERR_INVALID, "skb_flow_set_background: components must be 0, 1 or 2");
+        fl->bg_comp[j] = components[j];
+        fl->bg_scale[j] = scale_factor[j];
+        fl->bg_uniform[j] = uniform[j];
+    }
+    fl->has_background = true;
+    return SKB_OK;
+}
+
 int skb_flow_velocity_at_targets(skb_flow *fl, const double *r_trg, int64_t n_trg, const double *fib_forces,
                                  const double *shell_density, const double *body_densities,
                                  const double *body_forces_torques, double eta, double *vel) {
@@ -440,6 +481,29 @@ int skb_flow_velocity_at_targets(skb_flow *fl, const double *r_trg, int64_t n_tr
     SKB_TRY(bodies_dev(fl, fl->body[0], (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
                        (const double *)fl->in_torque.ptr, eta, d_v, 1));
     SKB_TRY(periphery_dev(fl, fl->shell[0], (const double *)fl->in_shell.ptr, eta, d_v, 1));
+    // + psc_.flow(r_trg, eta, time) + bs_.flow(r_trg, eta)                                  system.cpp:358-359
+    const double *d_trg = (const double *)fl->fib[0]->devs[0].r_trg.ptr;
+    const int bs = 128;
+    const unsigned nblk = (unsigned)((n_trg + bs - 1) / bs);
+    if (fl->n_points > 0) {
+        oseen_contract_add_kernel<<<nblk, bs, 0, fl->stream>>>((const double *)fl->pt_pos.ptr,
+                                                               (const double *)fl->pt_force.ptr, fl->n_points, d_trg,
+                                                               n_trg, 1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps, d_v);
+        rotlet_add_kernel<<<nblk, bs, 0, fl->stream>>>((const double *)fl->pt_pos.ptr,
+                                                       (const double *)fl->pt_torque.ptr, fl->n_points, d_trg, n_trg,
+                                                       1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps * kEps, d_v);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(2);
+        fl->launches += 2;
+    }
+    if (fl->has_background) {
+        background_add_kernel<<<nblk, bs, 0, fl->stream>>>(d_trg, n_trg, fl->bg_comp[0], fl->bg_comp[1], fl->bg_comp[2],
+                                                           fl->bg_scale[0], fl->bg_scale[1], fl->bg_scale[2],
+                                                           fl->bg_uniform[0], fl->bg_uniform[1], fl->bg_uniform[2], d_v);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        fl->launches += 1;
+    }
     CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
     CUDA_TRY(cudaMemcpyAsync(vel, d_v, (size_t)n_trg * 24, cudaMemcpyDeviceToHost, fl->stream));
     CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));

@@ -194,3 +194,26 @@ def test_velocity_at_targets(n_trg):
                          body["torques"], eta)
     ref += orc.periphery_flow(r_trg, shell["pos"], shell["normals"], shell["density"], eta)
     _check(v, ref)
+
+
+def test_velocity_at_targets_with_point_and_background_sources():
+    # + psc_.flow + bs_.flow (system.cpp:358-359; point_source.cpp:16-54, background_source.cpp:15-24)
+    fib, shell, body = make_system(35, 10, 200, 0, 0)
+    rng = np.random.default_rng(2)
+    r_trg = rng.uniform(-2, 2, (500, 3))
+    pts = rng.uniform(-1, 1, (3, 3))
+    r_trg[0] = pts[0]                      # a target exactly on a point source: skipped, no NaN
+    r_trg[1] = pts[1] + 1e-7               # inside the regularisation radius (eps = 1e-5)
+    pf, ptq = rng.normal(size=(3, 3)), rng.normal(size=(3, 3))
+    comp, scale, uni = [1, 0, 2], np.array([0.5, -0.25, 0.0]), np.array([0.1, 0.0, -0.3])
+    eta = 0.8
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        fl.set_point_sources(pts, pf, ptq)
+        fl.set_background(comp, scale, uni)
+        v = fl.velocity_at_targets(r_trg, fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+    ref = orc.fiber_flow(r_trg, fib["pos"], fib["n_nodes"], fib["lengths"], fib["forces"], eta, subtract_self=False)
+    ref += orc.periphery_flow(r_trg, shell["pos"], shell["normals"], shell["density"], eta)
+    ref += orc.oseen_contract(pts, r_trg, pf, eta) + orc.rotlet(pts, r_trg, ptq, eta)
+    ref += uni[None, :] + r_trg[:, comp] * scale[None, :]
+    _check(v, ref)
