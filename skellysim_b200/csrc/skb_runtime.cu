@@ -485,8 +485,7 @@ static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long lo
         s.n_pad = n_pad;
         s.has_normals = false;
         s.has_weights = false;
-        s.self_state = -1;
-        s.sym_plan_valid = false;
+        s.self_state = -1; // (the symmetric plan depends on the block count only and survives position updates)
         if (n_src == 0)
             continue;
         CUDA_TRY(cudaSetDevice(d.info.dev));
