@@ -217,3 +217,13 @@ def test_velocity_at_targets_with_point_and_background_sources():
     ref += orc.oseen_contract(pts, r_trg, pf, eta) + orc.rotlet(pts, r_trg, ptq, eta)
     ref += uni[None, :] + r_trg[:, comp] * scale[None, :]
     _check(v, ref)
+
+
+def test_cpp_flow_engine():
+    # tests/cpp/flow_test.cpp: C++ host code -> skelly_b200/flow.hpp -> C ABI, against host loops
+    import os
+    import subprocess
+    exe = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cpp", "flow_test")
+    assert os.path.exists(exe), "tests/cpp/flow_test not built (run __graft_entry__.build())"
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stdout + r.stderr
