@@ -50,8 +50,8 @@ int main() {
         }
     }
     Matrix empty;
-    skelly_b200::FlowEngine eng(0), eng_copy = eng;
     try {
+        skelly_b200::FlowEngine eng(0), eng_copy = eng;
         eng.set_fibers(r_fib, std::vector<int>(n_fibers, n), std::vector<double>(n_fibers, L));
         eng.set_periphery(r_shell, n_shell_m);
         eng.set_bodies(empty, empty, empty);
