@@ -21,9 +21,8 @@ namespace skelly_b200 {
 template <class M> class FlowEngineT {
   public:
     explicit FlowEngineT(int device = 0) {
-        skb_flow *p = nullptr;
-        check(skb_flow_create(device, &p), "skb_flow_create");
-        fl_.reset(p, [](skb_flow *q) { skb_flow_destroy(q); });
+        st_ = std::make_shared<State>();
+        check(skb_flow_create(device, &st_->fl), "skb_flow_create");
     }
 
     // ---- geometry: call after positions change (System::step), not per GMRES iteration ----
@@ -31,40 +30,40 @@ template <class M> class FlowEngineT {
     void set_fibers(const M &r_fib, const std::vector<int> &n_nodes, const std::vector<double> &lengths) {
         if (n_nodes.size() != lengths.size())
             throw std::runtime_error("skelly_b200: n_nodes / lengths size mismatch");
-        check(skb_flow_set_fibers(fl_.get(), r_fib.data(), n_nodes.data(), lengths.data(), (int)n_nodes.size()),
+        check(skb_flow_set_fibers(st_->fl, r_fib.data(), n_nodes.data(), lengths.data(), (int)n_nodes.size()),
               "skb_flow_set_fibers");
-        n_fib_ = r_fib.cols();
+        st_->n_fib = r_fib.cols();
     }
     void set_periphery(const M &node_pos, const M &node_normal) {
-        check(skb_flow_set_periphery(fl_.get(), node_pos.data(), node_normal.data(), node_pos.cols()),
+        check(skb_flow_set_periphery(st_->fl, node_pos.data(), node_normal.data(), node_pos.cols()),
               "skb_flow_set_periphery");
-        n_shell_ = node_pos.cols();
+        st_->n_shell = node_pos.cols();
     }
     void set_bodies(const M &node_pos, const M &node_normal, const M &centers) {
-        check(skb_flow_set_bodies(fl_.get(), node_pos.data(), node_normal.data(), node_pos.cols(), centers.data(),
+        check(skb_flow_set_bodies(st_->fl, node_pos.data(), node_normal.data(), node_pos.cols(), centers.data(),
                                   (int)centers.cols()),
               "skb_flow_set_bodies");
-        n_body_ = node_pos.cols();
+        st_->n_body = node_pos.cols();
     }
 
     // ---- the reference's flow() functions ----
     M fiber_flow(const M &r_trg, const M &fib_forces, double eta, bool subtract_self = true) const {
         M vel = M::Zero(3, r_trg.cols());
-        check(skb_flow_fibers(fl_.get(), r_trg.data(), r_trg.cols(), fib_forces.data(), eta, subtract_self ? 1 : 0,
+        check(skb_flow_fibers(st_->fl, r_trg.data(), r_trg.cols(), fib_forces.data(), eta, subtract_self ? 1 : 0,
                               vel.data()),
               "skb_flow_fibers");
         return vel;
     }
     M periphery_flow(const M &r_trg, const M &density, double eta) const {
         M vel = M::Zero(3, r_trg.cols());
-        check(skb_flow_periphery(fl_.get(), r_trg.data(), r_trg.cols(), density.data(), eta, vel.data()),
+        check(skb_flow_periphery(st_->fl, r_trg.data(), r_trg.cols(), density.data(), eta, vel.data()),
               "skb_flow_periphery");
         return vel;
     }
     /// forces_torques: 6 x n_bodies (body_container.cpp:128-135)
     M body_flow(const M &r_trg, const M &densities, const M &forces_torques, double eta) const {
         M vel = M::Zero(3, r_trg.cols());
-        check(skb_flow_bodies(fl_.get(), r_trg.data(), r_trg.cols(), densities.data(), forces_torques.data(), eta,
+        check(skb_flow_bodies(st_->fl, r_trg.data(), r_trg.cols(), densities.data(), forces_torques.data(), eta,
                               vel.data()),
               "skb_flow_bodies");
         return vel;
@@ -72,8 +71,8 @@ template <class M> class FlowEngineT {
     /// hydrodynamic part of System::apply_matvec: 3 x (N_f + N_s + N_b), targets [fibers | shell | bodies]
     M matvec_flow(const M &fib_forces, const M &shell_density, const M &body_densities, const M &forces_torques,
                   double eta) const {
-        M v = M::Zero(3, n_fib_ + n_shell_ + n_body_);
-        check(skb_flow_matvec(fl_.get(), fib_forces.data(), shell_density.data(), body_densities.data(),
+        M v = M::Zero(3, st_->n_fib + st_->n_shell + st_->n_body);
+        check(skb_flow_matvec(st_->fl, fib_forces.data(), shell_density.data(), body_densities.data(),
                               forces_torques.data(), eta, v.data()),
               "skb_flow_matvec");
         return v;
@@ -81,17 +80,21 @@ template <class M> class FlowEngineT {
     M velocity_at_targets(const M &r_trg, const M &fib_forces, const M &shell_density, const M &body_densities,
                           const M &forces_torques, double eta) const {
         M vel = M::Zero(3, r_trg.cols());
-        check(skb_flow_velocity_at_targets(fl_.get(), r_trg.data(), r_trg.cols(), fib_forces.data(),
+        check(skb_flow_velocity_at_targets(st_->fl, r_trg.data(), r_trg.cols(), fib_forces.data(),
                                            shell_density.data(), body_densities.data(), forces_torques.data(), eta,
                                            vel.data()),
               "skb_flow_velocity_at_targets");
         return vel;
     }
-    skb_flow *handle() const { return fl_.get(); }
+    skb_flow *handle() const { return st_->fl; }
 
   private:
-    std::shared_ptr<skb_flow> fl_; // copies share the device state, like the evaluators
-    long n_fib_ = 0, n_shell_ = 0, n_body_ = 0;
+    struct State { // copies of the engine share the device state and the geometry sizes, like the evaluators
+        skb_flow *fl = nullptr;
+        long n_fib = 0, n_shell = 0, n_body = 0;
+        ~State() { skb_flow_destroy(fl); }
+    };
+    std::shared_ptr<State> st_;
 };
 
 using FlowEngine = FlowEngineT<Matrix>;
