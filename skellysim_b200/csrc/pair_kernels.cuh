@@ -109,23 +109,10 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 }
 
 // ---------------------------------------------------------------------------------------------
-// 1/sqrt(r2) in FP64 with the reference's r == 0 rule.
-// MUFU.RSQ64H seed (rel. err <= 2^-22.4), masked to 0 for r2 below the smallest normal (r2 == 0 and
-// subnormal r2, which the seed instruction flushes), then y = y0 + y0 e (1/2 + 3/8 e), e = 1 - r2 y0^2:
+// 1/sqrt(r2) in FP64 with the reference's r == 0 rule (inlined stage-wise in the *_chains routines below):
+// MUFU.RSQ64H seed y0 (rel. err <= 2^-22.4), masked to 0 for r2 below the smallest normal (r2 == 0 and
+// subnormal r2, which the seed instruction flushes), then y = y0 + y0 h, h = e (1/2 + 3/8 e), e = 1 - r2 y0^2:
 // third-order, residual error ~(5/16) e^3 < 2^-64.  A zero seed stays exactly zero.
-// ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ double rinv_masked(double r2) {
-    double y0;
-    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2));
-    if (__double2hiint(r2) < 0x00100000)
-        y0 = 0.0;
-    const double t = r2 * y0;
-    const double e = fma(-t, y0, 1.0);
-    const double p = fma(0.375, e, 0.5);
-    const double q = y0 * e;
-    return fma(q, p, y0);
-}
-
 // ---------------------------------------------------------------------------------------------
 // C independent (target, source) pair chains evaluated stage by stage, so a warp always has C FP64
 // instructions in flight.  A single pair's chain is ~15 dependent FP64 instructions; issued back to back
