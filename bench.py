@@ -415,8 +415,21 @@ def main():
     stream = torch.cuda.current_stream().cuda_stream  # kernels are launched on torch's current stream
     d_rsrc = torch.from_numpy(r_src_all).to(dev)
     d_rtrg = torch.from_numpy(my_trg).to(dev)
+    # N > 1 with the symmetric layout: the self block (partial sums, needs the reduce-scatter) and the rank's remainder
+    # targets live in two contexts, so the remainder runs on a side stream WHILE the fiber rows are reduce-scattered
+    two_ctx = sym_layout and world > 1
+    ctx_rem, side, ev_g, ev_s = None, None, None, None
     ctx.set_sources_device(skb.KERNEL_STOKESLET, d_rsrc.data_ptr(), n_src, stream)
-    ctx.set_targets_device(d_rtrg.data_ptr(), n_my_trg, stream)
+    if two_ctx:
+        ctx.set_targets_device(d_rtrg.data_ptr(), n_src, stream)
+        ctx_rem = skb.Context(1, device_ids=[local_rank])
+        ctx_rem.set_symmetric(0)
+        ctx_rem.set_sources_device(skb.KERNEL_STOKESLET, d_rsrc.data_ptr(), n_src, stream)
+        ctx_rem.set_targets_device(d_rtrg.data_ptr() + 24 * n_src, n_my_trg - n_src, stream)
+        side = torch.cuda.Stream(device=dev)
+        ev_g, ev_s = torch.cuda.Event(), torch.cuda.Event()
+    else:
+        ctx.set_targets_device(d_rtrg.data_ptr(), n_my_trg, stream)
     d_f_gather = torch.zeros((world * src_chunk, 3), dtype=torch.float64, device=dev)  # all-gather landing zone
     d_f_mine = d_f_gather[rank * src_chunk:(rank + 1) * src_chunk]
     h_f_mine = torch.zeros((src_chunk, 3), dtype=torch.float64).pin_memory()
@@ -435,9 +448,21 @@ def main():
     # otherwise the tail ranks are short.  Keep it simple: require divisibility (sizes above are multiples of 32).
     def step_device():
         allgather_strengths(d_f_gather, d_f_mine)  # ONE NCCL all-gather per step (no-op at world == 1)
-        ctx.eval_device(skb.KERNEL_STOKESLET, d_f_gather.data_ptr(), d_u.data_ptr(), False, stream)
-        if world > 1 and sym_layout:  # fiber rows are per-rank partial sums of the symmetric block rows:
-            dist.reduce_scatter_tensor(d_u_mine, d_u_fib)  # every rank ends up with the velocities of ITS fibers
+        if two_ctx:
+            ev_g.record()
+            side.wait_event(ev_g)
+            ctx.eval_device(skb.KERNEL_STOKESLET, d_f_gather.data_ptr(), d_u.data_ptr(), False, stream)
+            if n_my_trg > n_src:
+                with torch.cuda.stream(side):
+                    ctx_rem.eval_device(skb.KERNEL_STOKESLET, d_f_gather.data_ptr(), d_u.data_ptr() + 24 * n_src,
+                                        False, side.cuda_stream)
+            ev_s.record(side)
+            # fiber rows are per-rank partial sums of the symmetric block rows: every rank ends up with the
+            # velocities of ITS fibers; the collective overlaps with the remainder targets on the side stream
+            dist.reduce_scatter_tensor(d_u_mine, d_u_fib)
+            torch.cuda.current_stream().wait_event(ev_s)
+        else:
+            ctx.eval_device(skb.KERNEL_STOKESLET, d_f_gather.data_ptr(), d_u.data_ptr(), False, stream)
 
     def step_e2e():
         d_f_mine.copy_(h_f_mine, non_blocking=True)
@@ -499,8 +524,12 @@ def main():
     e2e_ms, _, _ = timed(step_e2e, args.steps)
 
     pairs_total = float(n_src) * float(n_trg)
-    pairs_rank = (float(n_src) * float(n_src) / world + float(n_src) * float(n_my_trg - n_src)) if sym_layout \
-        else float(n_src) * float(n_my_trg)
+    if two_ctx:      # kernel_ms below is the symmetric context's (self block rows of this rank)
+        pairs_rank = float(n_src) * float(n_src) / world
+    elif sym_layout:
+        pairs_rank = float(n_src) * float(n_src) / world + float(n_src) * float(n_my_trg - n_src)
+    else:
+        pairs_rank = float(n_src) * float(n_my_trg)
     ms_per_step = tot_ms / args.steps
     value = pairs_total / (ms_per_step * 1e-3)
     e2e_val = pairs_total / (e2e_ms / args.steps * 1e-3)
@@ -574,6 +603,8 @@ def main():
             out["cpu_baseline"] = cpu_baseline_leg(r_src_all, f_all, r_trg_all)
     _log("headline + e2e + cpu baseline done")
     ctx.close()
+    if ctx_rem is not None:
+        ctx_rem.close()
     del flush
     mv = None if args.no_matvec else matvec_leg(torch, dist, skb, dev, local_rank, rank, world)
     if rank == 0:
