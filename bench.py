@@ -524,9 +524,7 @@ def main():
     e2e_ms, _, _ = timed(step_e2e, args.steps)
 
     pairs_total = float(n_src) * float(n_trg)
-    if two_ctx:      # kernel_ms below is the symmetric context's (self block rows of this rank)
-        pairs_rank = float(n_src) * float(n_src) / world
-    elif sym_layout:
+    if sym_layout:   # (N > 1: the remainder context runs concurrently inside the symmetric context's kernel interval)
         pairs_rank = float(n_src) * float(n_src) / world + float(n_src) * float(n_my_trg - n_src)
     else:
         pairs_rank = float(n_src) * float(n_my_trg)
