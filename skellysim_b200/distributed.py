@@ -48,3 +48,21 @@ def allgather_strengths(gathered, mine, group=None):
     if dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_gather_into_tensor(gathered, mine, group=group)
     return gathered
+
+
+def sym_row_owner(block_row: int, n_parts: int) -> int:
+    """Owner of block row I of the symmetric kernel's upper triangle (mirror of sym_row_owner in
+    csrc/pair_kernels.cuh): serpentine over rows, so every rank gets the same mix of long and short rows."""
+    k, m = divmod(block_row, n_parts)
+    return n_parts - 1 - m if (k & 1) else m
+
+
+def sym_block_pairs(n_blocks: int, part: int, n_parts: int):
+    """(I, J) block pairs a rank evaluates in both directions: rows it owns of the strict upper triangle, plus its
+    diagonal blocks (I, I)."""
+    for i in range(n_blocks):
+        if sym_row_owner(i, n_parts) != part:
+            continue
+        yield i, i
+        for j in range(i + 1, n_blocks):
+            yield i, j
