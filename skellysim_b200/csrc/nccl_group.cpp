@@ -22,6 +22,7 @@ struct NcclApi {
     ncclResult_t (*GroupStart)() = nullptr;
     ncclResult_t (*GroupEnd)() = nullptr;
     ncclResult_t (*AllGather)(const void *, void *, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*ReduceScatter)(const void *, void *, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(ncclResult_t) = nullptr;
 };
 
@@ -43,6 +44,7 @@ int load_api(NcclApi &api) {
     LOAD(GroupStart, "ncclGroupStart")
     LOAD(GroupEnd, "ncclGroupEnd")
     LOAD(AllGather, "ncclAllGather")
+    LOAD(ReduceScatter, "ncclReduceScatter")
     LOAD(GetErrorString, "ncclGetErrorString")
 #undef LOAD
     return SKB_OK;
@@ -92,6 +94,25 @@ int nccl_group_allgather_inplace(void *group, void *const *bufs, size_t count, c
         r = r2;
     if (r != 0)
         return set_error(SKB_ERR_NCCL, "ncclAllGather failed: %s", g->api.GetErrorString(r));
+    return SKB_OK;
+}
+
+int nccl_group_reduce_scatter(void *group, void *const *send, void *const *recv, size_t count,
+                              const cudaStream_t *streams) {
+    NcclGroup *g = static_cast<NcclGroup *>(group);
+    if (!g)
+        return set_error(SKB_ERR_STATE, "NCCL group missing");
+    enum { kNcclSum = 0 }; // ncclRedOp_t::ncclSum
+    ncclResult_t r = g->api.GroupStart();
+    for (size_t i = 0; r == 0 && i < g->comms.size(); ++i) {
+        cudaSetDevice(g->devs[i]);
+        r = g->api.ReduceScatter(send[i], recv[i], count, kNcclFloat64, kNcclSum, g->comms[i], streams[i]);
+    }
+    ncclResult_t r2 = g->api.GroupEnd();
+    if (r == 0)
+        r = r2;
+    if (r != 0)
+        return set_error(SKB_ERR_NCCL, "ncclReduceScatter failed: %s", g->api.GetErrorString(r));
     return SKB_OK;
 }
 

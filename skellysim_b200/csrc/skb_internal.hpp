@@ -73,6 +73,10 @@ struct DeviceState {
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
     long long trg_begin = 0, n_trg = 0; // this device's block of the global target list
+    // symmetric multi-device layout: targets = [all n_self leading targets | remainder rows [rem_begin, +rem_count)]
+    long long rem_begin = 0, rem_count = 0;
+    int sym_part = 0, sym_parts = 1;    // block rows of the self-interaction this device evaluates
+    skb::DevBuf u_rs;                   // reduce-scatter output (this device's chunk of the leading rows)
     skb::DevBuf r_trg, u, partial, scratch;
     SourceSet src[2];
 };
@@ -83,7 +87,11 @@ struct skb_ctx {
     int force_T = 0, force_S = 0;
     int sym_mode = -1; // -1 auto, 0 never, 1 whenever the sources are the leading targets
     bool last_was_sym = false;
-    int sym_part = 0, sym_parts = 1; // this context evaluates block rows owned by part `sym_part` of `sym_parts`
+    // single-process multi-device symmetric layout (host-pointer API): host copies of the positions decide it
+    std::vector<double> h_trg, h_src[2];
+    bool sym_layout = false;    // devices currently hold the targets in the symmetric layout
+    bool layout_dirty = false;  // positions changed since the devices' target layout was decided
+    long long n_self = 0;       // leading targets that are the Stokeslet sources
     skb_eval_stats stats{};
     bool kernel_events_pending = false; // device-pointer path: kernel_ms is read back lazily
     void *nccl = nullptr; // NcclGroup*, multi-device contexts only
@@ -102,6 +110,9 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
 int nccl_group_create(size_t n, const std::function<int(int)> &device_of, void **out);
 int nccl_group_allgather_inplace(void *group, void *const *bufs, size_t count_per_rank_doubles,
                                  const cudaStream_t *streams);
+// recv[g] (count doubles) = sum over ranks of send[r][g*count : (g+1)*count]
+int nccl_group_reduce_scatter(void *group, void *const *send, void *const *recv, size_t count_per_rank_doubles,
+                              const cudaStream_t *streams);
 void nccl_group_destroy(void *group);
 
 } // namespace skb

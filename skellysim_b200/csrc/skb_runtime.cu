@@ -329,6 +329,7 @@ int skb_ctx_destroy(skb_ctx *ctx) {
         d.u.release();
         d.partial.release();
         d.scratch.release();
+        d.u_rs.release();
         for (auto &s : d.src) {
             s.r.release();
             s.normals.release();
@@ -395,8 +396,8 @@ int skb_ctx_set_sym_partition(skb_ctx *ctx, int part, int n_parts) {
         return set_error(SKB_ERR_INVALID, "skb_ctx_set_sym_partition: need 0 <= part < n_parts");
     if (ctx->devs.size() != 1)
         return set_error(SKB_ERR_INVALID, "skb_ctx_set_sym_partition: single-GPU contexts only");
-    ctx->sym_part = part;
-    ctx->sym_parts = n_parts;
+    ctx->devs[0].sym_part = part;
+    ctx->devs[0].sym_parts = n_parts;
     return SKB_OK;
 }
 
@@ -441,6 +442,14 @@ static int set_targets_impl(skb_ctx *ctx, const double *r_trg, long long n_trg, 
         return set_error(SKB_ERR_INVALID, "set_targets: bad arguments (n_trg=%lld)", n_trg);
     if (on_device && ctx->devs.size() != 1)
         return set_error(SKB_ERR_INVALID, "device-pointer entry points need a single-GPU context");
+    if (!on_device && ctx->devs.size() > 1) {
+        // multi-device context: the device layout of the targets (plain block partition, or the symmetric layout
+        // when they start with the Stokeslet sources) is decided at the next evaluation, see update_layout()
+        ctx->h_trg.assign(r_trg, r_trg + 3 * n_trg);
+        ctx->n_trg = n_trg;
+        ctx->layout_dirty = true;
+        return SKB_OK;
+    }
     partition_targets(ctx, n_trg);
     for (auto &d : ctx->devs) {
         d.src[0].self_state = -1;
@@ -462,6 +471,81 @@ static int set_targets_impl(skb_ctx *ctx, const double *r_trg, long long n_trg, 
     return SKB_OK;
 }
 
+namespace skb {
+static long long sym_mem_budget();
+}
+
+// Multi-device contexts (host-pointer API): put the targets on the devices.  Plain layout: contiguous blocks.
+// Symmetric layout (the targets start with the Stokeslet sources, no stresslet sources in this context): every
+// device holds ALL n_self leading targets -- it evaluates its serpentine share of the self-interaction's block rows
+// and produces partial sums for all of them -- followed by its block of the remaining targets.
+static int update_layout(skb_ctx *ctx) {
+    if (ctx->devs.size() < 2 || !ctx->layout_dirty)
+        return SKB_OK;
+    const long long P = (long long)ctx->devs.size();
+    const long long n_trg = ctx->n_trg;
+    const long long n_sl = ctx->devs[0].src[SKB_STOKESLET].n, n_dl = ctx->devs[0].src[SKB_STRESSLET].n;
+    const long long block = (long long)kSymThreads * 4;
+    bool want = ctx->sym_mode != 0 && n_dl <= 0 && n_sl >= (ctx->sym_mode == 1 ? 2 : 8) * block && n_trg >= n_sl &&
+                (long long)ctx->h_src[SKB_STOKESLET].size() == 3 * n_sl &&
+                std::memcmp(ctx->h_trg.data(), ctx->h_src[SKB_STOKESLET].data(), (size_t)n_sl * 24) == 0;
+    if (want) {
+        const long long n_pad = ctx->devs[0].src[SKB_STOKESLET].n_pad;
+        if ((n_pad / block) * n_pad * 24 > sym_mem_budget())
+            want = false;
+    }
+    ctx->sym_layout = want;
+    ctx->n_self = want ? n_sl : 0;
+    if (!want) {
+        partition_targets(ctx, n_trg);
+        for (auto &d : ctx->devs) {
+            d.sym_part = 0;
+            d.sym_parts = 1;
+            d.rem_begin = d.rem_count = 0;
+        }
+    } else {
+        const long long n_rem = n_trg - n_sl, chunk = (n_rem + P - 1) / P;
+        for (long long g = 0; g < P; ++g) {
+            DeviceState &d = ctx->devs[g];
+            d.rem_begin = std::min(n_rem, g * chunk);
+            d.rem_count = std::min(n_rem, (g + 1) * chunk) - d.rem_begin;
+            d.trg_begin = 0;
+            d.n_trg = n_sl + d.rem_count;
+            d.sym_part = (int)g;
+            d.sym_parts = (int)P;
+        }
+    }
+    for (auto &d : ctx->devs) {
+        d.src[0].self_state = want ? 1 : 0; // decided on the host copies
+        d.src[1].self_state = 0;
+        if (d.n_trg == 0)
+            continue;
+        CUDA_TRY(cudaSetDevice(d.info.dev));
+        const long long chunk_f = want ? (ctx->n_self + P - 1) / P : 0;
+        const long long u_rows = std::max(d.n_trg, chunk_f * P);
+        SKB_TRY(d.r_trg.ensure((size_t)d.n_trg * 24));
+        SKB_TRY(d.u.ensure((size_t)u_rows * 24));
+        if (want) {
+            SKB_TRY(d.u_rs.ensure((size_t)chunk_f * 24));
+            CUDA_TRY(cudaMemcpyAsync(d.r_trg.ptr, ctx->h_trg.data(), (size_t)ctx->n_self * 24, cudaMemcpyHostToDevice,
+                                     d.stream));
+            if (d.rem_count > 0)
+                CUDA_TRY(cudaMemcpyAsync((double *)d.r_trg.ptr + 3 * ctx->n_self,
+                                         ctx->h_trg.data() + 3 * (ctx->n_self + d.rem_begin), (size_t)d.rem_count * 24,
+                                         cudaMemcpyHostToDevice, d.stream));
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(d.r_trg.ptr, ctx->h_trg.data() + 3 * d.trg_begin, (size_t)d.n_trg * 24,
+                                     cudaMemcpyHostToDevice, d.stream));
+        }
+    }
+    for (auto &d : ctx->devs) {
+        CUDA_TRY(cudaSetDevice(d.info.dev));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+    }
+    ctx->layout_dirty = false;
+    return SKB_OK;
+}
+
 static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long long n_src, bool on_device,
                             cudaStream_t user) {
     if (!ctx)
@@ -479,6 +563,10 @@ static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long lo
     const int fdim_packed = kind == SKB_STOKESLET ? 3 : 6;
     const long long P = (long long)ctx->devs.size();
     const long long chunk = (n_src + P - 1) / P; // all-gather slot per device
+    if (!on_device && P > 1) {
+        ctx->h_src[kind].assign(r_src, r_src + 3 * n_src);
+        ctx->layout_dirty = true;
+    }
     for (auto &d : ctx->devs) {
         SourceSet &s = d.src[kind];
         s.n = n_src;
@@ -581,11 +669,11 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
     }
     if (s.self_state != 1)
         return SKB_OK;
-    if (!s.sym_plan_valid || s.sym_T != T || s.sym_nb != (int)nb || s.sym_part != ctx->sym_part ||
-        s.sym_parts != ctx->sym_parts) {
+    if (!s.sym_plan_valid || s.sym_T != T || s.sym_nb != (int)nb || s.sym_part != d.sym_part ||
+        s.sym_parts != d.sym_parts) {
         // work items: (I, [J0,J1)) over the strict upper triangle of blocks, rows cut into near-equal chunks
         int occ = 3;
-        const long long pairs = nb * (nb - 1) / 2 / ctx->sym_parts;
+        const long long pairs = nb * (nb - 1) / 2 / d.sym_parts;
         const long long slots = (long long)d.info.num_sms * occ;
         long long chunk = std::max<long long>(1, pairs / (slots * 6));
         std::vector<SymItem> items;
@@ -593,7 +681,7 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
         for (int I = 0; I < nb; ++I) {
             row_begin[I] = (int)items.size();
             const int len = (int)nb - 1 - I;
-            if (len <= 0 || sym_row_owner(I, ctx->sym_parts) != ctx->sym_part)
+            if (len <= 0 || sym_row_owner(I, d.sym_parts) != d.sym_part)
                 continue;
             const int n_chunks = (int)((len + chunk - 1) / chunk);
             for (int c = 0; c < n_chunks; ++c) {
@@ -623,8 +711,8 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
         s.sym_T = T;
         s.sym_nb = (int)nb;
         s.sym_items = (int)order.size();
-        s.sym_part = ctx->sym_part;
-        s.sym_parts = ctx->sym_parts;
+        s.sym_part = d.sym_part;
+        s.sym_parts = d.sym_parts;
         s.sym_plan_valid = true;
     }
     *use = 1;
@@ -715,7 +803,7 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
     // 2. pair sums
     // ---- symmetric path: sources are the leading targets (fiber -> fiber block of apply_matvec) ----
     long long n_sym = 0;
-    if (kind == SKB_STOKESLET && ctx->devs.size() == 1 && ctx->sym_mode != 0) {
+    if (kind == SKB_STOKESLET && (ctx->devs.size() == 1 || ctx->sym_layout) && ctx->sym_mode != 0) {
         int use = 0;
         SKB_TRY(sym_prepare(ctx, d, st, &use));
         if (use)
@@ -783,6 +871,9 @@ static int eval_host(skb_ctx *ctx, int kind, StrengthMode mode, const double *f_
         return set_error(SKB_ERR_INVALID, "eval: NULL strength or output pointer");
     if (mode == kNormalDensity && n_src > 0 && !ctx->devs[0].src[kind].has_normals)
         return set_error(SKB_ERR_STATE, "eval_double_layer: skb_set_source_normals has not been called");
+    SKB_TRY(update_layout(ctx));
+    const bool sym_layout = ctx->sym_layout && kind == SKB_STOKESLET; // (no stresslet sources exist in that layout)
+    const long long n_self = sym_layout ? ctx->n_self : 0;
     const int fdim = (kind == SKB_STOKESLET || mode == kNormalDensity) ? 3 : 9;
     const long long P = (long long)ctx->devs.size();
     const long long chunk = (n_src + P - 1) / P;
@@ -812,20 +903,62 @@ static int eval_host(skb_ctx *ctx, int kind, StrengthMode mode, const double *f_
         }
         SKB_TRY(nccl_group_allgather_inplace(ctx->nccl, bufs.data(), (size_t)chunk * fdim, sts.data()));
     }
-    // stage 2: every device evaluates its target block against all sources
+    // stage 2: every device evaluates its targets against all sources
+    const long long chunk_f = sym_layout ? (n_self + P - 1) / P : 0; // reduce-scatter slot (leading rows per device)
     for (long long g = 0; g < P; ++g) {
         DeviceState &d = ctx->devs[g];
         if (d.n_trg == 0)
             continue;
         CUDA_TRY(cudaSetDevice(d.info.dev));
-        if (accumulate)
-            CUDA_TRY(cudaMemcpyAsync(d.u.ptr, u_trg + 3 * d.trg_begin, (size_t)d.n_trg * 24, cudaMemcpyHostToDevice,
-                                     d.stream));
+        if (!sym_layout) {
+            if (accumulate)
+                CUDA_TRY(cudaMemcpyAsync(d.u.ptr, u_trg + 3 * d.trg_begin, (size_t)d.n_trg * 24,
+                                         cudaMemcpyHostToDevice, d.stream));
+        } else {
+            // leading rows are partial sums over the devices: the caller's values enter once (device 0)
+            if (chunk_f * P > n_self)
+                CUDA_TRY(cudaMemsetAsync((double *)d.u.ptr + 3 * n_self, 0, (size_t)(chunk_f * P - n_self) * 24,
+                                         d.stream));
+            if (accumulate) {
+                if (g == 0)
+                    CUDA_TRY(cudaMemcpyAsync(d.u.ptr, u_trg, (size_t)n_self * 24, cudaMemcpyHostToDevice, d.stream));
+                else
+                    CUDA_TRY(cudaMemsetAsync(d.u.ptr, 0, (size_t)n_self * 24, d.stream));
+                if (d.rem_count > 0)
+                    CUDA_TRY(cudaMemcpyAsync((double *)d.u.ptr + 3 * n_self, u_trg + 3 * (n_self + d.rem_begin),
+                                             (size_t)d.rem_count * 24, cudaMemcpyHostToDevice, d.stream));
+            }
+        }
         SKB_TRY(eval_on_device(ctx, d, kind, mode, (const double *)d.src[kind].f_raw.ptr, 2.0 * eta,
                                (double *)d.u.ptr, accumulate, d.stream, true, &launches, g == 0 ? &plan : nullptr, 1.0));
-        CUDA_TRY(cudaMemcpyAsync(u_trg + 3 * d.trg_begin, d.u.ptr, (size_t)d.n_trg * 24, cudaMemcpyDeviceToHost,
-                                 d.stream));
-        CUDA_TRY(cudaEventRecord(d.ev_t1, d.stream));
+        if (!sym_layout) {
+            CUDA_TRY(cudaMemcpyAsync(u_trg + 3 * d.trg_begin, d.u.ptr, (size_t)d.n_trg * 24, cudaMemcpyDeviceToHost,
+                                     d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev_t1, d.stream));
+        }
+    }
+    if (sym_layout) {
+        // one reduce-scatter of the leading rows: device g ends up with rows [g*chunk_f, (g+1)*chunk_f)
+        std::vector<void *> send(P), recv(P);
+        std::vector<cudaStream_t> sts(P);
+        for (long long g = 0; g < P; ++g) {
+            send[g] = ctx->devs[g].u.ptr;
+            recv[g] = ctx->devs[g].u_rs.ptr;
+            sts[g] = ctx->devs[g].stream;
+        }
+        SKB_TRY(nccl_group_reduce_scatter(ctx->nccl, send.data(), recv.data(), (size_t)chunk_f * 3, sts.data()));
+        for (long long g = 0; g < P; ++g) {
+            DeviceState &d = ctx->devs[g];
+            CUDA_TRY(cudaSetDevice(d.info.dev));
+            const long long b = std::min(n_self, g * chunk_f), e = std::min(n_self, (g + 1) * chunk_f);
+            if (e > b)
+                CUDA_TRY(cudaMemcpyAsync(u_trg + 3 * b, d.u_rs.ptr, (size_t)(e - b) * 24, cudaMemcpyDeviceToHost,
+                                         d.stream));
+            if (d.rem_count > 0)
+                CUDA_TRY(cudaMemcpyAsync(u_trg + 3 * (n_self + d.rem_begin), (double *)d.u.ptr + 3 * n_self,
+                                         (size_t)d.rem_count * 24, cudaMemcpyDeviceToHost, d.stream));
+            CUDA_TRY(cudaEventRecord(d.ev_t1, d.stream));
+        }
     }
     // stage 3: wait, collect timings
     double k_ms = 0, t_ms = 0;

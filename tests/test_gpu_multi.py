@@ -49,3 +49,43 @@ def test_multi_device_matches_single_device_bitwise_per_block():
         c2.set_sources(SL, rs)
         u2 = c2.eval(SL, f3)
     assert rel_max(u2, orc.stokeslet_direct(rs, f3, rt)) < 1e-12
+
+
+@pytest.mark.parametrize("n_gpus", [2, 4, 8])
+def test_multi_device_symmetric_layout(n_gpus):
+    # single process, P devices, targets = [sources | extra]: every device evaluates its serpentine share of the
+    # self-interaction's block rows for ALL leading targets; one NCCL reduce-scatter combines the partial sums
+    _need(n_gpus)
+    rng = np.random.default_rng(50 + n_gpus)
+    n_src, n_extra = 6000, 333
+    rs = rng.uniform(-2, 2, (n_src, 3))
+    rt = np.concatenate([rs, rng.uniform(-2, 2, (n_extra, 3))])
+    f = rng.uniform(-1, 1, (n_src, 3))
+    ref = orc.stokeslet_direct_cpu(rs, f, rt, 1.0)
+    with skb.Context(n_gpus) as c:
+        c.set_symmetric(1)
+        c.set_targets(rt)
+        c.set_sources(SL, rs)
+        u = c.eval(SL, f)
+        assert c.last_eval_was_symmetric()
+        u2 = c.eval(SL, f)
+        out = u.copy()
+        c.eval(SL, 0.5 * f, out=out, accumulate=True)
+        # new strengths, same positions
+        g = rng.uniform(-1, 1, (n_src, 3))
+        ug = c.eval(SL, g)
+        # a stresslet source set in the same context switches back to the plain block layout
+        c.set_sources(DL, rs[:100])
+        u_plain = c.eval(SL, f)
+        assert not c.last_eval_was_symmetric()
+        # targets that no longer start with the sources: plain layout as well
+        c.set_sources(DL, np.zeros((0, 3)))
+        rt2 = rt.copy()
+        rt2[5, 0] += 1e-3
+        c.set_targets(rt2)
+        u_moved = c.eval(SL, f)
+        assert not c.last_eval_was_symmetric()
+    for got, want in ((u, ref), (u_plain, ref), (out, 1.5 * ref), (ug, orc.stokeslet_direct_cpu(rs, g, rt, 1.0)),
+                      (u_moved, orc.stokeslet_direct_cpu(rs, f, rt2, 1.0))):
+        assert rel_max(got, want) < 1e-12 and rel_l2(got, want) < 1e-12
+    assert np.array_equal(u, u2)
