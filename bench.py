@@ -519,9 +519,35 @@ def main():
         n0 = capi.launch_count()
         tot_ms, wall, kms = timed(step_device, args.steps)
         launches = capi.launch_count() - n0
-    for _ in range(args.warmup):
-        step_e2e()
-    e2e_ms, _, _ = timed(step_e2e, args.steps)
+    e2e_path = "pinned host strengths -> H2D -> (all-gather) -> skb_eval_device -> (reduce-scatter) -> D2H velocities"
+    if world == 1:
+        # the call a SkellySim evaluator makes: skb_eval with HOST buffers (positions cached in a context, strengths
+        # in, velocities out; both copies inside the call), pinned buffers, wall clock around the synchronous call
+        ctx_host = skb.Context(1, device_ids=[local_rank])
+        if args.no_symmetric:
+            ctx_host.set_symmetric(0)
+        ctx_host.set_targets(my_trg)
+        ctx_host.set_sources(skb.KERNEL_STOKESLET, r_src_all)
+        f_np = h_f_mine.numpy()[:n_src]
+        u_np = h_u.numpy()[:n_my_trg]
+        for _ in range(args.warmup):
+            ctx_host.eval(skb.KERNEL_STOKESLET, f_np, out=u_np)
+        e2e_ms = 0.0
+        for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            ctx_host.eval(skb.KERNEL_STOKESLET, f_np, out=u_np)
+            e2e_ms += 1e3 * (time.perf_counter() - t0)
+        if rank == 0:
+            ref_sub = d_u.cpu().numpy()
+            assert np.abs(u_np - ref_sub).max() <= 1e-12 * np.abs(ref_sub).max(), "host-pointer path disagrees"
+        ctx_host.close()
+        e2e_path = "skb_eval (C ABI, host pointers, pinned buffers): H2D strengths + kernels + D2H velocities, wall clock"
+    else:
+        for _ in range(args.warmup):
+            step_e2e()
+        e2e_ms, _, _ = timed(step_e2e, args.steps)
 
     pairs_total = float(n_src) * float(n_trg)
     if sym_layout:   # (N > 1: the remainder context runs concurrently inside the symmetric context's kernel interval)
@@ -587,7 +613,7 @@ def main():
             "e2e": {"value": e2e_val, "unit": "pairs/s", "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(h_f_mine.numel() * 8 * world),
                     "d2h_bytes_per_step": int((world * n_src + (n_trg - n_src)) * 24 if sym_layout else n_trg * 24),
-                    "path": "pinned host strengths -> H2D -> (all-gather) -> skb_eval_device -> D2H velocities"},
+                    "path": e2e_path},
             "gpu_launches": launches_all,
             "launches_per_step": launches_all / args.steps / world,
             "clocks": clk.summary(),

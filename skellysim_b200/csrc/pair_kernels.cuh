@@ -458,14 +458,24 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
         for (int k = 0; k < kPrefetch && k < n_tiles; ++k)
             issue_tile(k);
     }
-    // coalesced load of this CTA's contiguous target block (AoS xyz) into shared memory; the tail is
+    // coalesced load of this CTA's contiguous target block (AoS xyz) into shared memory: 128-bit loads when the
+    // block starts 16-byte aligned (always, except for an odd-offset sub-range of a target list); the tail is
     // filled with the last valid target so no lane ever computes on garbage
     {
         long long n_valid = a.n_trg - t_base;
         n_valid = n_valid < kTileT ? n_valid : kTileT;
         const double *g = a.r_trg + 3 * t_base;
         const int n_dbl = (int)n_valid * 3;
-        for (int i = tid; i < kTileT * 3; i += kCtaThreads)
+        int done = 0;
+        if ((reinterpret_cast<unsigned long long>(g) & 15ULL) == 0) {
+            const int n_vec = n_dbl >> 1;
+            const double2 *g2 = reinterpret_cast<const double2 *>(g);
+            double2 *s2 = reinterpret_cast<double2 *>(trg_s);
+            for (int i = tid; i < n_vec; i += kCtaThreads)
+                s2[i] = __ldg(g2 + i);
+            done = n_vec << 1;
+        }
+        for (int i = done + tid; i < kTileT * 3; i += kCtaThreads)
             trg_s[i] = (i < n_dbl) ? __ldg(g + i) : __ldg(g + (n_dbl - 3) + (i % 3));
     }
     __syncthreads(); // barrier init + target block visible to everyone
