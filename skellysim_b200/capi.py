@@ -18,6 +18,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = os.environ.get("SKB_LIBRARY") or os.path.join(_HERE, "lib", "libskelly_b200.so")  # override: tuning A/B only
 _dp = C.POINTER(C.c_double)
 _lib = None
+BOUND_FUNCTIONS = ()  # names of the C-ABI functions this binding declares signatures for (filled by library())
 
 
 class SkbError(RuntimeError):
@@ -113,6 +114,8 @@ def library() -> C.CDLL:
         "skb_dense_last_stats": ([ctxp, C.POINTER(DenseStats)], C.c_int),
         "skb_flow_matvec_device": ([ctxp] + [C.c_void_p] * 5 + [C.c_double, C.c_void_p, C.c_void_p], C.c_int),
     }
+    global BOUND_FUNCTIONS
+    BOUND_FUNCTIONS = tuple(sorted(sig))
     for name, (args, res) in sig.items():
         fn = getattr(L, name)
         fn.argtypes = args
