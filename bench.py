@@ -134,13 +134,21 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm (oracle port of kernels::stokeslet_direct_cpu, all host threads)
 # ------------------------------------------------------------------------------------------------
+def host_threads() -> int:
+    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
 def cpu_sample_plan(orc, r_src, f_src, r_trg, budget_s: float):
     """Pick how many targets a bounded CPU sample evaluates so that one call takes ~budget_s."""
-    n_probe = min(r_trg.shape[0], max(256, 16 * orc.max_threads()))
+    n_probe = min(r_trg.shape[0], max(256, 16 * host_threads()))
     t0 = time.perf_counter()
-    orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n_probe], 1.0)
+    orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n_probe], 1.0, host_threads())
     t0 = time.perf_counter()
-    orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n_probe], 1.0)
+    orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n_probe], 1.0, host_threads())
     dt = time.perf_counter() - t0
     rate = r_src.shape[0] * n_probe / max(dt, 1e-9)
     n = int(min(r_trg.shape[0], max(n_probe, rate * budget_s / r_src.shape[0])))
@@ -152,12 +160,12 @@ def cpu_baseline_leg(r_src, f_src, r_trg, budget_s=10.0):
     n, _ = cpu_sample_plan(orc, r_src, f_src, r_trg, budget_s)
     calls, t0 = 0, time.perf_counter()
     while True:  # bounded sample: repeat the call until ~budget_s of CPU work has been timed
-        orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n], 1.0)
+        orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n], 1.0, host_threads())
         calls += 1
         dt = time.perf_counter() - t0
         if dt >= budget_s or calls >= 10000:
             break
-    return {"value": calls * r_src.shape[0] * n / dt, "unit": "pairs/s", "cores": orc.max_threads(), "kind": "port",
+    return {"value": calls * r_src.shape[0] * n / dt, "unit": "pairs/s", "cores": host_threads(), "kind": "port",
             "simd": {0: "scalar", 1: "avx2+fma", 2: "avx512"}[orc.simd_level()],
             "sample": f"all {r_src.shape[0]} sources x first {n} of {r_trg.shape[0]} targets, {calls} calls, "
                       f"{dt:.2f} s; OpenMP static target chunks as kernels.cpp:42-65 (the reference CPU path itself "
@@ -178,10 +186,10 @@ def run_reference_arm(args, rank, world):
     per_step = min(20.0, 150.0 / max(1, args.steps + args.warmup))
     n, _ = cpu_sample_plan(orc, r_src, f, r_trg, per_step)
     for _ in range(args.warmup):
-        orc.stokeslet_direct_cpu(r_src, f, r_trg[:n], 1.0)
+        orc.stokeslet_direct_cpu(r_src, f, r_trg[:n], 1.0, host_threads())
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        orc.stokeslet_direct_cpu(r_src, f, r_trg[:n], 1.0)
+        orc.stokeslet_direct_cpu(r_src, f, r_trg[:n], 1.0, host_threads())
     dt = time.perf_counter() - t0
     val = args.steps * r_src.shape[0] * n / dt
     sample = f"each step = all {r_src.shape[0]} sources x first {n} of {r_trg.shape[0]} targets"
@@ -191,7 +199,7 @@ def run_reference_arm(args, rank, world):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": workload_name(args.workload, n_fib, n_shell), "n_src": int(r_src.shape[0]),
                    "n_trg": int(r_trg.shape[0]), "sample": sample},
-        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": orc.max_threads(), "kind": "port",
+        "cpu_baseline": {"value": val, "unit": "pairs/s", "cores": host_threads(), "kind": "port",
                          "simd": {0: "scalar", 1: "avx2+fma", 2: "avx512"}[orc.simd_level()], "sample": sample},
         "e2e": {"value": val, "unit": "pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
