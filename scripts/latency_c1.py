@@ -47,6 +47,8 @@ for n_fib in (16, 64, 256):
         fl.set_bodies(e3, e3, e3)
         ft = np.zeros((0, 6))
         rec["skb_flow_matvec_us"] = wall(lambda: fl.matvec(f, e3, e3, ft, 1.0))
+        t6 = rng.uniform(-2, 2, (6, 3))
+        rec["skb_flow_velocity_at_6_targets_us"] = wall(lambda: fl.velocity_at_targets(t6, f, e3, e3, ft, 1.0))
     rec["cpu_port_all_threads_us"] = wall(lambda: orc.stokeslet_direct_cpu(r, f, r, 1.0), reps=100)
     rec["cpu_port_1_thread_us"] = wall(lambda: orc.stokeslet_direct_cpu(r, f, r, 1.0, 1), reps=20)
     if orc.refgpu_available():

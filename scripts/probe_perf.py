@@ -23,6 +23,10 @@ def run(ctx, kind, f, reps=5):
 
 
 QUICK = "--quick" in sys.argv
+SPLITS = (0, 4, 8, 16)
+for _a in sys.argv:
+    if _a.startswith("--splits="):
+        SPLITS = tuple(int(x) for x in _a.split("=")[1].split(","))
 
 
 def main():
@@ -39,11 +43,11 @@ def main():
             rs = rng.uniform(-1, 1, (ns, 3))
             rt = np.concatenate([rs, rng.uniform(-1, 1, (nt - ns, 3))]) if nt >= ns else rng.uniform(-1, 1, (nt, 3))
             ctx.set_targets(rt)
-            for kind, fdim, flop, name in ((0, 3, 28, "SL"), (1, 9, 40, "DL")):
+            for kind, fdim, flop, name in (((0, 3, 28, "SL"),) if "--sl-only" in sys.argv else ((0, 3, 28, "SL"), (1, 9, 40, "DL"))):
                 ctx.set_sources(kind, rs)
                 f = rng.uniform(-1, 1, (ns, fdim))
                 for T in (-1, 0, 1, 2, 4, 8):
-                    for S in ((0,) if (T <= 0 or QUICK) else (0, 4, 8, 16)):
+                    for S in ((0,) if (T <= 0 or QUICK) else SPLITS):
                         if T == -1:  # symmetric (Newton's third law) kernel, Stokeslet self-interaction only
                             if kind != 0 or nt < ns:
                                 continue

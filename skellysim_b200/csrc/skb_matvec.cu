@@ -7,6 +7,8 @@
 #include "../../include/skelly_b200_flow.h"
 
 #include <cmath>
+#include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -64,6 +66,23 @@ struct skb_flow {
     int n_points = 0;
     DevBuf pt_pos, pt_force, pt_torque;
     bool has_background = false;
+    // CUDA-graph replay of the launch-bound small-size calls (BASELINE C1, listener / streamline path)
+    struct GraphSlot {
+        cudaGraphExec_t exec = nullptr;
+        unsigned long long key = 0, seen = 0;
+        int launches = 0;
+        long long pairs = 0;
+        void reset() {
+            if (exec)
+                cudaGraphExecDestroy(exec);
+            exec = nullptr;
+            key = seen = 0;
+        }
+    } g_matvec, g_vat;
+    unsigned long long geom_version = 1;
+    bool graphs_enabled = true;
+    double *h_stage = nullptr; // pinned staging: the graph's memcpy nodes need fixed host addresses
+    size_t h_stage_cap = 0;
     int bg_comp[3] = {0, 1, 2};
     double bg_scale[3] = {0, 0, 0}, bg_uniform[3] = {0, 0, 0};
     // staging
@@ -182,6 +201,97 @@ static void split_forces_torques(const double *ft, int n_bodies, std::vector<dou
         }
 }
 
+
+// ---- CUDA-graph helpers ----------------------------------------------------------------------------------------
+static constexpr size_t kGraphMaxBytes = 512 * 1024; // strengths + velocities of one call; beyond this the copies
+                                                     // and kernels dwarf the launch gaps and the plain path is used
+static unsigned long long mix_key(unsigned long long h, unsigned long long v) {
+    h ^= v + 0x9e3779b97f4a7c15ULL + (h << 6) + (h >> 2);
+    return h;
+}
+static unsigned long long dbl_bits(double x) {
+    unsigned long long b;
+    std::memcpy(&b, &x, 8);
+    return b;
+}
+static int ensure_stage(skb_flow *fl, size_t n_doubles) {
+    if (n_doubles <= fl->h_stage_cap)
+        return SKB_OK;
+    if (fl->h_stage)
+        cudaFreeHost(fl->h_stage);
+    fl->h_stage = nullptr;
+    fl->h_stage_cap = 0;
+    fl->g_matvec.reset(); // graphs hold the old staging addresses
+    fl->g_vat.reset();
+    CUDA_TRY(cudaMallocHost((void **)&fl->h_stage, (n_doubles + 64) * 8));
+    fl->h_stage_cap = n_doubles + 64;
+    return SKB_OK;
+}
+
+// every device address a captured sequence may bake in: a reallocation anywhere invalidates the graph
+static unsigned long long buffer_key(const skb_flow *fl, int which) {
+    unsigned long long h = 0x1234567ULL;
+    const DevBuf *bufs[] = {&fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel,
+                            &fl->tmp,    &fl->pt_pos,   &fl->pt_force, &fl->pt_torque, &fl->centers, &fl->r_fib};
+    for (const DevBuf *b : bufs)
+        h = mix_key(h, (unsigned long long)(uintptr_t)b->ptr);
+    const skb_ctx *ctxs[] = {fl->fib[which], fl->shell[which], fl->body[which]};
+    for (const skb_ctx *c : ctxs) {
+        const DeviceState &d = c->devs[0];
+        h = mix_key(h, (unsigned long long)(uintptr_t)d.r_trg.ptr);
+        h = mix_key(h, (unsigned long long)(uintptr_t)d.partial.ptr);
+        for (int k = 0; k < 2; ++k) {
+            h = mix_key(h, (unsigned long long)(uintptr_t)d.src[k].f_packed.ptr);
+            h = mix_key(h, (unsigned long long)(uintptr_t)d.src[k].r.ptr);
+        }
+    }
+    return h;
+}
+
+// Run `body` (asynchronous work on fl->stream, fixed addresses only) either directly, as a capture followed by a
+// replay, or as a replay of the cached graph.  First call with a key: direct (it also warms every buffer); second
+// call with the same key: captured; afterwards: one cudaGraphLaunch per call.
+template <class Body> static int run_graphed(skb_flow *fl, skb_flow::GraphSlot &slot, unsigned long long key, Body body) {
+    if (slot.exec && slot.key == key) {
+        CUDA_TRY(cudaGraphLaunch(slot.exec, fl->stream));
+        count_launch(slot.launches);
+        fl->launches = slot.launches;
+        fl->pairs = slot.pairs;
+        return SKB_OK;
+    }
+    if (slot.seen == key && fl->graphs_enabled) {
+        if (slot.exec) {
+            cudaGraphExecDestroy(slot.exec);
+            slot.exec = nullptr;
+        }
+        cudaGraph_t graph = nullptr;
+        const long long before = launch_count();
+        CUDA_TRY(cudaStreamBeginCapture(fl->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = body();
+        cudaError_t e = cudaStreamEndCapture(fl->stream, &graph);
+        count_launch((int)(before - launch_count())); // nothing was launched while capturing
+        if (rc == SKB_OK && e == cudaSuccess && graph &&
+            cudaGraphInstantiate(&slot.exec, graph, nullptr, nullptr, 0) == cudaSuccess) {
+            cudaGraphDestroy(graph);
+            slot.key = key;
+            slot.launches = fl->launches;
+            slot.pairs = fl->pairs;
+            CUDA_TRY(cudaGraphLaunch(slot.exec, fl->stream));
+            count_launch(slot.launches);
+            return SKB_OK;
+        }
+        if (graph)
+            cudaGraphDestroy(graph);
+        (void)cudaGetLastError();
+        slot.exec = nullptr;
+        fl->graphs_enabled = false; // capture is not possible in this process: stay on the direct path
+        fl->launches = 0;
+        fl->pairs = 0;
+    }
+    slot.seen = key;
+    return body();
+}
+
 static void begin_stats(skb_flow *fl) {
     fl->launches = 0;
     fl->pairs = 0;
@@ -217,6 +327,8 @@ int skb_flow_create(int device, skb_flow **out) {
     CUDA_TRY(cudaEventCreate(&fl->ev1));
     CUDA_TRY(cudaEventCreate(&fl->evt0));
     CUDA_TRY(cudaEventCreate(&fl->evt1));
+    if (const char *e = getenv("SKB_GRAPHS"))
+        fl->graphs_enabled = atoi(e) != 0;
     for (int k = 0; k < 2; ++k) {
         SKB_TRY(ensure_ctx(fl.get(), &fl->fib[k]));
         SKB_TRY(ensure_ctx(fl.get(), &fl->shell[k]));
@@ -248,6 +360,10 @@ int skb_flow_destroy(skb_flow *fl) {
                       &fl->pt_pos, &fl->pt_force, &fl->pt_torque, &fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel, &fl->tmp};
     for (DevBuf *b : bufs)
         b->release();
+    fl->g_matvec.reset();
+    fl->g_vat.reset();
+    if (fl->h_stage)
+        cudaFreeHost(fl->h_stage);
     if (fl->ev0) cudaEventDestroy(fl->ev0);
     if (fl->ev1) cudaEventDestroy(fl->ev1);
     if (fl->evt0) cudaEventDestroy(fl->evt0);
@@ -275,6 +391,7 @@ int skb_flow_set_fibers(skb_flow *fl, const double *r_fib, const int *n_nodes, c
     fl->max_fiber_nodes = max_n;
     fl->h_r_fib.assign(r_fib, r_fib + 3 * fl->n_fib);
     fl->mv_dirty = true;
+    fl->geom_version++;
     CUDA_TRY(cudaSetDevice(fl->dev));
     for (int k = 0; k < 2; ++k)
         SKB_TRY(skb_set_sources(fl->fib[k], SKB_STOKESLET, r_fib, fl->n_fib));
@@ -310,6 +427,7 @@ int skb_flow_set_periphery(skb_flow *fl, const double *node_pos, const double *n
     fl->n_shell = n_nodes;
     fl->h_r_shell.assign(node_pos, node_pos + 3 * n_nodes);
     fl->mv_dirty = true;
+    fl->geom_version++;
     for (int k = 0; k < 2; ++k) {
         SKB_TRY(skb_set_sources(fl->shell[k], SKB_STRESSLET, node_pos, n_nodes));
         SKB_TRY(skb_set_source_normals(fl->shell[k], node_normal, n_nodes));
@@ -326,6 +444,7 @@ int skb_flow_set_bodies(skb_flow *fl, const double *node_pos, const double *node
     fl->n_bodies = n_bodies;
     fl->h_r_body.assign(node_pos, node_pos + 3 * n_nodes);
     fl->mv_dirty = true;
+    fl->geom_version++;
     for (int k = 0; k < 2; ++k) {
         SKB_TRY(skb_set_sources(fl->body[k], SKB_STRESSLET, node_pos, n_nodes));
         SKB_TRY(skb_set_source_normals(fl->body[k], node_normal, n_nodes));
@@ -416,6 +535,7 @@ int skb_flow_set_point_sources(skb_flow *fl, const double *positions, const doub
     if (!fl || n_points < 0 || (n_points > 0 && (!positions || !forces || !torques)))
         return set_error(SKB_ERR_INVALID, "skb_flow_set_point_sources: bad arguments");
     fl->n_points = n_points;
+    fl->geom_version++;
     if (n_points == 0)
         return SKB_OK;
     CUDA_TRY(cudaSetDevice(fl->dev));
@@ -432,6 +552,7 @@ int skb_flow_set_point_sources(skb_flow *fl, const double *positions, const doub
 int skb_flow_set_background(skb_flow *fl, const int *components, const double *scale_factor, const double *uniform) {
     if (!fl)
         return set_error(SKB_ERR_INVALID, "skb_flow_set_background: NULL");
+    fl->geom_version++;
     if (!components || !scale_factor || !uniform) {
         fl->has_background = false;
         return SKB_OK;
@@ -467,45 +588,77 @@ int skb_flow_velocity_at_targets(skb_flow *fl, const double *r_trg, int64_t n_tr
     if (fl->n_bodies > 0)
         split_forces_torques(body_forces_torques, fl->n_bodies, f, t);
     fl->cur = fl->stream;
-    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
-    SKB_TRY(upload(fl, fl->in_fib, fib_forces, (size_t)fl->n_fib * 3));
-    SKB_TRY(upload(fl, fl->in_shell, shell_density, (size_t)fl->n_shell * 3));
-    SKB_TRY(upload(fl, fl->in_body, body_densities, (size_t)fl->n_body * 3));
-    SKB_TRY(upload(fl, fl->in_force, f.data(), f.size()));
-    SKB_TRY(upload(fl, fl->in_torque, t.data(), t.size()));
+    const long long nf = fl->n_fib, ns = fl->n_shell, nb = fl->n_body;
     SKB_TRY(fl->vel.ensure((size_t)n_trg * 24));
     double *d_v = (double *)fl->vel.ptr;
+    // device-side sequence with the strengths at (ff, sd, bd, fo, to) and the velocities going to v_host
+    auto body = [&](const double *ff, const double *sd, const double *bd, const double *fo, const double *to,
+                    double *v_host) -> int {
+        SKB_TRY(upload(fl, fl->in_fib, ff, (size_t)nf * 3));
+        SKB_TRY(upload(fl, fl->in_shell, sd, (size_t)ns * 3));
+        SKB_TRY(upload(fl, fl->in_body, bd, (size_t)nb * 3));
+        SKB_TRY(upload(fl, fl->in_force, fo, f.size()));
+        SKB_TRY(upload(fl, fl->in_torque, to, t.size()));
+        // fc_->flow(r_trg, f_on_fibers, eta, /*subtract_self=*/false) + bc_.flow + shell_->flow   system.cpp:355-359
+        SKB_TRY(fibers_dev(fl, fl->fib[0], (const double *)fl->in_fib.ptr, eta, 0, d_v, 0, 0, 0));
+        SKB_TRY(bodies_dev(fl, fl->body[0], (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
+                           (const double *)fl->in_torque.ptr, eta, d_v, 1));
+        SKB_TRY(periphery_dev(fl, fl->shell[0], (const double *)fl->in_shell.ptr, eta, d_v, 1));
+        // + psc_.flow(r_trg, eta, time) + bs_.flow(r_trg, eta)                                  system.cpp:358-359
+        const double *d_trg = (const double *)fl->fib[0]->devs[0].r_trg.ptr;
+        const int bs = 128;
+        const unsigned nblk = (unsigned)((n_trg + bs - 1) / bs);
+        if (fl->n_points > 0) {
+            oseen_contract_add_kernel<<<nblk, bs, 0, fl->stream>>>((const double *)fl->pt_pos.ptr,
+                                                                   (const double *)fl->pt_force.ptr, fl->n_points,
+                                                                   d_trg, n_trg, 1.0 / (8.0 * M_PI * eta),
+                                                                   kReg * kReg, kEps, d_v);
+            rotlet_add_kernel<<<nblk, bs, 0, fl->stream>>>((const double *)fl->pt_pos.ptr,
+                                                           (const double *)fl->pt_torque.ptr, fl->n_points, d_trg,
+                                                           n_trg, 1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps * kEps,
+                                                           d_v);
+            CUDA_TRY(cudaGetLastError());
+            count_launch(2);
+            fl->launches += 2;
+        }
+        if (fl->has_background) {
+            background_add_kernel<<<nblk, bs, 0, fl->stream>>>(d_trg, n_trg, fl->bg_comp[0], fl->bg_comp[1],
+                                                               fl->bg_comp[2], fl->bg_scale[0], fl->bg_scale[1],
+                                                               fl->bg_scale[2], fl->bg_uniform[0], fl->bg_uniform[1],
+                                                               fl->bg_uniform[2], d_v);
+            CUDA_TRY(cudaGetLastError());
+            count_launch(1);
+            fl->launches += 1;
+        }
+        CUDA_TRY(cudaMemcpyAsync(v_host, d_v, (size_t)n_trg * 24, cudaMemcpyDeviceToHost, fl->stream));
+        return SKB_OK;
+    };
+    const size_t n_in = (size_t)(nf + ns + nb) * 3 + f.size() + t.size(), n_out = (size_t)n_trg * 3;
+    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
     CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
-    // fc_->flow(r_trg, f_on_fibers, eta, /*subtract_self=*/false) + bc_.flow + shell_->flow   system.cpp:355-359
-    SKB_TRY(fibers_dev(fl, fl->fib[0], (const double *)fl->in_fib.ptr, eta, 0, d_v, 0, 0, 0));
-    SKB_TRY(bodies_dev(fl, fl->body[0], (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
-                       (const double *)fl->in_torque.ptr, eta, d_v, 1));
-    SKB_TRY(periphery_dev(fl, fl->shell[0], (const double *)fl->in_shell.ptr, eta, d_v, 1));
-    // + psc_.flow(r_trg, eta, time) + bs_.flow(r_trg, eta)                                  system.cpp:358-359
-    const double *d_trg = (const double *)fl->fib[0]->devs[0].r_trg.ptr;
-    const int bs = 128;
-    const unsigned nblk = (unsigned)((n_trg + bs - 1) / bs);
-    if (fl->n_points > 0) {
-        oseen_contract_add_kernel<<<nblk, bs, 0, fl->stream>>>((const double *)fl->pt_pos.ptr,
-                                                               (const double *)fl->pt_force.ptr, fl->n_points, d_trg,
-                                                               n_trg, 1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps, d_v);
-        rotlet_add_kernel<<<nblk, bs, 0, fl->stream>>>((const double *)fl->pt_pos.ptr,
-                                                       (const double *)fl->pt_torque.ptr, fl->n_points, d_trg, n_trg,
-                                                       1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps * kEps, d_v);
-        CUDA_TRY(cudaGetLastError());
-        count_launch(2);
-        fl->launches += 2;
+    if (fl->graphs_enabled && (n_in + n_out) * 8 <= kGraphMaxBytes) {
+        // the listener / streamline integrator asks for 1-6 targets per call (streamline.cpp:11-35): launch-bound
+        SKB_TRY(ensure_stage(fl, n_in + n_out));
+        double *h = fl->h_stage;
+        double *h_ff = h, *h_sd = h_ff + 3 * nf, *h_bd = h_sd + 3 * ns, *h_f = h_bd + 3 * nb, *h_t = h_f + f.size();
+        double *h_v = h_t + t.size();
+        if (nf) std::memcpy(h_ff, fib_forces, (size_t)nf * 24);
+        if (ns) std::memcpy(h_sd, shell_density, (size_t)ns * 24);
+        if (nb) std::memcpy(h_bd, body_densities, (size_t)nb * 24);
+        if (!f.empty()) std::memcpy(h_f, f.data(), f.size() * 8);
+        if (!t.empty()) std::memcpy(h_t, t.data(), t.size() * 8);
+        unsigned long long key = mix_key(fl->geom_version, (unsigned long long)n_trg);
+        key = mix_key(key, dbl_bits(eta));
+        key = mix_key(key, buffer_key(fl, 0));
+        SKB_TRY(run_graphed(fl, fl->g_vat, key, [&]() { return body(h_ff, h_sd, h_bd, h_f, h_t, h_v); }));
+        CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+        CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+        SKB_TRY(finish_stats(fl));
+        std::memcpy(vel, h_v, (size_t)n_trg * 24);
+        return SKB_OK;
     }
-    if (fl->has_background) {
-        background_add_kernel<<<nblk, bs, 0, fl->stream>>>(d_trg, n_trg, fl->bg_comp[0], fl->bg_comp[1], fl->bg_comp[2],
-                                                           fl->bg_scale[0], fl->bg_scale[1], fl->bg_scale[2],
-                                                           fl->bg_uniform[0], fl->bg_uniform[1], fl->bg_uniform[2], d_v);
-        CUDA_TRY(cudaGetLastError());
-        count_launch(1);
-        fl->launches += 1;
-    }
+    SKB_TRY(body(fib_forces, shell_density, body_densities, f.data(), t.data(), vel));
     CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
-    CUDA_TRY(cudaMemcpyAsync(vel, d_v, (size_t)n_trg * 24, cudaMemcpyDeviceToHost, fl->stream));
     CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
     return finish_stats(fl);
 }
@@ -583,6 +736,7 @@ int skb_flow_set_target_window(skb_flow *fl, int64_t begin, int64_t end) {
     fl->win_begin = begin;
     fl->win_end = end;
     fl->mv_dirty = true;
+    fl->geom_version++;
     return SKB_OK;
 }
 
@@ -606,6 +760,45 @@ int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double *shell_
     if (fl->n_bodies > 0)
         split_forces_torques(body_forces_torques, fl->n_bodies, f, t);
     fl->cur = fl->stream;
+    const size_t n_in = (size_t)(nf + ns + nb) * 3 + f.size() + t.size(), n_out = (size_t)n_win * 3;
+    if (fl->graphs_enabled && (n_in + n_out) * 8 <= kGraphMaxBytes) {
+        // launch-bound size: stage through pinned memory and replay the whole sequence as one CUDA graph
+        SKB_TRY(ensure_stage(fl, n_in + n_out));
+        double *h = fl->h_stage;
+        double *h_ff = h, *h_sd = h_ff + 3 * nf, *h_bd = h_sd + 3 * ns, *h_f = h_bd + 3 * nb, *h_t = h_f + f.size();
+        double *h_v = h_t + t.size();
+        if (nf) std::memcpy(h_ff, fib_forces, (size_t)nf * 24);
+        if (ns) std::memcpy(h_sd, shell_density, (size_t)ns * 24);
+        if (nb) std::memcpy(h_bd, body_densities, (size_t)nb * 24);
+        if (!f.empty()) std::memcpy(h_f, f.data(), f.size() * 8);
+        if (!t.empty()) std::memcpy(h_t, t.data(), t.size() * 8);
+        SKB_TRY(fl->vel.ensure((size_t)n_win * 24));
+        unsigned long long key = mix_key(fl->geom_version, (unsigned long long)fl->w0);
+        key = mix_key(key, (unsigned long long)fl->w1);
+        key = mix_key(key, dbl_bits(eta));
+        key = mix_key(key, buffer_key(fl, 1));
+        const size_t nfs = f.size();
+        auto body = [&]() -> int {
+            SKB_TRY(upload(fl, fl->in_fib, h_ff, (size_t)nf * 3));
+            SKB_TRY(upload(fl, fl->in_shell, h_sd, (size_t)ns * 3));
+            SKB_TRY(upload(fl, fl->in_body, h_bd, (size_t)nb * 3));
+            SKB_TRY(upload(fl, fl->in_force, h_f, nfs));
+            SKB_TRY(upload(fl, fl->in_torque, h_t, nfs));
+            SKB_TRY(matvec_core(fl, (const double *)fl->in_fib.ptr, (const double *)fl->in_shell.ptr,
+                                (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
+                                (const double *)fl->in_torque.ptr, eta, (double *)fl->vel.ptr));
+            CUDA_TRY(cudaMemcpyAsync(h_v, fl->vel.ptr, (size_t)n_win * 24, cudaMemcpyDeviceToHost, fl->stream));
+            return SKB_OK;
+        };
+        CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
+        CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+        SKB_TRY(run_graphed(fl, fl->g_matvec, key, body));
+        CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+        CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+        SKB_TRY(finish_stats(fl));
+        std::memcpy(v_all, h_v, (size_t)n_win * 24);
+        return SKB_OK;
+    }
     CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
     SKB_TRY(upload(fl, fl->in_fib, fib_forces, (size_t)nf * 3));
     SKB_TRY(upload(fl, fl->in_shell, shell_density, (size_t)ns * 3));

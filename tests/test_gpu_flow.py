@@ -227,3 +227,56 @@ def test_cpp_flow_engine():
     assert os.path.exists(exe), "tests/cpp/flow_test not built (run __graft_entry__.build())"
     r = subprocess.run([exe], capture_output=True, text=True, timeout=120)
     assert r.returncode == 0, r.stdout + r.stderr
+
+
+def test_small_calls_replayed_as_cuda_graphs():
+    # launch-bound sizes (BASELINE C1, listener / streamline path) are captured on the third identical-shape call and
+    # replayed as one CUDA graph afterwards; strengths, targets and geometry keep changing underneath
+    fib, shell, body = make_system(41, 16, 120, 80, 1, nodes=(32,))
+    rng = np.random.default_rng(4)
+    eta = 1.1
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        for it in range(7):
+            fib_i = dict(fib, forces=rng.normal(size=fib["forces"].shape))
+            shell_i = dict(shell, density=rng.normal(size=shell["density"].shape))
+            v = fl.matvec(fib_i["forces"], shell_i["density"], body["density"], ft_of(body), eta)
+            _check(v, orc.matvec_flow(fib_i, shell_i, body, eta))
+        launches_replayed = fl.stats()["launches"]
+        assert launches_replayed > 0
+        # streamline-like: 6 fresh targets every call
+        for it in range(6):
+            r_trg = rng.uniform(-2, 2, (6, 3))
+            v = fl.velocity_at_targets(r_trg, fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+            ref = orc.fiber_flow(r_trg, fib["pos"], fib["n_nodes"], fib["lengths"], fib["forces"], eta, False)
+            ref += orc.body_flow(r_trg, body["pos"], body["normals"], body["density"], body["centers"],
+                                 body["forces"], body["torques"], eta)
+            ref += orc.periphery_flow(r_trg, shell["pos"], shell["normals"], shell["density"], eta)
+            _check(v, ref)
+        # a different target count in between (buffers may move), then back
+        r_big = rng.uniform(-2, 2, (3000, 3))
+        fl.velocity_at_targets(r_big, fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+        for it in range(4):
+            r_trg = rng.uniform(-2, 2, (6, 3))
+            v = fl.velocity_at_targets(r_trg, fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+            ref = orc.fiber_flow(r_trg, fib["pos"], fib["n_nodes"], fib["lengths"], fib["forces"], eta, False)
+            ref += orc.body_flow(r_trg, body["pos"], body["normals"], body["density"], body["centers"],
+                                 body["forces"], body["torques"], eta)
+            ref += orc.periphery_flow(r_trg, shell["pos"], shell["normals"], shell["density"], eta)
+            _check(v, ref)
+        # geometry update invalidates the matvec graph
+        fib2 = dict(fib, pos=fib["pos"] + 0.02)
+        fl.set_fibers(fib2["pos"], fib2["n_nodes"], fib2["lengths"])
+        for it in range(4):
+            v = fl.matvec(fib2["forces"], shell["density"], body["density"], ft_of(body), eta)
+            _check(v, orc.matvec_flow(fib2, shell, body, eta))
+
+
+def test_graphs_can_be_disabled(monkeypatch):
+    monkeypatch.setenv("SKB_GRAPHS", "0")
+    fib, shell, body = make_system(43, 8, 50, 0, 0, nodes=(16,))
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        for _ in range(4):
+            v = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), 1.0)
+    _check(v, orc.matvec_flow(fib, shell, body, 1.0))
