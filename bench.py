@@ -8,17 +8,23 @@
 Metric (BASELINE.json): Stokeslet pair-interactions/s.  One "step" = one Stokeslet evaluator call of a GMRES
 matvec (FiberContainer::flow's all-pairs call, fiber nodes -> fiber+shell nodes) on the BASELINE `configs[1]`
 geometry (ellipsoidal periphery + 1000 fibers x 32 nodes), positions resident on the device(s) exactly as they are
-between the matvecs of one timestep, strengths changing every step.
+between the matvecs of one timestep, strengths changing every step.  Every ordered (source, target) pair counts once;
+the fiber-fiber block is evaluated with the Newton's-third-law kernel (both directions from one geometry pass).
 
   value : whole-job pairs/s with the step's strengths already in HBM (device-pointer C-ABI entry points).
-  e2e   : the same step through the host-pointer path: strengths start in (pinned) host memory, velocities end in
-          host memory; H2D + D2H copies are inside the timed region.
-  N > 1 : one rank per GPU; targets AND sources block-partitioned over ranks (weak scaling: the suspension grows
-          so that pairs per GPU stay fixed: n_nodes ~ sqrt(N)); per step ONE NCCL all-gather of the source
-          strengths, then every rank evaluates its target block against all sources.  No other collective.
+  e2e   : N = 1: the call a SkellySim evaluator makes -- `skb_eval` with HOST buffers (pinned), H2D of the strengths
+          and D2H of the velocities inside the call, wall clock.  N > 1: pinned H2D + collectives + eval + D2H.
+  N > 1 : one rank per GPU, weak scaling (the suspension grows so that pairs per GPU stay fixed: nodes ~ sqrt(N)).
+          Every rank owns a serpentine set of block rows of the fiber-fiber interaction and a block of the remaining
+          targets; per step ONE NCCL all-gather of the source strengths and ONE reduce-scatter of the fiber
+          velocities (overlapped with the remainder targets).  `--no-symmetric`: plain kernel, targets block-partitioned,
+          all-gather only.
+  extras: `matvec` = hydrodynamic part of System::apply_matvec at 102 400 nodes (BASELINE C3), strong-scaled over the
+          ranks by target windows; `periphery_dense` = the periphery's dense operator (HBM-bound GEMV), N = 1 only;
+          `cpu_baseline` = CPU port of kernels::stokeslet_direct_cpu on all host cores (bounded sample), N = 1 only.
 
 Prints ONE JSON line (rank 0).  `--impl reference` times the CPU port of the reference's OpenMP direct path
-(oracle/, all host threads) on a bounded sample of the same workload.
+(oracle/, all host threads) on a bounded sample of the same workload; ranks > 0 exit at once.
 """
 from __future__ import annotations
 
