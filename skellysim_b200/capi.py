@@ -89,6 +89,10 @@ def library() -> C.CDLL:
         "skb_ctx_set_tuning": ([ctxp, C.c_int, C.c_int], C.c_int),
         "skb_measure_fp64_peak": ([ctxp, C.POINTER(C.c_double)], C.c_int),
         "skb_ctx_set_symmetric": ([ctxp, C.c_int], C.c_int),
+        "skb_plan_query": ([C.c_int, C.c_int64, C.c_int64, C.c_int, C.POINTER(C.c_int), C.c_int, C.c_int]
+                           + [C.POINTER(C.c_int)] * 4, C.c_int),
+        "skb_sym_plan_query": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
+                                C.POINTER(C.c_int)], C.c_int),
         "skb_ctx_set_sym_partition": ([ctxp, C.c_int, C.c_int], C.c_int),
         "skb_ctx_last_eval_was_symmetric": ([ctxp, C.POINTER(C.c_int)], C.c_int),
         # include/skelly_b200_flow.h
@@ -466,3 +470,24 @@ class Dense:
         s = DenseStats()
         _check(library().skb_dense_last_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in DenseStats._fields_}
+
+
+def plan_query(kind, n_trg, n_src, num_sms=148, occupancy=(8, 6, 4, 2), force_T=0, force_S=0) -> dict:
+    """Host-side launch planner of the plain pair kernel (no GPU needed)."""
+    occ = (C.c_int * 4)(*occupancy)
+    T, S, per, gx = C.c_int(), C.c_int(), C.c_int(), C.c_int()
+    _check(library().skb_plan_query(int(kind), int(n_trg), int(n_src), int(num_sms), occ, int(force_T), int(force_S),
+                                    C.byref(T), C.byref(S), C.byref(per), C.byref(gx)))
+    return {"T": T.value, "n_splits": S.value, "tiles_per_split": per.value, "grid_x": gx.value}
+
+
+def sym_plan_query(n_blocks, part=0, n_parts=1, num_sms=148):
+    """Host-side work list of the symmetric kernel (no GPU needed): list of (I, J0, J1, slot), row_begin."""
+    n = C.c_int()
+    _check(library().skb_sym_plan_query(int(n_blocks), int(part), int(n_parts), int(num_sms), 0, None, C.byref(n),
+                                        None))
+    items = (C.c_int * (4 * max(n.value, 1)))()
+    rb = (C.c_int * (n_blocks + 1))()
+    _check(library().skb_sym_plan_query(int(n_blocks), int(part), int(n_parts), int(num_sms), n.value, items,
+                                        C.byref(n), rb))
+    return [tuple(items[4 * i:4 * i + 4]) for i in range(n.value)], list(rb)

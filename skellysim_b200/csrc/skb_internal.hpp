@@ -105,6 +105,10 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
                    double *d_u_out, int accumulate, cudaStream_t st, bool record_events, int *launches,
                    LaunchPlan *plan_out, double scale_mul);
 
+struct SymItem;
+void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymItem> &order,
+                     std::vector<int> &row_begin);
+
 // NCCL is bound at run time (dlopen "libnccl.so.2"): a single-GPU user never needs it, and a host that
 // already loaded NCCL (PyTorch) shares that copy instead of getting a second one.
 int nccl_group_create(size_t n, const std::function<int(int)> &device_of, void **out);

@@ -384,6 +384,44 @@ int skb_ctx_set_symmetric(skb_ctx *ctx, int mode) {
     return SKB_OK;
 }
 
+int skb_plan_query(int kind, int64_t n_trg, int64_t n_src, int num_sms, const int *occupancy4, int force_T,
+                   int force_S, int *T, int *n_splits, int *tiles_per_split, int *grid_x) {
+    if ((kind != 0 && kind != 1) || n_trg < 1 || n_src < 1 || num_sms < 1 || !occupancy4 || !T || !n_splits ||
+        !tiles_per_split || !grid_x)
+        return set_error(SKB_ERR_INVALID, "skb_plan_query: bad arguments");
+    DeviceInfo di;
+    di.num_sms = num_sms;
+    for (int i = 0; i < 4; ++i)
+        di.occupancy[kind][i] = std::max(1, occupancy4[i]);
+    const LaunchPlan p = plan_launch(di, kind, n_trg, (int)((n_src + kSrcTile - 1) / kSrcTile), force_T, force_S);
+    *T = p.T;
+    *n_splits = p.n_splits;
+    *tiles_per_split = p.tiles_per_split;
+    *grid_x = (int)p.grid_x;
+    return SKB_OK;
+}
+
+int skb_sym_plan_query(int n_blocks, int part, int n_parts, int num_sms, int max_items, int *items4, int *n_items,
+                       int *row_begin) {
+    if (n_blocks < 1 || n_parts < 1 || part < 0 || part >= n_parts || num_sms < 1 || !n_items)
+        return set_error(SKB_ERR_INVALID, "skb_sym_plan_query: bad arguments");
+    std::vector<SymItem> order;
+    std::vector<int> rb;
+    build_sym_items(n_blocks, part, n_parts, num_sms, order, rb);
+    *n_items = (int)order.size();
+    if (items4)
+        for (int i = 0; i < (int)order.size() && i < max_items; ++i) {
+            items4[4 * i + 0] = order[i].I;
+            items4[4 * i + 1] = order[i].J0;
+            items4[4 * i + 2] = order[i].J1;
+            items4[4 * i + 3] = order[i].slot;
+        }
+    if (row_begin)
+        for (int b = 0; b <= n_blocks; ++b)
+            row_begin[b] = rb[b];
+    return SKB_OK;
+}
+
 int skb_ctx_last_eval_was_symmetric(const skb_ctx *ctx, int *yes) {
     if (!ctx || !yes)
         return set_error(SKB_ERR_INVALID, "skb_ctx_last_eval_was_symmetric: NULL");
@@ -640,6 +678,38 @@ static long long sym_mem_budget() {
     return e ? atoll(e) : (8LL << 30);
 }
 
+// Work items of the symmetric kernel: (I, [J0,J1)) over the strict upper triangle of nb blocks, restricted to the block
+// rows owned by `part`; rows are cut into near-equal chunks sized for ~6 waves of resident CTAs.  `order` is the launch
+// order (large items first); item.slot is its row-major position, row_begin[b]..row_begin[b+1] the slots of row b.
+void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymItem> &order,
+                     std::vector<int> &row_begin) {
+    const int occ = 3;
+    const long long pairs = (long long)nb * (nb - 1) / 2 / std::max(parts, 1);
+    const long long slots = (long long)num_sms * occ;
+    const long long chunk = std::max<long long>(1, pairs / (slots * 6));
+    std::vector<SymItem> items;
+    row_begin.assign(nb + 1, 0);
+    for (int I = 0; I < nb; ++I) {
+        row_begin[I] = (int)items.size();
+        const int len = nb - 1 - I;
+        if (len <= 0 || sym_row_owner(I, parts) != part)
+            continue;
+        const int n_chunks = (int)((len + chunk - 1) / chunk);
+        for (int c = 0; c < n_chunks; ++c) {
+            SymItem it;
+            it.I = I;
+            it.J0 = I + 1 + (int)((long long)len * c / n_chunks);
+            it.J1 = I + 1 + (int)((long long)len * (c + 1) / n_chunks);
+            it.slot = (int)items.size();
+            items.push_back(it);
+        }
+    }
+    row_begin[nb] = (int)items.size();
+    order = items;
+    std::stable_sort(order.begin(), order.end(),
+                     [](const SymItem &a, const SymItem &b) { return (a.J1 - a.J0) > (b.J1 - b.J0); });
+}
+
 // Decide whether the symmetric path applies and make sure its plan / buffers exist.
 static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) {
     *use = 0;
@@ -671,33 +741,9 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
         return SKB_OK;
     if (!s.sym_plan_valid || s.sym_T != T || s.sym_nb != (int)nb || s.sym_part != d.sym_part ||
         s.sym_parts != d.sym_parts) {
-        // work items: (I, [J0,J1)) over the strict upper triangle of blocks, rows cut into near-equal chunks
-        int occ = 3;
-        const long long pairs = nb * (nb - 1) / 2 / d.sym_parts;
-        const long long slots = (long long)d.info.num_sms * occ;
-        long long chunk = std::max<long long>(1, pairs / (slots * 6));
-        std::vector<SymItem> items;
-        std::vector<int> row_begin(nb + 1, 0);
-        for (int I = 0; I < nb; ++I) {
-            row_begin[I] = (int)items.size();
-            const int len = (int)nb - 1 - I;
-            if (len <= 0 || sym_row_owner(I, d.sym_parts) != d.sym_part)
-                continue;
-            const int n_chunks = (int)((len + chunk - 1) / chunk);
-            for (int c = 0; c < n_chunks; ++c) {
-                SymItem it;
-                it.I = I;
-                it.J0 = I + 1 + (int)((long long)len * c / n_chunks);
-                it.J1 = I + 1 + (int)((long long)len * (c + 1) / n_chunks);
-                it.slot = (int)items.size();
-                items.push_back(it);
-            }
-        }
-        row_begin[nb] = (int)items.size();
-        // launch the large items first (slot keeps the row-major position for the reduction)
-        std::vector<SymItem> order = items;
-        std::stable_sort(order.begin(), order.end(),
-                         [](const SymItem &a, const SymItem &b) { return (a.J1 - a.J0) > (b.J1 - b.J0); });
+        std::vector<SymItem> order;
+        std::vector<int> row_begin;
+        build_sym_items((int)nb, d.sym_part, d.sym_parts, d.info.num_sms, order, row_begin);
         SKB_TRY(s.sym_item_buf.ensure(order.size() * sizeof(SymItem) + 16));
         SKB_TRY(s.sym_row_begin.ensure(row_begin.size() * sizeof(int)));
         SKB_TRY(s.sym_P.ensure((size_t)nb * (size_t)s.n_pad * 24));

@@ -1,0 +1,67 @@
+"""CPU tests of the host-side planners (no GPU): the launch plan of the plain pair kernel and the work list of the
+symmetric kernel, through the C ABI (skb_plan_query / skb_sym_plan_query)."""
+import pytest
+
+from skellysim_b200 import capi
+
+SRC_TILE = 128
+
+
+@pytest.mark.parametrize("kind", [0, 1])
+@pytest.mark.parametrize("n_trg,n_src", [(1, 1), (6, 96000), (512, 512), (743, 1229), (8000, 32000), (40000, 32000),
+                                         (102400, 96000), (1000000, 1000000), (2829, 90496)])
+def test_launch_plan_covers_the_problem(kind, n_trg, n_src):
+    p = capi.plan_query(kind, n_trg, n_src)
+    assert p["T"] in (1, 2, 4, 8)
+    tile_t = 128 * p["T"]
+    assert p["grid_x"] == -(-n_trg // tile_t)                       # every target in exactly one tile
+    n_src_tiles = -(-n_src // SRC_TILE)
+    assert p["n_splits"] >= 1 and p["tiles_per_split"] >= 1
+    assert p["n_splits"] * p["tiles_per_split"] >= n_src_tiles      # every source tile in some split
+    assert (p["n_splits"] - 1) * p["tiles_per_split"] < n_src_tiles  # no empty split
+    assert p["n_splits"] <= 256
+
+
+def test_launch_plan_fills_the_gpu_for_few_targets():
+    # few targets, many sources (listener path / remainder targets): the source dimension must be split
+    p = capi.plan_query(0, 6, 96000)
+    assert p["grid_x"] == 1 and p["n_splits"] >= 100
+    # plenty of targets: no need for many splits
+    p = capi.plan_query(0, 1000000, 1000000)
+    assert p["grid_x"] * p["n_splits"] >= 148 * 2
+
+
+def test_forced_tuning_is_honoured():
+    p = capi.plan_query(0, 50000, 50000, force_T=2, force_S=5)
+    assert p["T"] == 2 and p["n_splits"] == 5
+
+
+@pytest.mark.parametrize("nb", [2, 3, 63, 178, 188])
+@pytest.mark.parametrize("parts", [1, 2, 8])
+def test_symmetric_work_list_covers_the_upper_triangle_exactly_once(nb, parts):
+    seen = set()
+    for part in range(parts):
+        items, row_begin = capi.sym_plan_query(nb, part, parts)
+        slots = sorted(it[3] for it in items)
+        assert slots == list(range(len(items)))                    # forward-partial slabs: a permutation
+        assert row_begin[0] == 0 and row_begin[-1] == len(items)
+        sizes = [j1 - j0 for (_, j0, j1, _) in items]
+        assert sizes == sorted(sizes, reverse=True)                # launch order: large items first
+        by_slot = {it[3]: it for it in items}
+        for b in range(nb):
+            for s in range(row_begin[b], row_begin[b + 1]):
+                assert by_slot[s][0] == b                          # row b's slabs are contiguous
+        for (i, j0, j1, _) in items:
+            assert 0 <= i < j0 < j1 <= nb
+            for j in range(j0, j1):
+                assert (i, j) not in seen
+                seen.add((i, j))
+    assert len(seen) == nb * (nb - 1) // 2
+
+
+def test_symmetric_work_list_is_balanced_across_parts():
+    loads = []
+    for part in range(8):
+        items, _ = capi.sym_plan_query(178, part, 8)
+        loads.append(sum(j1 - j0 for (_, j0, j1, _) in items))
+    assert max(loads) - min(loads) <= 0.03 * max(loads) + 8
