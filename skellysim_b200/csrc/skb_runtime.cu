@@ -686,7 +686,11 @@ void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymIt
     const int occ = 3;
     const long long pairs = (long long)nb * (nb - 1) / 2 / std::max(parts, 1);
     const long long slots = (long long)num_sms * occ;
-    const long long chunk = std::max<long long>(1, pairs / (slots * 6));
+    static const int waves = [] {
+        const char *e = getenv("SKB_SYM_WAVES"); // tuning knob: target number of CTA waves (finer items, smaller tail)
+        return e && atoi(e) > 0 ? atoi(e) : 6;
+    }();
+    const long long chunk = std::max<long long>(1, pairs / (slots * waves));
     std::vector<SymItem> items;
     row_begin.assign(nb + 1, 0);
     for (int I = 0; I < nb; ++I) {
