@@ -511,6 +511,7 @@ static int set_targets_impl(skb_ctx *ctx, const double *r_trg, long long n_trg, 
 
 namespace skb {
 static long long sym_mem_budget();
+static int sym_owned_rows(int nb, int part, int parts);
 }
 
 // Multi-device contexts (host-pointer API): put the targets on the devices.  Plain layout: contiguous blocks.
@@ -529,7 +530,7 @@ static int update_layout(skb_ctx *ctx) {
                 std::memcmp(ctx->h_trg.data(), ctx->h_src[SKB_STOKESLET].data(), (size_t)n_sl * 24) == 0;
     if (want) {
         const long long n_pad = ctx->devs[0].src[SKB_STOKESLET].n_pad;
-        if ((n_pad / block) * n_pad * 24 > sym_mem_budget())
+        if (((n_pad / block + P - 1) / P) * n_pad * 24 > sym_mem_budget())
             want = false;
     }
     ctx->sym_layout = want;
@@ -673,9 +674,24 @@ template <int T, int MINB> static cudaError_t launch_sym(const SymArgs &a, int n
     return cudaGetLastError();
 }
 
+// bytes the reverse partials of the symmetric kernel may occupy: SKB_SYM_MAX_BYTES, else 30 % of the device memory
+// (at least 8 GiB): 47 GB at 1e6 nodes on one 180 GB B200, 1/P of that per rank with the row partition
 static long long sym_mem_budget() {
-    const char *e = getenv("SKB_SYM_MAX_BYTES");
-    return e ? atoll(e) : (8LL << 30);
+    static long long cached = -1; // all devices of a box are alike; the environment is read once
+    if (cached >= 0)
+        return cached;
+    if (const char *e = getenv("SKB_SYM_MAX_BYTES"))
+        return cached = atoll(e);
+    size_t free_b = 0, total_b = 0;
+    if (cudaMemGetInfo(&free_b, &total_b) != cudaSuccess)
+        return cached = 8LL << 30;
+    return cached = std::max<long long>(8LL << 30, (long long)(0.30 * (double)total_b));
+}
+static int sym_owned_rows(int nb, int part, int parts) {
+    int n = 0;
+    for (int I = 0; I < nb; ++I)
+        n += sym_row_owner(I, parts) == part;
+    return n;
 }
 
 // Work items of the symmetric kernel: (I, [J0,J1)) over the strict upper triangle of nb blocks, restricted to the block
@@ -693,10 +709,14 @@ void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymIt
     const long long chunk = std::max<long long>(1, pairs / (slots * waves));
     std::vector<SymItem> items;
     row_begin.assign(nb + 1, 0);
+    int prow = 0;
     for (int I = 0; I < nb; ++I) {
         row_begin[I] = (int)items.size();
         const int len = nb - 1 - I;
-        if (len <= 0 || sym_row_owner(I, parts) != part)
+        if (sym_row_owner(I, parts) != part)
+            continue;
+        const int my_prow = prow++; // every owned row has a P row, in increasing I (sym_reduce_kernel counts the same way)
+        if (len <= 0)
             continue;
         const int n_chunks = (int)((len + chunk - 1) / chunk);
         for (int c = 0; c < n_chunks; ++c) {
@@ -705,6 +725,8 @@ void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymIt
             it.J0 = I + 1 + (int)((long long)len * c / n_chunks);
             it.J1 = I + 1 + (int)((long long)len * (c + 1) / n_chunks);
             it.slot = (int)items.size();
+            it.prow = my_prow;
+            it.pad = 0;
             items.push_back(it);
         }
     }
@@ -725,7 +747,7 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
     if (s.n < 2 * block || d.n_trg < s.n)
         return SKB_OK;
     const long long nb = s.n_pad / block; // n_pad is a multiple of 1024
-    if ((long long)nb * s.n_pad * 24 > sym_mem_budget())
+    if ((long long)sym_owned_rows((int)nb, d.sym_part, d.sym_parts) * s.n_pad * 24 > sym_mem_budget())
         return SKB_OK;
     if (s.self_state < 0) { // positions changed: are the first n_src targets bit-identical to the sources?
         SKB_TRY(s.sym_flag.ensure(sizeof(int)));
@@ -750,7 +772,12 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
         build_sym_items((int)nb, d.sym_part, d.sym_parts, d.info.num_sms, order, row_begin);
         SKB_TRY(s.sym_item_buf.ensure(order.size() * sizeof(SymItem) + 16));
         SKB_TRY(s.sym_row_begin.ensure(row_begin.size() * sizeof(int)));
-        SKB_TRY(s.sym_P.ensure((size_t)nb * (size_t)s.n_pad * 24));
+        if (s.sym_P.ensure((size_t)sym_owned_rows((int)nb, d.sym_part, d.sym_parts) * (size_t)s.n_pad * 24) !=
+            SKB_OK) { // not enough free memory for the reverse partials: the plain kernel serves this geometry
+            (void)cudaGetLastError();
+            s.self_state = 0;
+            return SKB_OK;
+        }
         SKB_TRY(s.sym_F.ensure(order.size() * (size_t)block * 24 + 16));
         SKB_TRY(s.sym_diag.ensure((size_t)T * (size_t)s.n_pad * 24));
         CUDA_TRY(cudaMemcpyAsync(s.sym_item_buf.ptr, order.data(), order.size() * sizeof(SymItem),

@@ -25,13 +25,14 @@ constexpr int kSymStages = 2;
 
 struct SymItem {
     int I, J0, J1, slot; // target block, source blocks [J0, J1) (all > I), forward-partial slab index
+    int prow, pad;       // row of P this item writes: index of I among the block rows owned by this part
 };
 
 struct SymArgs {
     const double *r;      // [n_pad*3] node positions, padded to a multiple of the block (pads replicate the last node)
     const double *f;      // [n_pad*3] packed Stokeslet strengths, zero padded
     const SymItem *items; // [gridDim.x]
-    double *P;            // [nb][n_pad*3]  reverse partials: P[I][node of J] = sum over targets in I
+    double *P;            // [owned rows][n_pad*3]  reverse partials: P[prow(I)][node of J] = sum over targets in I
     double *F;            // [n_items][block*3] forward partials of each item
     long long n_pad;
     int nb;
@@ -220,7 +221,7 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
             __syncthreads(); // fixed order of the 4 warps' additions per group -> reproducible
         }
         // reverse partial of (I -> block J0+k): one coalesced write
-        double *out = a.P + ((size_t)item.I * a.n_pad + (size_t)(item.J0 + k) * kBlock) * 3;
+        double *out = a.P + ((size_t)item.prow * a.n_pad + (size_t)(item.J0 + k) * kBlock) * 3;
         for (int i = tid; i < kBlock * 3; i += kSymThreads)
             out[i] = rev[i];
         __syncthreads();
@@ -238,7 +239,7 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
 }
 
 // Fixed-order combination for the symmetric path, one thread per velocity component of node `n` (block b):
-//   u = (acc ? u : 0) + scale * ( diag[n] + sum_{I < b} P[I][n] + sum_{items of row b} F[item][n - b*block] )
+//   u = (acc ? u : 0) + scale * ( diag[n] + sum_{owned I < b} P[prow(I)][n] + sum_{items of row b} F[item][n - b*block] )
 __global__ void sym_reduce_kernel(const double *__restrict__ diag, const double *__restrict__ P,
                                   const double *__restrict__ F, const int *__restrict__ row_item_begin, int block,
                                   long long n_pad, long long n_valid3, double scale, int accumulate,
@@ -253,9 +254,12 @@ __global__ void sym_reduce_kernel(const double *__restrict__ diag, const double 
     if (sym_row_owner(b, n_parts) == part)
         for (int y = 0; y < n_diag; ++y) // diagonal block, one slab per source tile of the block
             acc += diag[(size_t)y * n_valid * 3 + i];
+    int prow = 0; // P holds only the rows this part owns, in increasing I
     for (int I = 0; I < b; ++I)
-        if (sym_row_owner(I, n_parts) == part)
-            acc += P[((size_t)I * n_pad) * 3 + i];
+        if (sym_row_owner(I, n_parts) == part) {
+            acc += P[((size_t)prow * n_pad) * 3 + i];
+            ++prow;
+        }
     const long long local = i - (long long)b * block * 3;
     for (int it = row_item_begin[b]; it < row_item_begin[b + 1]; ++it)
         acc += F[(size_t)it * block * 3 + local];
