@@ -140,16 +140,45 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------
 # CPU arm (oracle port of kernels::stokeslet_direct_cpu, all host threads)
 # ------------------------------------------------------------------------------------------------
+_BEST_THREADS = None
+
+
 def host_threads() -> int:
-    """All host cores this process may use (torchrun exports OMP_NUM_THREADS=1, which must not throttle the CPU arm)."""
+    """Thread count of the CPU arms: every logical CPU of the affinity mask, or half of them (one per physical core
+    on an SMT-2 host) when that is faster -- decided once by cpu_pick_threads(); never OMP_NUM_THREADS, which torchrun
+    sets to 1."""
+    if _BEST_THREADS is not None:
+        return _BEST_THREADS
     try:
         return max(1, len(os.sched_getaffinity(0)))
     except AttributeError:
         return max(1, os.cpu_count() or 1)
 
 
+def cpu_pick_threads(orc, r_src, f_src, r_trg):
+    """Give the CPU arm its best shot: time a probe with all logical CPUs and with half of them, keep the faster."""
+    global _BEST_THREADS
+    if _BEST_THREADS is not None:
+        return _BEST_THREADS
+    full = host_threads()
+    cands = sorted({full, max(1, full // 2)}, reverse=True)
+    n = min(r_trg.shape[0], max(512, 16 * full))
+    best, best_t = full, float("inf")
+    for th in cands:
+        orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n], 1.0, th)
+        t0 = time.perf_counter()
+        for _ in range(3):
+            orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n], 1.0, th)
+        dt = time.perf_counter() - t0
+        if dt < best_t:
+            best, best_t = th, dt
+    _BEST_THREADS = best
+    return best
+
+
 def cpu_sample_plan(orc, r_src, f_src, r_trg, budget_s: float):
     """Pick how many targets a bounded CPU sample evaluates so that one call takes ~budget_s."""
+    cpu_pick_threads(orc, r_src, f_src, r_trg)
     n_probe = min(r_trg.shape[0], max(256, 16 * host_threads()))
     t0 = time.perf_counter()
     orc.stokeslet_direct_cpu(r_src, f_src, r_trg[:n_probe], 1.0, host_threads())
