@@ -384,6 +384,83 @@ def dense_leg(skb, hbm_peak_gbs, n_nodes=6000, reps=10):
 
 
 # ------------------------------------------------------------------------------------------------
+# "next" row N2: per-fiber dense operators on the device -- System::apply_matvec end to end for the fiber rows
+# (apply_fiber_force -> flows -> fc.matvec), C3 geometry, random dense stand-ins for A_ / force_operator_
+# ------------------------------------------------------------------------------------------------
+def fiber_ops_leg(skb, hbm_peak_gbs, reps=10):
+    import oracle as orc
+    g = make_c3_system()
+    nf, ns, nb = g["fib"].shape[0], g["shell"].shape[0], g["body"].shape[0]
+    n, n_fibers, eta = 32, 3000, 1.0
+    rng = np.random.default_rng(6)
+    _log("fiber ops: generating operators")
+    A = rng.standard_normal((n_fibers, 4 * n, 4 * n)) / np.sqrt(4 * n)       # 393 MB
+    F = rng.standard_normal((n_fibers, 3 * n, 4 * n)) / np.sqrt(4 * n)       # 295 MB
+    D = rng.standard_normal((n, n))
+    P = rng.standard_normal((4 * n - 14, 4 * n)) / np.sqrt(4 * n)
+    xs = rng.standard_normal((nf, 3))
+    xs /= np.linalg.norm(xs, axis=1)[:, None]
+    lprev, plus = np.ones(n_fibers), rng.integers(0, 2, n_fibers).astype(np.int32)
+    x = rng.standard_normal(4 * nf)
+    link = rng.standard_normal((n_fibers, 7))
+    ft = np.concatenate([g["force"], g["torque"]], axis=1)
+    with skb.Flow(0) as fl:
+        fl.set_fibers(g["fib"], g["n_nodes"], g["lengths"])
+        fl.set_periphery(g["shell"], g["shell_n"])
+        fl.set_bodies(g["body"], g["body_n"], g["centers"])
+        fl.set_fiber_class(n, D, P)
+        t0 = time.perf_counter()
+        # (the binding lays every matrix out column-major, as Eigen's .data())
+        fl.set_fiber_operators(list(A), list(F), xs, lprev, plus)
+        set_ms = 1e3 * (time.perf_counter() - t0)
+        _log("fiber ops: uploaded")
+        res, v_s, v_b = fl.apply_matvec(x, g["sd"], g["bd"], ft, eta, link)
+        dev, wall = [], []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            res, v_s, v_b = fl.apply_matvec(x, g["sd"], g["bd"], ft, eta, link)
+            wall.append(1e3 * (time.perf_counter() - t0))
+            dev.append(fl.stats()["device_ms"])
+        launches = fl.stats()["launches"]
+        k_force, k_mv = [], []
+        v_fib = np.ascontiguousarray(rng.standard_normal((nf, 3)))
+        for _ in range(reps):
+            fw = fl.apply_fiber_force(x)
+            k_force.append(fl.stats()["device_ms"])
+            fl.fiber_matvec(x, v_fib, link)
+            k_mv.append(fl.stats()["device_ms"])
+        # accuracy: sampled fibers against the oracle, the velocities taken from the (separately gated) flow matvec
+        v_all = fl.matvec(fw, g["sd"], g["bd"], ft, eta)
+    sel = rng.choice(n_fibers, 16, replace=False)
+    e_f = e_r = 0.0
+    for i in sel:
+        s4, s1 = slice(4 * n * i, 4 * n * (i + 1)), slice(n * i, n * (i + 1))
+        ref_fw = orc.apply_fiber_force([F[i]], x[s4], [n])
+        e_f = max(e_f, float(np.abs(fw[s1] - ref_fw).max() / np.abs(ref_fw).max()))
+        ref = orc.fiber_matvec(A[i], D, P, xs[s1], lprev[i], plus[i], x[s4], v_all[s1], link[i])
+        e_r = max(e_r, float(np.abs(res[s4] - ref).max() / np.abs(ref).max()))
+    # the host work this replaces, batched BLAS on this box's cores (the reference loops over fibers with Eigen GEMVs)
+    xb = x.reshape(n_fibers, 4 * n, 1)
+    t0 = time.perf_counter()
+    for _ in range(3):
+        np.matmul(F, xb)
+        np.matmul(A, xb)
+    cpu_ms = 1e3 * (time.perf_counter() - t0) / 3
+    mat_bytes = (A.nbytes + F.nbytes)
+    k = float(np.median(k_force) + np.median(k_mv))
+    gbs = mat_bytes / (k * 1e-3) / 1e9
+    return {"workload": "c3 (3000 fibers x 32 nodes): System::apply_matvec with apply_fiber_force (3n x 4n) and fc.matvec "
+                        "(4n x 4n A_, P_downsample_bc, D_1) as batched device GEMVs; fw and v_fibers never leave the GPU",
+            "apply_matvec_device_ms": float(np.median(dev)), "apply_matvec_e2e_ms": float(np.median(wall)),
+            "launches": int(launches), "set_operators_ms": set_ms,
+            "fiber_force_kernel_ms": float(np.median(k_force)), "fiber_matvec_kernels_ms": float(np.median(k_mv)),
+            "operator_bytes": int(mat_bytes), "host_blas_gemv_ms": cpu_ms,
+            "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s",
+                         "frac": gbs / hbm_peak_gbs},
+            "max_rel_err_fw": e_f, "max_rel_err_res_fibers": e_r}
+
+
+# ------------------------------------------------------------------------------------------------
 # GPU arm
 # ------------------------------------------------------------------------------------------------
 def main():
@@ -396,6 +473,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-matvec", action="store_true")
     ap.add_argument("--no-dense", action="store_true")
+    ap.add_argument("--no-fiber-ops", action="store_true")
     ap.add_argument("--no-symmetric", action="store_true", help="plain kernel only (A/B)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -680,6 +758,8 @@ def main():
         _log("matvec leg done")
         if world == 1 and not args.no_dense:
             out["periphery_dense"] = dense_leg(skb, out["roofline"]["hbm"]["peak"])
+        if world == 1 and not args.no_fiber_ops:
+            out["fiber_operators"] = fiber_ops_leg(skb, out["roofline"]["hbm"]["peak"])
         print(json.dumps(out))
     if world > 1:
         dist.barrier()

@@ -94,6 +94,39 @@ SKB_API int skb_flow_matvec_device(skb_flow *fl, const double *d_fib_forces, con
                                    const double *d_body_densities, const double *d_body_forces,
                                    const double *d_body_torques, double eta, double *d_v_window, void *stream);
 
+/* ---- per-fiber dense operators on the device ------------------------------------------
+ * The O(N_f n^2) host work of one GMRES iteration -- FiberContainerFiniteDifference::apply_fiber_force
+ * (fiber_container_finite_difference.cpp:272-287) and ::matvec (:216-232 -> FiberFiniteDifference::matvec,
+ * fiber_finite_difference.cpp:276-312) -- as batched GEMVs over operators that stay resident for the timestep.
+ * All matrices are COLUMN-MAJOR, exactly as Eigen stores the reference's members, so `.data()` goes in as is.
+ *
+ * skb_flow_set_fiber_class: the per-node-count constants FiberFiniteDifference::matrices_.at(n)
+ *   (fiber_finite_difference.cpp:537-555): D_1_0 (n x n) and P_downsample_bc ((4n-14) x 4n).  Call once per
+ *   distinct n (n >= 4), any time before skb_flow_set_fiber_operators.
+ * skb_flow_set_fiber_operators: once per timestep, after skb_flow_set_fibers (which defines the fibers and their
+ *   node counts): A = concatenated A_ (4n x 4n each), force_operator = concatenated force_operator_ (3n x 4n
+ *   each), xs = 3 x N_f tangents xs_, length_prev[f] = length_prev_, plus_bc_velocity[f] = (bc_plus_.first ==
+ *   Velocity). */
+SKB_API int skb_flow_set_fiber_class(skb_flow *fl, int n_nodes, const double *D_1_0, const double *P_downsample_bc);
+SKB_API int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *force_operator,
+                                         const double *xs, const double *length_prev, const int *plus_bc_velocity);
+/* fw (3 x N_f) = apply_fiber_force(x_fibers); x_fibers = per fiber [x; y; z; T] of 4n (fcfd.cpp:272-287) */
+SKB_API int skb_flow_apply_fiber_force(skb_flow *fl, const double *x_fibers, double *fw);
+/* res (4 N_f) = fc.matvec(x_fibers, v_fibers, v_fib_boundary); v_fibers 3 x N_f, v_fib_boundary 7 x n_fibers
+ * (fiber_link_conditions of BodyContainer::calculate_link_conditions) or NULL for none (fcfd.cpp:216-232) */
+SKB_API int skb_flow_fiber_matvec(skb_flow *fl, const double *x_fibers, const double *v_fibers,
+                                  const double *v_fib_boundary, double *res);
+/* System::apply_matvec (system.cpp:269-324) with the fiber operators on the device:
+ *   fw = apply_fiber_force(x_fibers); v_all = the fused flow of skb_flow_matvec;
+ *   res_fibers = fc.matvec(x_fibers, v_fibers, fiber_link_conditions)
+ * and the periphery / body rows of v_all returned for shell.matvec / bc.matvec (periphery.cpp:38-47 ->
+ * skb_dense_apply; body_container.cpp matvec stays host glue).  Needs the full target window.  One H2D of the
+ * solution-sized inputs, one D2H of the solution-sized outputs; fw and v_fibers never leave the device. */
+SKB_API int skb_flow_apply_matvec(skb_flow *fl, const double *x_fibers, const double *shell_density,
+                                  const double *body_densities, const double *body_forces_torques,
+                                  const double *fiber_link_conditions, double eta, double *res_fibers,
+                                  double *v_shell, double *v_bodies);
+
 typedef struct skb_flow_stats {
     double device_ms;   /* CUDA-event time of the last call, first launch to last kernel (copies excluded) */
     double total_ms;    /* including H2D / D2H */

@@ -261,6 +261,102 @@ def matvec_flow(fib, shell, body, eta):
 
 
 # ----------------------------------------------------------------------------------------------
+# per-fiber dense operators of the matvec.  PARITY UNPINNED: the reference's fiber code needs
+# Eigen/toml/spdlog/MPI and cannot be built here, and its Python package has no counterpart, so these numpy
+# restatements are checked only against each other (loop form vs. assembled dense operator), not against
+# reference output.
+# ----------------------------------------------------------------------------------------------
+
+def apply_fiber_force(force_ops, x_fibers, n_nodes):
+    """FiberContainerFiniteDifference::apply_fiber_force (fiber_container_finite_difference.cpp:272-287).
+
+    force_ops: list of (3n, 4n) arrays (FiberFiniteDifference::force_operator_); x_fibers: concatenated per-fiber
+    [x; y; z; T] of 4n.  Returns fw as (N_f, 3) (the reference's 3 x N_f, column-major)."""
+    x_fibers = np.asarray(x_fibers, dtype=np.float64).reshape(-1)
+    fw = np.zeros((int(np.sum(n_nodes)), 3))
+    off = 0
+    for F, n in zip(force_ops, n_nodes):
+        ff = np.asarray(F) @ x_fibers[4 * off:4 * off + 4 * n]     # :278
+        for k in range(3):
+            fw[off:off + n, k] = ff[k * n:(k + 1) * n]             # :279-281
+        off += n
+    return fw
+
+
+def fiber_matvec(A, D_1_0, P_downsample_bc, xs, length_prev, plus_bc_velocity, x, v, v_boundary=None):
+    """FiberFiniteDifference::matvec (fiber_finite_difference.cpp:276-312) for one fiber.
+
+    A (4n,4n); D_1_0 (n,n); P_downsample_bc (4n-14,4n); xs (n,3) tangents; x (4n); v (n,3); v_boundary (7,) or
+    None."""
+    n = xs.shape[0]
+    bc = 4 * n - 14                                                 # :279
+    D_1 = np.asarray(D_1_0) * (2.0 / length_prev)                   # :280
+    xsDs = (D_1 * xs[:, 0][:, None]).T                              # :281  (D_1.colwise() * xs_x)^T
+    ysDs = (D_1 * xs[:, 1][:, None]).T
+    zsDs = (D_1 * xs[:, 2][:, None]).T
+    vT = np.empty(4 * n)
+    vT[0:n], vT[n:2 * n], vT[2 * n:3 * n] = v[:, 0], v[:, 1], v[:, 2]   # :290-292
+    vT[3 * n:] = xsDs @ v[:, 0] + ysDs @ v[:, 1] + zsDs @ v[:, 2]   # :293
+    vT_in = np.zeros(4 * n)
+    vT_in[:bc] = np.asarray(P_downsample_bc) @ vT                   # :296
+    xs_vT = np.zeros(4 * n)
+    xs_vT[bc + 3] = v[0] @ xs[0]                                    # :301
+    y_BC = np.zeros(4 * n)
+    if v_boundary is not None and np.size(v_boundary) > 0:
+        y_BC[bc:bc + 7] = v_boundary                                # :305-306
+    if plus_bc_velocity:
+        xs_vT[bc + 10] = v[n - 1] @ xs[n - 1]                       # :308-309
+    return np.asarray(A) @ np.asarray(x) - vT_in + xs_vT + y_BC     # :311
+
+
+def fiber_container_matvec(ops, x_fibers, v_fibers, v_fib_boundary=None):
+    """FiberContainerFiniteDifference::matvec (fiber_container_finite_difference.cpp:216-232).
+
+    ops = dict(A=[...], D_1_0={n: ..}, P={n: ..}, xs (N_f,3), length_prev, plus, n_nodes);
+    v_fib_boundary (n_fibers, 7) (the reference's 7 x n_fibers, column-major) or None."""
+    x_fibers = np.asarray(x_fibers, dtype=np.float64).reshape(-1)
+    res = np.zeros_like(x_fibers)
+    off = 0
+    for i, n in enumerate(ops["n_nodes"]):
+        vb = None if v_fib_boundary is None else np.asarray(v_fib_boundary)[i]
+        res[4 * off:4 * off + 4 * n] = fiber_matvec(
+            ops["A"][i], ops["D_1_0"][n], ops["P"][n], ops["xs"][off:off + n], ops["length_prev"][i],
+            ops["plus"][i], x_fibers[4 * off:4 * off + 4 * n], np.asarray(v_fibers)[off:off + n], vb)
+        off += n
+    return res
+
+
+def fiber_velocity_operator(D_1_0, P_downsample_bc, xs, length_prev, plus_bc_velocity):
+    """The (4n x 3n) matrix V with fiber_matvec(...) == A x + V vec(v) + y_BC, vec(v) = AoS [v_0x v_0y v_0z v_1x ...].
+    An independent assembly of ffd.cpp:280-309 used to cross-check fiber_matvec."""
+    n = xs.shape[0]
+    bc = 4 * n - 14
+    D_1 = np.asarray(D_1_0) * (2.0 / length_prev)
+    T = np.zeros((4 * n, 3 * n))                    # vT = T vec(v)
+    for i in range(n):
+        for k in range(3):
+            T[k * n + i, 3 * i + k] = 1.0
+            T[3 * n:, 3 * i + k] = D_1[i, :] * xs[i, k]
+    V = np.zeros((4 * n, 3 * n))
+    V[:bc] = -np.asarray(P_downsample_bc) @ T
+    V[bc + 3, 0:3] += xs[0]
+    if plus_bc_velocity:
+        V[bc + 10, 3 * (n - 1):3 * n] += xs[n - 1]
+    return V
+
+
+def apply_matvec_fibers(fib, shell, body, ops, x_fibers, eta, fiber_link_conditions=None):
+    """System::apply_matvec (system.cpp:298-318) up to res_fibers: fw = apply_fiber_force(x_fibers), v_all =
+    matvec_flow, res_fibers = fc.matvec(x_fibers, v_fibers, fiber_link_conditions).  Returns (res_fibers, v_all)."""
+    fw = apply_fiber_force(ops["force"], x_fibers, ops["n_nodes"])
+    fib = dict(fib, forces=fw)
+    v_all = matvec_flow(fib, shell, body, eta)
+    nf = int(np.sum(ops["n_nodes"]))
+    res = fiber_container_matvec(ops, x_fibers, v_all[:nf], fiber_link_conditions)
+    return res, v_all
+
+
+# ----------------------------------------------------------------------------------------------
 # the reference's own CUDA direct kernels (GPU box only): oracle/_ref/libskelly_ref_kernels_cu.so
 # ----------------------------------------------------------------------------------------------
 _refgpu = None

@@ -110,6 +110,11 @@ def library() -> C.CDLL:
         "skb_flow_set_background": ([ctxp, C.POINTER(C.c_int), _dp, _dp], C.c_int),
         "skb_flow_velocity_at_targets": ([ctxp, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_set_target_window": ([ctxp, C.c_int64, C.c_int64], C.c_int),
+        "skb_flow_set_fiber_class": ([ctxp, C.c_int, _dp, _dp], C.c_int),
+        "skb_flow_set_fiber_operators": ([ctxp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
+        "skb_flow_apply_fiber_force": ([ctxp, _dp, _dp], C.c_int),
+        "skb_flow_fiber_matvec": ([ctxp, _dp, _dp, _dp, _dp], C.c_int),
+        "skb_flow_apply_matvec": ([ctxp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp], C.c_int),
         # include/skelly_b200_dense.h
         "skb_dense_create": ([C.c_int, C.POINTER(ctxp)], C.c_int),
         "skb_dense_destroy": ([ctxp], C.c_int),
@@ -411,6 +416,62 @@ class Flow:
         v = np.empty((max(w1 - w0, 0), 3))
         _check(library().skb_flow_matvec(self._h, _p(a), _p(b), _p(c), _p(ft), float(eta), _p(v)))
         return v
+
+    # ---- per-fiber dense operators; matrices go in column-major like Eigen's .data() ----
+    def set_fiber_class(self, n_nodes: int, D_1_0, P_downsample_bc):
+        """FiberFiniteDifference::matrices_.at(n): D_1_0 (n,n), P_downsample_bc (4n-14,4n)."""
+        n = int(n_nodes)
+        D = np.asfortranarray(D_1_0, dtype=np.float64)
+        P = np.asfortranarray(P_downsample_bc, dtype=np.float64)
+        if D.shape != (n, n) or P.shape != (4 * n - 14, 4 * n):
+            raise ValueError(f"class matrices for n={n}: got {D.shape}, {P.shape}")
+        _check(library().skb_flow_set_fiber_class(self._h, n, _p(D), _p(P)))
+
+    def set_fiber_operators(self, A_list, force_list, xs, length_prev, plus_bc_velocity):
+        """A_ (4n,4n) and force_operator_ (3n,4n) per fiber, tangents xs (N_f,3), length_prev_, plus-end velocity BC."""
+        A = np.concatenate([np.asfortranarray(a, dtype=np.float64).ravel(order="F") for a in A_list]) \
+            if len(A_list) else np.zeros(0)
+        F = np.concatenate([np.asfortranarray(f, dtype=np.float64).ravel(order="F") for f in force_list]) \
+            if len(force_list) else np.zeros(0)
+        xs = _arr(xs, 3)
+        lp = np.ascontiguousarray(length_prev, dtype=np.float64)
+        pl = np.ascontiguousarray(plus_bc_velocity, dtype=np.int32)
+        assert xs.shape[0] == self.n_fib and lp.shape == pl.shape == (len(A_list),)
+        _check(library().skb_flow_set_fiber_operators(self._h, _p(A), _p(F), _p(xs), _p(lp),
+                                                      pl.ctypes.data_as(C.POINTER(C.c_int))))
+
+    def apply_fiber_force(self, x_fibers):
+        """fc.apply_fiber_force (fcfd.cpp:272-287): (4 N_f,) -> fw (N_f, 3)."""
+        x = np.ascontiguousarray(x_fibers, dtype=np.float64).reshape(-1)
+        assert x.shape[0] == 4 * self.n_fib
+        fw = np.empty((self.n_fib, 3))
+        _check(library().skb_flow_apply_fiber_force(self._h, _p(x), _p(fw)))
+        return fw
+
+    def fiber_matvec(self, x_fibers, v_fibers, v_fib_boundary=None):
+        """fc.matvec (fcfd.cpp:216-232): x (4 N_f,), v (N_f,3), v_fib_boundary (n_fibers,7) or None -> res (4 N_f,)."""
+        x = np.ascontiguousarray(x_fibers, dtype=np.float64).reshape(-1)
+        v = _arr(v_fibers, 3)
+        assert x.shape[0] == 4 * self.n_fib and v.shape[0] == self.n_fib
+        vb = None if v_fib_boundary is None else _arr(v_fib_boundary, 7)
+        res = np.empty(4 * self.n_fib)
+        _check(library().skb_flow_fiber_matvec(self._h, _p(x), _p(v), None if vb is None else _p(vb), _p(res)))
+        return res
+
+    def apply_matvec(self, x_fibers, shell_density, body_densities, body_forces_torques, eta,
+                     fiber_link_conditions=None):
+        """System::apply_matvec (system.cpp:298-318) with the fiber operators on the device.
+        Returns (res_fibers (4 N_f,), v_shell (N_s,3), v_bodies (N_b,3))."""
+        x = np.ascontiguousarray(x_fibers, dtype=np.float64).reshape(-1)
+        assert x.shape[0] == 4 * self.n_fib
+        b, c = _arr(shell_density, 3), _arr(body_densities, 3)
+        ft = _arr(body_forces_torques, 6)
+        vb = None if fiber_link_conditions is None else _arr(fiber_link_conditions, 7)
+        res = np.empty(4 * self.n_fib)
+        v_s, v_b = np.empty((self.n_shell, 3)), np.empty((self.n_body, 3))
+        _check(library().skb_flow_apply_matvec(self._h, _p(x), _p(b), _p(c), _p(ft), None if vb is None else _p(vb),
+                                               float(eta), _p(res), _p(v_s), _p(v_b)))
+        return res, v_s, v_b
 
     def stats(self) -> dict:
         s = FlowStats()

@@ -3,6 +3,7 @@
 // (src/core/system.cpp:284-316).  Built on the pair-kernel contexts of skb_runtime.cu; everything between the
 // upload of the strengths and the download of the velocities stays on the device.
 #include "aux_kernels.cuh"
+#include "fiber_ops.cuh"
 #include "skb_internal.hpp"
 #include "../../include/skelly_b200_flow.h"
 
@@ -10,6 +11,7 @@
 #include <cstdint>
 #include <cstdlib>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <vector>
 
@@ -85,6 +87,18 @@ struct skb_flow {
     size_t h_stage_cap = 0;
     int bg_comp[3] = {0, 1, 2};
     double bg_scale[3] = {0, 0, 0}, bg_uniform[3] = {0, 0, 0};
+    // per-fiber dense operators: A_, force_operator_, xs_ resident for the timestep
+    std::vector<int> h_fiber_n;
+    std::vector<long long> h_fiber_off;
+    struct FiberClass {
+        std::vector<double> D, P; // D_1_0 (n x n), P_downsample_bc ((4n-14) x 4n), column-major
+    };
+    std::map<int, FiberClass> fiber_classes;
+    bool ops_ready = false;
+    int n_items_A = 0, n_items_F = 0;
+    size_t gemv_smem = 0, fvel_smem = 0;
+    DevBuf op_A, op_F, op_xs, op_len, op_plus, op_class, op_classD, op_classP, items_A, items_F;
+    DevBuf x_fib, res_fib, vb;
     // staging
     DevBuf in_fib, in_shell, in_body, in_force, in_torque, vel, tmp;
     skb_flow_stats stats{};
@@ -357,7 +371,9 @@ int skb_flow_destroy(skb_flow *fl) {
         skb_ctx_destroy(fl->body[k]);
     }
     DevBuf *bufs[] = {&fl->fiber_offset, &fl->fiber_length, &fl->r_fib, &fl->r_shell, &fl->r_body, &fl->centers,
-                      &fl->pt_pos, &fl->pt_force, &fl->pt_torque, &fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel, &fl->tmp};
+                      &fl->pt_pos, &fl->pt_force, &fl->pt_torque, &fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel, &fl->tmp,
+                      &fl->op_A, &fl->op_F, &fl->op_xs, &fl->op_len, &fl->op_plus, &fl->op_class, &fl->op_classD,
+                      &fl->op_classP, &fl->items_A, &fl->items_F, &fl->x_fib, &fl->res_fib, &fl->vb};
     for (DevBuf *b : bufs)
         b->release();
     fl->g_matvec.reset();
@@ -390,6 +406,9 @@ int skb_flow_set_fibers(skb_flow *fl, const double *r_fib, const int *n_nodes, c
     fl->n_fib = off[n_fibers];
     fl->max_fiber_nodes = max_n;
     fl->h_r_fib.assign(r_fib, r_fib + 3 * fl->n_fib);
+    fl->h_fiber_n.assign(n_nodes, n_nodes + n_fibers);
+    fl->h_fiber_off = off;
+    fl->ops_ready = false; // operators belong to one set of fibers
     fl->mv_dirty = true;
     fl->geom_version++;
     CUDA_TRY(cudaSetDevice(fl->dev));
@@ -840,6 +859,256 @@ int skb_flow_matvec_device(skb_flow *fl, const double *d_fib_forces, const doubl
     fl->stats.n_pairs = fl->pairs;
     fl->stats.launches = fl->launches;
     return SKB_OK;
+}
+
+// ---- per-fiber dense operators ---------------------------------------------------------------
+
+int skb_flow_set_fiber_class(skb_flow *fl, int n_nodes, const double *D_1_0, const double *P_downsample_bc) {
+    if (!fl || !D_1_0 || !P_downsample_bc)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_class: NULL argument");
+    if (n_nodes < 4) // bc_start_i = 4n - 14 must leave room for the 14 boundary rows (ffd.cpp:279)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_class: n_nodes = %d (need >= 4)", n_nodes);
+    const size_t n = (size_t)n_nodes;
+    skb_flow::FiberClass &c = fl->fiber_classes[n_nodes];
+    c.D.assign(D_1_0, D_1_0 + n * n);
+    c.P.assign(P_downsample_bc, P_downsample_bc + (4 * n - 14) * 4 * n);
+    fl->ops_ready = false;
+    return SKB_OK;
+}
+
+int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *force_operator, const double *xs,
+                                 const double *length_prev, const int *plus_bc_velocity) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_operators: NULL flow");
+    const int nfib = fl->n_fibers;
+    fl->ops_ready = false;
+    if (nfib == 0) {
+        fl->n_items_A = fl->n_items_F = 0;
+        fl->ops_ready = true;
+        return SKB_OK;
+    }
+    if (!A || !force_operator || !xs || !length_prev || !plus_bc_velocity)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_operators: NULL argument");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    // class matrices -> one device buffer, per-fiber offsets into it
+    std::vector<double> h_class;
+    std::map<int, std::pair<long long, long long>> class_off;
+    for (const auto &kv : fl->fiber_classes) {
+        class_off[kv.first] = {(long long)h_class.size(), (long long)(h_class.size() + kv.second.D.size())};
+        h_class.insert(h_class.end(), kv.second.D.begin(), kv.second.D.end());
+        h_class.insert(h_class.end(), kv.second.P.begin(), kv.second.P.end());
+    }
+    std::vector<long long> cD((size_t)nfib), cP((size_t)nfib);
+    std::vector<FiberGemvItem> itA, itF;
+    long long offA = 0, offF = 0;
+    int max_n = 0;
+    for (int f = 0; f < nfib; ++f) {
+        const int n = fl->h_fiber_n[f];
+        auto it = class_off.find(n);
+        if (it == class_off.end())
+            return set_error(SKB_ERR_INVALID, "fiber %d has %d nodes but skb_flow_set_fiber_class(%d, ...) was never "
+                                              "called", f, n, n);
+        if (!(length_prev[f] > 0))
+            return set_error(SKB_ERR_INVALID, "fiber %d: length_prev = %g", f, length_prev[f]);
+        cD[f] = it->second.first;
+        cP[f] = it->second.second;
+        max_n = std::max(max_n, n);
+        const long long node_off = fl->h_fiber_off[f];
+        for (int r0 = 0; r0 < 4 * n; r0 += kFiberGemvRows)
+            itA.push_back(FiberGemvItem{offA, 4 * node_off, 4 * node_off, 4 * n, 4 * n, r0, n});
+        for (int r0 = 0; r0 < 3 * n; r0 += kFiberGemvRows)
+            itF.push_back(FiberGemvItem{offF, 4 * node_off, node_off, 3 * n, 4 * n, r0, n});
+        offA += 16LL * n * n;
+        offF += 12LL * n * n;
+    }
+    fl->gemv_smem = ((size_t)((4 * max_n + 1) & ~1) + kFiberGemvThreads) * sizeof(double);
+    fl->fvel_smem = (size_t)5 * max_n * sizeof(double);
+    if (fl->gemv_smem > 200 * 1024)
+        return set_error(SKB_ERR_INVALID, "fiber with %d nodes exceeds the shared-memory fiber operator kernels", max_n);
+    if (fl->gemv_smem > 48 * 1024) {
+        CUDA_TRY(cudaFuncSetAttribute(fiber_gemv_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)fl->gemv_smem));
+        CUDA_TRY(cudaFuncSetAttribute(fiber_gemv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)fl->gemv_smem));
+    }
+    if (fl->fvel_smem > 48 * 1024)
+        CUDA_TRY(cudaFuncSetAttribute(fiber_velocity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)fl->fvel_smem));
+    const long long nf = fl->n_fib;
+    auto put = [&](DevBuf &b, const void *h, size_t bytes) -> int {
+        SKB_TRY(b.ensure(bytes));
+        CUDA_TRY(cudaMemcpyAsync(b.ptr, h, bytes, cudaMemcpyHostToDevice, fl->stream));
+        return SKB_OK;
+    };
+    SKB_TRY(put(fl->op_A, A, (size_t)offA * 8));
+    SKB_TRY(put(fl->op_F, force_operator, (size_t)offF * 8));
+    SKB_TRY(put(fl->op_xs, xs, (size_t)nf * 24));
+    SKB_TRY(put(fl->op_len, length_prev, (size_t)nfib * 8));
+    SKB_TRY(put(fl->op_plus, plus_bc_velocity, (size_t)nfib * sizeof(int)));
+    SKB_TRY(put(fl->op_class, h_class.data(), h_class.size() * 8));
+    SKB_TRY(put(fl->op_classD, cD.data(), cD.size() * 8));
+    SKB_TRY(put(fl->op_classP, cP.data(), cP.size() * 8));
+    SKB_TRY(put(fl->items_A, itA.data(), itA.size() * sizeof(FiberGemvItem)));
+    SKB_TRY(put(fl->items_F, itF.data(), itF.size() * sizeof(FiberGemvItem)));
+    SKB_TRY(fl->x_fib.ensure((size_t)nf * 32));
+    SKB_TRY(fl->res_fib.ensure((size_t)nf * 32));
+    SKB_TRY(fl->vb.ensure((size_t)nfib * 56));
+    CUDA_TRY(cudaStreamSynchronize(fl->stream)); // the host vectors above go out of scope
+    fl->n_items_A = (int)itA.size();
+    fl->n_items_F = (int)itF.size();
+    fl->ops_ready = true;
+    return SKB_OK;
+}
+
+} // extern "C"
+
+static int need_ops(const skb_flow *fl, const char *who) {
+    if (!fl->ops_ready)
+        return set_error(SKB_ERR_INVALID, "%s: call skb_flow_set_fiber_operators after skb_flow_set_fibers / "
+                                          "skb_flow_set_fiber_class first", who);
+    return SKB_OK;
+}
+
+// fw = force_operator_ * x per fiber, scattered to 3 x N_f (fcfd.cpp:272-287); on fl->cur
+static int fiber_force_dev(skb_flow *fl, const double *d_x, double *d_fw) {
+    if (fl->n_items_F == 0)
+        return SKB_OK;
+    fiber_gemv_kernel<1><<<fl->n_items_F, kFiberGemvThreads, fl->gemv_smem, fl->cur>>>(
+        (const FiberGemvItem *)fl->items_F.ptr, (const double *)fl->op_F.ptr, d_x, d_fw);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    fl->launches += 1;
+    return SKB_OK;
+}
+
+// res = A_ x - P_downsample_bc vT(v) + xs_vT + y_BC per fiber (ffd.cpp:276-312); on fl->cur
+static int fiber_matvec_dev(skb_flow *fl, const double *d_x, const double *d_v, const double *d_vb, double *d_res) {
+    if (fl->n_items_A == 0)
+        return SKB_OK;
+    fiber_gemv_kernel<0><<<fl->n_items_A, kFiberGemvThreads, fl->gemv_smem, fl->cur>>>(
+        (const FiberGemvItem *)fl->items_A.ptr, (const double *)fl->op_A.ptr, d_x, d_res);
+    CUDA_TRY(cudaGetLastError());
+    fiber_velocity_kernel<<<fl->n_fibers, 256, fl->fvel_smem, fl->cur>>>(
+        (const long long *)fl->fiber_offset.ptr, (const double *)fl->op_xs.ptr, d_v, (const double *)fl->op_len.ptr,
+        (const int *)fl->op_plus.ptr, (const double *)fl->op_class.ptr, (const long long *)fl->op_classD.ptr,
+        (const long long *)fl->op_classP.ptr, d_vb, d_res);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(2);
+    fl->launches += 2;
+    return SKB_OK;
+}
+
+extern "C" {
+
+int skb_flow_apply_fiber_force(skb_flow *fl, const double *x_fibers, double *fw) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_fiber_force: NULL flow");
+    SKB_TRY(need_ops(fl, "skb_flow_apply_fiber_force"));
+    const long long nf = fl->n_fib;
+    begin_stats(fl);
+    if (nf == 0)
+        return SKB_OK;
+    if (!x_fibers || !fw)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_fiber_force: NULL argument");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    fl->cur = fl->stream;
+    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(fl->x_fib.ptr, x_fibers, (size_t)nf * 32, cudaMemcpyHostToDevice, fl->stream));
+    SKB_TRY(fl->in_fib.ensure((size_t)nf * 24));
+    CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    SKB_TRY(fiber_force_dev(fl, (const double *)fl->x_fib.ptr, (double *)fl->in_fib.ptr));
+    CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(fw, fl->in_fib.ptr, (size_t)nf * 24, cudaMemcpyDeviceToHost, fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+    return finish_stats(fl);
+}
+
+int skb_flow_fiber_matvec(skb_flow *fl, const double *x_fibers, const double *v_fibers, const double *v_fib_boundary,
+                          double *res) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_fiber_matvec: NULL flow");
+    SKB_TRY(need_ops(fl, "skb_flow_fiber_matvec"));
+    const long long nf = fl->n_fib;
+    begin_stats(fl);
+    if (nf == 0)
+        return SKB_OK;
+    if (!x_fibers || !v_fibers || !res)
+        return set_error(SKB_ERR_INVALID, "skb_flow_fiber_matvec: NULL argument");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    fl->cur = fl->stream;
+    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(fl->x_fib.ptr, x_fibers, (size_t)nf * 32, cudaMemcpyHostToDevice, fl->stream));
+    SKB_TRY(fl->vel.ensure((size_t)nf * 24));
+    CUDA_TRY(cudaMemcpyAsync(fl->vel.ptr, v_fibers, (size_t)nf * 24, cudaMemcpyHostToDevice, fl->stream));
+    if (v_fib_boundary)
+        CUDA_TRY(cudaMemcpyAsync(fl->vb.ptr, v_fib_boundary, (size_t)fl->n_fibers * 56, cudaMemcpyHostToDevice,
+                                 fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    SKB_TRY(fiber_matvec_dev(fl, (const double *)fl->x_fib.ptr, (const double *)fl->vel.ptr,
+                             v_fib_boundary ? (const double *)fl->vb.ptr : nullptr, (double *)fl->res_fib.ptr));
+    CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(res, fl->res_fib.ptr, (size_t)nf * 32, cudaMemcpyDeviceToHost, fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+    return finish_stats(fl);
+}
+
+int skb_flow_apply_matvec(skb_flow *fl, const double *x_fibers, const double *shell_density,
+                          const double *body_densities, const double *body_forces_torques,
+                          const double *fiber_link_conditions, double eta, double *res_fibers, double *v_shell,
+                          double *v_bodies) {
+    if (!fl || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec: bad arguments");
+    SKB_TRY(need_ops(fl, "skb_flow_apply_matvec"));
+    const long long nf = fl->n_fib, ns = fl->n_shell, nb = fl->n_body, n_all = nf + ns + nb;
+    if ((nf > 0 && (!x_fibers || !res_fibers)) || (ns > 0 && (!shell_density || !v_shell)) ||
+        (nb > 0 && (!body_densities || !v_bodies)) || (fl->n_bodies > 0 && !body_forces_torques))
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec: NULL argument for a non-empty class");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    begin_stats(fl);
+    if (n_all == 0)
+        return SKB_OK;
+    SKB_TRY(prepare_matvec_targets(fl));
+    if (fl->w0 != 0 || fl->w1 != n_all)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec needs the full target window (have [%lld, %lld) of "
+                                          "%lld)", fl->w0, fl->w1, n_all);
+    std::vector<double> f, t;
+    if (fl->n_bodies > 0)
+        split_forces_torques(body_forces_torques, fl->n_bodies, f, t);
+    fl->cur = fl->stream;
+    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
+    if (nf)
+        CUDA_TRY(cudaMemcpyAsync(fl->x_fib.ptr, x_fibers, (size_t)nf * 32, cudaMemcpyHostToDevice, fl->stream));
+    if (nf && fiber_link_conditions)
+        CUDA_TRY(cudaMemcpyAsync(fl->vb.ptr, fiber_link_conditions, (size_t)fl->n_fibers * 56,
+                                 cudaMemcpyHostToDevice, fl->stream));
+    SKB_TRY(upload(fl, fl->in_shell, shell_density, (size_t)ns * 3));
+    SKB_TRY(upload(fl, fl->in_body, body_densities, (size_t)nb * 3));
+    SKB_TRY(upload(fl, fl->in_force, f.data(), f.size()));
+    SKB_TRY(upload(fl, fl->in_torque, t.data(), t.size()));
+    SKB_TRY(fl->in_fib.ensure((size_t)nf * 24 + 8));
+    SKB_TRY(fl->vel.ensure((size_t)n_all * 24));
+    CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    // MatrixXd fw = fc.apply_fiber_force(x_fibers)                       system.cpp:298
+    SKB_TRY(fiber_force_dev(fl, (const double *)fl->x_fib.ptr, (double *)fl->in_fib.ptr));
+    // v_all of system.cpp:299-316
+    SKB_TRY(matvec_core(fl, (const double *)fl->in_fib.ptr, (const double *)fl->in_shell.ptr,
+                        (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
+                        (const double *)fl->in_torque.ptr, eta, (double *)fl->vel.ptr));
+    // res_fibers = fc.matvec(x_fibers, v_fibers, fiber_link_conditions)   system.cpp:318
+    SKB_TRY(fiber_matvec_dev(fl, (const double *)fl->x_fib.ptr, (const double *)fl->vel.ptr,
+                             fiber_link_conditions ? (const double *)fl->vb.ptr : nullptr,
+                             (double *)fl->res_fib.ptr));
+    CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+    if (nf)
+        CUDA_TRY(cudaMemcpyAsync(res_fibers, fl->res_fib.ptr, (size_t)nf * 32, cudaMemcpyDeviceToHost, fl->stream));
+    if (ns)
+        CUDA_TRY(cudaMemcpyAsync(v_shell, (const double *)fl->vel.ptr + 3 * nf, (size_t)ns * 24,
+                                 cudaMemcpyDeviceToHost, fl->stream));
+    if (nb)
+        CUDA_TRY(cudaMemcpyAsync(v_bodies, (const double *)fl->vel.ptr + 3 * (nf + ns), (size_t)nb * 24,
+                                 cudaMemcpyDeviceToHost, fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+    return finish_stats(fl);
 }
 
 int skb_flow_last_stats(const skb_flow *fl, skb_flow_stats *out) {

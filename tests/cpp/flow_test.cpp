@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdio>
 #include <random>
+#include <vector>
 
 using skelly_b200::Matrix;
 
@@ -90,7 +91,80 @@ int main() {
             umax = std::fmax(umax, std::fabs(ref[i]));
         }
         printf("flow_test: max rel err %.3e (gate 1e-11)\n", dmax / umax);
-        return dmax / umax > 1e-11;
+        if (dmax / umax > 1e-11)
+            return 1;
+
+        // ---- per-fiber dense operators through the wrapper (fcfd.cpp:272-287, ffd.cpp:276-312) ----
+        const int n4 = 4 * n, n3 = 3 * n, bc = n4 - 14;
+        Matrix D(n, n), P(bc, n4), xs(3, nf), x(4 * nf, 1), link(7, n_fibers);
+        for (long i = 0; i < D.size(); ++i) D.data()[i] = U(gen);
+        for (long i = 0; i < P.size(); ++i) P.data()[i] = U(gen) / n4;
+        for (long i = 0; i < xs.size(); ++i) xs.data()[i] = U(gen);
+        for (long i = 0; i < x.size(); ++i) x.data()[i] = U(gen);
+        for (long i = 0; i < link.size(); ++i) link.data()[i] = U(gen);
+        std::vector<Matrix> A(n_fibers, Matrix(n4, n4)), F(n_fibers, Matrix(n3, n4));
+        std::vector<const double *> Ap, Fp;
+        std::vector<double> lprev(n_fibers);
+        std::vector<int> plus(n_fibers);
+        for (int f = 0; f < n_fibers; ++f) {
+            for (long i = 0; i < A[f].size(); ++i) A[f].data()[i] = U(gen) / n4;
+            for (long i = 0; i < F[f].size(); ++i) F[f].data()[i] = U(gen) / n4;
+            Ap.push_back(A[f].data());
+            Fp.push_back(F[f].data());
+            lprev[f] = 1.0 + 0.05 * f;
+            plus[f] = f % 2;
+        }
+        eng.set_fiber_class(n, D, P);
+        eng.set_fiber_operators(Ap, Fp, xs, lprev, plus);
+        Matrix fw = eng.apply_fiber_force(x), v_s, v_b;
+        Matrix res = eng_copy.apply_matvec(x, rho, empty, empty, link, eta, v_s, v_b);
+        Matrix v_all = eng.matvec_flow(fw, rho, empty, empty, eta);
+        double e_fw = 0, m_fw = 0, e_res = 0, m_res = 0;
+        for (int f = 0; f < n_fibers; ++f) {
+            const double *xf = x.data() + (size_t)4 * f * n;
+            for (int r = 0; r < n3; ++r) { // fw(k, off + i) = (force_operator_ * x)(k n + i)
+                double s = 0;
+                for (int j = 0; j < n4; ++j)
+                    s += F[f](r, j) * xf[j];
+                const double got = fw(r / n, f * n + r % n);
+                e_fw = std::fmax(e_fw, std::fabs(s - got));
+                m_fw = std::fmax(m_fw, std::fabs(s));
+            }
+            std::vector<double> vT(n4, 0.0);
+            for (int i = 0; i < n; ++i)
+                for (int k = 0; k < 3; ++k)
+                    vT[k * n + i] = v_all(k, f * n + i);
+            for (int j = 0; j < n; ++j) // (xsDs vx + ysDs vy + zsDs vz)(j) = sum_i D_1(i,j) xs_i . v_i
+                for (int i = 0; i < n; ++i) {
+                    double dot = 0;
+                    for (int k = 0; k < 3; ++k)
+                        dot += xs(k, f * n + i) * v_all(k, f * n + i);
+                    vT[n3 + j] += D(i, j) * (2.0 / lprev[f]) * dot;
+                }
+            for (int r = 0; r < n4; ++r) {
+                double s = 0;
+                for (int j = 0; j < n4; ++j)
+                    s += A[f](r, j) * xf[j];
+                if (r < bc)
+                    for (int j = 0; j < n4; ++j)
+                        s -= P(r, j) * vT[j];
+                if (r >= bc && r < bc + 7)
+                    s += link(r - bc, f);
+                if (r == bc + 3 || (r == bc + 10 && plus[f])) {
+                    const int node = f * n + (r == bc + 3 ? 0 : n - 1);
+                    for (int k = 0; k < 3; ++k)
+                        s += v_all(k, node) * xs(k, node);
+                }
+                e_res = std::fmax(e_res, std::fabs(s - res.data()[(size_t)4 * f * n + r]));
+                m_res = std::fmax(m_res, std::fabs(s));
+            }
+        }
+        double e_vs = 0;
+        for (long i = 0; i < v_s.size(); ++i)
+            e_vs = std::fmax(e_vs, std::fabs(v_s.data()[i] - v_all.data()[3 * nf + i]));
+        printf("flow_test: fiber operators  fw %.3e  res %.3e  v_shell %.3e (gate 1e-12, exact)\n", e_fw / m_fw,
+               e_res / m_res, e_vs);
+        return (e_fw / m_fw > 1e-12 || e_res / m_res > 1e-12 || e_vs != 0.0) ? 2 : 0;
     } catch (const std::exception &e) {
         fprintf(stderr, "%s\n", e.what());
         return 3;

@@ -1,0 +1,161 @@
+"""GPU parity tests of the per-fiber dense operators (include/skelly_b200_flow.h
+skb_flow_apply_fiber_force / skb_flow_fiber_matvec / skb_flow_apply_matvec) against the oracle's restatement of
+FiberContainerFiniteDifference::apply_fiber_force (fcfd.cpp:272-287), FiberFiniteDifference::matvec
+(fiber_finite_difference.cpp:276-312) and System::apply_matvec (system.cpp:298-318).
+Tolerance 1e-12 relative (max-norm and l2): FP64 dot products of <= 4*64 terms in a different summation order."""
+import numpy as np
+import pytest
+
+import oracle as orc
+import skellysim_b200 as skb
+from conftest import rel_l2, rel_max
+from test_gpu_flow import ft_of, load, make_system
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-12
+
+
+def _check(u, ref, tol=TOL):
+    assert np.isfinite(u).all()
+    assert rel_max(u, ref) < tol, rel_max(u, ref)
+    assert rel_l2(u, ref) < tol, rel_l2(u, ref)
+
+
+def make_ops(fib, seed):
+    """Random dense stand-ins with the shapes of the reference's members (the kernels are plain linear algebra)."""
+    rng = np.random.default_rng(seed)
+    n_nodes = [int(n) for n in fib["n_nodes"]]
+    ops = dict(n_nodes=n_nodes, A=[], force=[], D_1_0={}, P={}, length_prev=[], plus=[])
+    xs = []
+    for n in n_nodes:
+        ops["A"].append(rng.normal(size=(4 * n, 4 * n)) / np.sqrt(4 * n))
+        ops["force"].append(rng.normal(size=(3 * n, 4 * n)) / np.sqrt(4 * n))
+        t = rng.normal(size=(n, 3))
+        xs.append(t / np.linalg.norm(t, axis=1)[:, None])
+        ops["length_prev"].append(rng.uniform(0.5, 2.0))
+        ops["plus"].append(int(rng.integers(0, 2)))
+        if n not in ops["D_1_0"]:
+            ops["D_1_0"][n] = rng.normal(size=(n, n))
+            ops["P"][n] = rng.normal(size=(4 * n - 14, 4 * n)) / np.sqrt(4 * n)
+    ops["xs"] = np.concatenate(xs) if xs else np.zeros((0, 3))
+    return ops
+
+
+def load_ops(fl, ops):
+    for n in ops["D_1_0"]:
+        fl.set_fiber_class(n, ops["D_1_0"][n], ops["P"][n])
+    fl.set_fiber_operators(ops["A"], ops["force"], ops["xs"], ops["length_prev"], ops["plus"])
+
+
+NODES = (4, 5, 8, 16, 17, 32, 48, 64)
+
+
+def test_apply_fiber_force_ragged():
+    fib, shell, body = make_system(21, 57, 0, 0, 0, nodes=NODES)
+    ops = make_ops(fib, 1)
+    x = np.random.default_rng(2).normal(size=4 * fib["pos"].shape[0])
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        load_ops(fl, ops)
+        fw = fl.apply_fiber_force(x)
+        assert fl.stats()["launches"] == 1
+    _check(fw, orc.apply_fiber_force(ops["force"], x, ops["n_nodes"]))
+
+
+@pytest.mark.parametrize("with_boundary", [False, True])
+def test_fiber_matvec_ragged(with_boundary):
+    fib, shell, body = make_system(22, 41, 0, 0, 0, nodes=NODES)
+    ops = make_ops(fib, 3)
+    rng = np.random.default_rng(4)
+    nf = fib["pos"].shape[0]
+    x, v = rng.normal(size=4 * nf), rng.normal(size=(nf, 3))
+    vb = rng.normal(size=(len(ops["n_nodes"]), 7)) if with_boundary else None
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        load_ops(fl, ops)
+        res = fl.fiber_matvec(x, v, vb)
+        res2 = fl.fiber_matvec(x, v, vb)
+    assert np.array_equal(res, res2)  # fixed summation order
+    _check(res, orc.fiber_container_matvec(ops, x, v, vb))
+
+
+def test_fiber_matvec_long_fiber():
+    """One fiber of 300 nodes: 1200 columns, several row blocks, shared memory above the smallest sizes."""
+    fib, shell, body = make_system(23, 3, 0, 0, 0, nodes=(300,))
+    ops = make_ops(fib, 5)
+    rng = np.random.default_rng(6)
+    nf = fib["pos"].shape[0]
+    x, v = rng.normal(size=4 * nf), rng.normal(size=(nf, 3))
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        load_ops(fl, ops)
+        fw = fl.apply_fiber_force(x)
+        res = fl.fiber_matvec(x, v, None)
+    _check(fw, orc.apply_fiber_force(ops["force"], x, ops["n_nodes"]))
+    _check(res, orc.fiber_container_matvec(ops, x, v, None))
+
+
+@pytest.mark.parametrize("shape", [(60, 700, 400, 2), (25, 0, 0, 0), (30, 500, 0, 0)])
+def test_apply_matvec_end_to_end(shape):
+    fib, shell, body = make_system(24, *shape, nodes=(8, 16, 32, 64))
+    ops = make_ops(fib, 7)
+    rng = np.random.default_rng(8)
+    nf, ns = fib["pos"].shape[0], shell["pos"].shape[0]
+    x = rng.normal(size=4 * nf)
+    link = rng.normal(size=(len(ops["n_nodes"]), 7))
+    eta = 0.8
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        load_ops(fl, ops)
+        res, v_s, v_b = fl.apply_matvec(x, shell["density"], body["density"], ft_of(body), eta, link)
+        # the two-step host path gives the same numbers
+        fw = fl.apply_fiber_force(x)
+        v_all = fl.matvec(fw, shell["density"], body["density"], ft_of(body), eta)
+        res_2 = fl.fiber_matvec(x, v_all[:nf], link)
+    ref_res, ref_v = orc.apply_matvec_fibers(fib, shell, body, ops, x, eta, link)
+    _check(res, ref_res)
+    if ns:
+        _check(v_s, ref_v[nf:nf + ns])
+    if body["pos"].shape[0]:
+        _check(v_b, ref_v[nf + ns:])
+    assert np.array_equal(res, res_2)
+    assert np.array_equal(v_s, v_all[nf:nf + ns])
+
+
+def test_operator_errors():
+    fib, shell, body = make_system(25, 6, 50, 0, 0, nodes=(8, 16))
+    ops = make_ops(fib, 9)
+    x = np.zeros(4 * fib["pos"].shape[0])
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        with pytest.raises(skb.SkbError, match="set_fiber_operators"):
+            fl.apply_fiber_force(x)
+        # a node count without class matrices
+        only = sorted(ops["D_1_0"])[0]
+        fl.set_fiber_class(only, ops["D_1_0"][only], ops["P"][only])
+        if len(ops["D_1_0"]) > 1:
+            with pytest.raises(skb.SkbError, match="set_fiber_class"):
+                fl.set_fiber_operators(ops["A"], ops["force"], ops["xs"], ops["length_prev"], ops["plus"])
+        load_ops(fl, ops)
+        fl.apply_fiber_force(x)
+        # new fibers invalidate the operators
+        load(fl, fib, shell, body)
+        with pytest.raises(skb.SkbError, match="set_fiber_operators"):
+            fl.fiber_matvec(x, np.zeros((fib["pos"].shape[0], 3)))
+        load_ops(fl, ops)
+        fl.set_target_window(0, 10)
+        with pytest.raises(skb.SkbError, match="full target window"):
+            fl.apply_matvec(x, shell["density"], body["density"], ft_of(body), 1.0)
+        with pytest.raises((skb.SkbError, ValueError)):
+            fl.set_fiber_class(3, np.zeros((3, 3)), np.zeros((0, 12)))
+
+
+def test_no_fibers():
+    fib, shell, body = make_system(26, 0, 300, 200, 1)
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        fl.set_fiber_operators([], [], np.zeros((0, 3)), [], [])
+        res, v_s, v_b = fl.apply_matvec(np.zeros(0), shell["density"], body["density"], ft_of(body), 1.0)
+        v_all = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), 1.0)
+    assert res.shape == (0,)
+    assert np.array_equal(v_s, v_all[:300]) and np.array_equal(v_b, v_all[300:])

@@ -157,3 +157,77 @@ def test_matvec_flow_shell_mask():
     v0 = orc.matvec_flow(fib, shell0, body, 1.0)
     assert np.array_equal(v[32:72], v0[32:72])
     assert not np.allclose(v[:32], v0[:32])
+
+
+# ---- per-fiber dense operators -------------------------------------------------------------
+
+def _fiber_ops(rng, n):
+    A = rng.normal(size=(4 * n, 4 * n))
+    D = rng.normal(size=(n, n))
+    P = rng.normal(size=(4 * n - 14, 4 * n))
+    xs = rng.normal(size=(n, 3))
+    return A, D, P, xs
+
+
+@pytest.mark.parametrize("n", [4, 5, 16, 33])
+@pytest.mark.parametrize("plus", [0, 1])
+def test_fiber_matvec_loop_form_equals_assembled_operator(n, plus):
+    # FiberFiniteDifference::matvec (ffd.cpp:276-312) restated statement by statement must equal
+    # A x + V vec(v) + y_BC with V assembled independently from the same statements
+    rng = np.random.default_rng(100 + n)
+    A, D, P, xs = _fiber_ops(rng, n)
+    x, v, vb = rng.normal(size=4 * n), rng.normal(size=(n, 3)), rng.normal(size=7)
+    r = orc.fiber_matvec(A, D, P, xs, 1.3, plus, x, v, vb)
+    V = orc.fiber_velocity_operator(D, P, xs, 1.3, plus)
+    y = np.zeros(4 * n)
+    y[4 * n - 14:4 * n - 7] = vb
+    assert rel_max(r, A @ x + V @ v.reshape(-1) + y) < 1e-13
+    # without link conditions (v_boundary.size() == 0, ffd.cpp:305)
+    r0 = orc.fiber_matvec(A, D, P, xs, 1.3, plus, x, v, None)
+    assert rel_max(r0, A @ x + V @ v.reshape(-1)) < 1e-13
+    # the last 14 rows see the velocity only through the two end-point projections (ffd.cpp:298-309)
+    bc = 4 * n - 14
+    tail = (r0 - A @ x)[bc:]
+    expect = np.zeros(14)
+    expect[3] = v[0] @ xs[0]
+    if plus:
+        expect[10] = v[-1] @ xs[-1]
+    assert np.allclose(tail, expect, atol=1e-12)
+
+
+def test_apply_fiber_force_layout():
+    # force_operator_ * x is [fx(n); fy(n); fz(n)] per fiber and lands in row k of the 3 x N block (fcfd.cpp:278-281)
+    rng = np.random.default_rng(7)
+    n_nodes = [4, 9, 6]
+    ops = [rng.normal(size=(3 * n, 4 * n)) for n in n_nodes]
+    x = rng.normal(size=4 * sum(n_nodes))
+    fw = orc.apply_fiber_force(ops, x, n_nodes)
+    assert fw.shape == (sum(n_nodes), 3)
+    off = 0
+    for F, n in zip(ops, n_nodes):
+        ff = F @ x[4 * off:4 * off + 4 * n]
+        assert np.array_equal(fw[off:off + n].T.reshape(-1), ff)
+        off += n
+
+
+def test_fiber_container_matvec_is_blockwise():
+    rng = np.random.default_rng(8)
+    n_nodes = [8, 5, 8]
+    ops = dict(n_nodes=n_nodes, A=[], D_1_0={}, P={}, length_prev=[1.0, 2.0, 0.7], plus=[1, 0, 1])
+    xs = []
+    for n in n_nodes:
+        A, D, P, t = _fiber_ops(rng, n)
+        ops["A"].append(A)
+        ops["D_1_0"].setdefault(n, D)
+        ops["P"].setdefault(n, P)
+        xs.append(t)
+    ops["xs"] = np.concatenate(xs)
+    N = sum(n_nodes)
+    x, v, vb = rng.normal(size=4 * N), rng.normal(size=(N, 3)), rng.normal(size=(3, 7))
+    res = orc.fiber_container_matvec(ops, x, v, vb)
+    off = 0
+    for i, n in enumerate(n_nodes):
+        one = orc.fiber_matvec(ops["A"][i], ops["D_1_0"][n], ops["P"][n], ops["xs"][off:off + n],
+                               ops["length_prev"][i], ops["plus"][i], x[4 * off:4 * off + 4 * n], v[off:off + n], vb[i])
+        assert np.array_equal(res[4 * off:4 * off + 4 * n], one)
+        off += n
