@@ -11,6 +11,7 @@
 //
 // Every failure of the C ABI becomes std::runtime_error (caught in skelly_sim.cpp:57-64).
 #pragma once
+#include "../skelly_b200_dense.h"
 #include "../skelly_b200_flow.h"
 #include "kernels.hpp"
 
@@ -148,6 +149,21 @@ template <class M> class FlowEngineT {
                                     fiber_link_conditions.size() > 0 ? fiber_link_conditions.data() : nullptr, eta,
                                     res.data(), v_shell.data(), v_bodies.data()),
               "skb_flow_apply_matvec");
+        return res;
+    }
+    /// The same with shell.matvec on the device: `dn` holds stresslet_plus_complementary_ (skelly_b200_dense.h);
+    /// res_shell (3 N_s) = stresslet_plus_complementary_ * x_shell + v_shell  (system.cpp:319, periphery.cpp:38-47)
+    M apply_matvec(skb_dense *dn, const M &x_fibers, const M &x_shell, const M &body_densities,
+                   const M &forces_torques, const M &fiber_link_conditions, double eta, M &res_shell,
+                   M &v_bodies) const {
+        M res = M::Zero(4 * st_->n_fib, 1);
+        res_shell = M::Zero(3 * st_->n_shell, 1);
+        v_bodies = M::Zero(3, st_->n_body);
+        check(skb_flow_apply_matvec_dense(st_->fl, dn, x_fibers.data(), x_shell.data(), body_densities.data(),
+                                          forces_torques.data(),
+                                          fiber_link_conditions.size() > 0 ? fiber_link_conditions.data() : nullptr,
+                                          eta, res.data(), res_shell.data(), v_bodies.data()),
+              "skb_flow_apply_matvec_dense");
         return res;
     }
     skb_flow *handle() const { return st_->fl; }

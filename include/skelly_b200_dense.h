@@ -36,6 +36,14 @@ SKB_API int skb_dense_set_matrix(skb_dense *dn, int op, const double *A_rowmajor
 /* y[n_rows] = A x (+ v_add if not NULL).  Host pointers, synchronous. */
 SKB_API int skb_dense_apply(skb_dense *dn, int op, const double *x, const double *v_add, double *y);
 
+/* Device-pointer form for a single-device handle: x, v_add (or NULL) and y already on the handle's device (device 0);
+ * asynchronous on `stream` (cudaStream_t as void*, used verbatim).  This is what keeps x_shell / v_shell on the
+ * device inside skb_flow_apply_matvec_dense (skelly_b200_flow.h). */
+SKB_API int skb_dense_apply_device(skb_dense *dn, int op, const double *d_x, const double *d_v_add, double *d_y,
+                                   void *stream);
+/* shape given to skb_dense_set_matrix (n_rows = -1 before it was called) */
+SKB_API int skb_dense_shape(const skb_dense *dn, int op, int64_t *n_rows, int64_t *n_cols);
+
 typedef struct skb_dense_stats {
     double kernel_ms; /* CUDA-event time of the GEMV kernel (max over devices) */
     double total_ms;  /* including H2D of x and D2H of y */

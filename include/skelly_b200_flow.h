@@ -127,6 +127,15 @@ SKB_API int skb_flow_apply_matvec(skb_flow *fl, const double *x_fibers, const do
                                   const double *fiber_link_conditions, double eta, double *res_fibers,
                                   double *v_shell, double *v_bodies);
 
+/* The same with Periphery::matvec on the device as well (skelly_b200_dense.h, single-device handle holding
+ * SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY of size 3 N_s): returns res_shell = stresslet_plus_complementary_ * x_shell +
+ * v_shell (system.cpp:319, periphery.cpp:38-47) instead of v_shell; x_shell and v_shell never leave the device. */
+struct skb_dense;
+SKB_API int skb_flow_apply_matvec_dense(skb_flow *fl, struct skb_dense *dn, const double *x_fibers,
+                                        const double *x_shell, const double *body_densities,
+                                        const double *body_forces_torques, const double *fiber_link_conditions,
+                                        double eta, double *res_fibers, double *res_shell, double *v_bodies);
+
 typedef struct skb_flow_stats {
     double device_ms;   /* CUDA-event time of the last call, first launch to last kernel (copies excluded) */
     double total_ms;    /* including H2D / D2H */

@@ -115,6 +115,9 @@ def library() -> C.CDLL:
         "skb_flow_apply_fiber_force": ([ctxp, _dp, _dp], C.c_int),
         "skb_flow_fiber_matvec": ([ctxp, _dp, _dp, _dp, _dp], C.c_int),
         "skb_flow_apply_matvec": ([ctxp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp], C.c_int),
+        "skb_flow_apply_matvec_dense": ([ctxp, ctxp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp], C.c_int),
+        "skb_dense_apply_device": ([ctxp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+        "skb_dense_shape": ([ctxp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
         # include/skelly_b200_dense.h
         "skb_dense_create": ([C.c_int, C.POINTER(ctxp)], C.c_int),
         "skb_dense_destroy": ([ctxp], C.c_int),
@@ -459,9 +462,10 @@ class Flow:
         return res
 
     def apply_matvec(self, x_fibers, shell_density, body_densities, body_forces_torques, eta,
-                     fiber_link_conditions=None):
+                     fiber_link_conditions=None, dense=None):
         """System::apply_matvec (system.cpp:298-318) with the fiber operators on the device.
-        Returns (res_fibers (4 N_f,), v_shell (N_s,3), v_bodies (N_b,3))."""
+        Returns (res_fibers (4 N_f,), v_shell (N_s,3), v_bodies (N_b,3)); with dense= a single-device Dense holding
+        stresslet_plus_complementary the second item is res_shell = shell.matvec(x_shell, v_shell) instead."""
         x = np.ascontiguousarray(x_fibers, dtype=np.float64).reshape(-1)
         assert x.shape[0] == 4 * self.n_fib
         b, c = _arr(shell_density, 3), _arr(body_densities, 3)
@@ -469,8 +473,14 @@ class Flow:
         vb = None if fiber_link_conditions is None else _arr(fiber_link_conditions, 7)
         res = np.empty(4 * self.n_fib)
         v_s, v_b = np.empty((self.n_shell, 3)), np.empty((self.n_body, 3))
-        _check(library().skb_flow_apply_matvec(self._h, _p(x), _p(b), _p(c), _p(ft), None if vb is None else _p(vb),
-                                               float(eta), _p(res), _p(v_s), _p(v_b)))
+        if dense is not None:
+            _check(library().skb_flow_apply_matvec_dense(self._h, dense._h, _p(x), _p(b), _p(c), _p(ft),
+                                                         None if vb is None else _p(vb), float(eta), _p(res), _p(v_s),
+                                                         _p(v_b)))
+        else:
+            _check(library().skb_flow_apply_matvec(self._h, _p(x), _p(b), _p(c), _p(ft),
+                                                   None if vb is None else _p(vb), float(eta), _p(res), _p(v_s),
+                                                   _p(v_b)))
         return res, v_s, v_b
 
     def stats(self) -> dict:

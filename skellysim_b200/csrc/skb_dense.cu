@@ -4,6 +4,7 @@
 #include "../../include/skelly_b200_dense.h"
 
 #include <algorithm>
+#include <cstdint>
 #include <memory>
 #include <vector>
 
@@ -251,6 +252,47 @@ int skb_dense_apply(skb_dense *dn, int op, const double *x, const double *v_add,
     }
     dn->stats.kernel_ms = k;
     dn->stats.total_ms = t;
+    dn->stats.bytes = 8 * n_rows * n_cols;
+    return SKB_OK;
+}
+
+int skb_dense_shape(const skb_dense *dn, int op, int64_t *n_rows, int64_t *n_cols) {
+    if (!dn || (op != 0 && op != 1) || !n_rows || !n_cols)
+        return set_error(SKB_ERR_INVALID, "skb_dense_shape: bad arguments");
+    *n_rows = dn->rows[op];
+    *n_cols = dn->cols[op];
+    return SKB_OK;
+}
+
+int skb_dense_apply_device(skb_dense *dn, int op, const double *d_x, const double *d_v_add, double *d_y,
+                           void *stream) {
+    if (!dn || (op != 0 && op != 1))
+        return set_error(SKB_ERR_INVALID, "skb_dense_apply_device: bad arguments");
+    if (dn->rows[op] < 0)
+        return set_error(SKB_ERR_STATE, "skb_dense_apply_device: skb_dense_set_matrix(op=%d) has not been called", op);
+    if (dn->devs.size() != 1)
+        return set_error(SKB_ERR_INVALID, "skb_dense_apply_device needs a single-device handle (this one spans %d)",
+                         (int)dn->devs.size());
+    const long long n_rows = dn->rows[op], n_cols = dn->cols[op];
+    if (n_rows == 0)
+        return SKB_OK;
+    if ((n_cols > 0 && !d_x) || !d_y)
+        return set_error(SKB_ERR_INVALID, "skb_dense_apply_device: NULL x or y");
+    DenseDev &d = dn->devs[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(d.dev));
+    const int vec_ok = (n_cols % 2 == 0 && ((uintptr_t)d_x & 15) == 0) ? 1 : 0;
+    int occ = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, dense_gemv_kernel, 256, 0) != cudaSuccess || occ < 1)
+        occ = 2;
+    SKB_TRY(d.ticket.ensure(8));
+    CUDA_TRY(cudaMemsetAsync(d.ticket.ptr, 0, 8, st));
+    dense_gemv_kernel<<<d.num_sms * occ, 256, 0, st>>>((const double *)d.A[op].ptr, d_x, d_v_add, d_y, n_rows, n_cols,
+                                                      vec_ok, (unsigned long long *)d.ticket.ptr);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    dn->stats.kernel_ms = 0;
+    dn->stats.total_ms = 0;
     dn->stats.bytes = 8 * n_rows * n_cols;
     return SKB_OK;
 }

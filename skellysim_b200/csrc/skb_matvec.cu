@@ -6,6 +6,7 @@
 #include "fiber_ops.cuh"
 #include "skb_internal.hpp"
 #include "../../include/skelly_b200_flow.h"
+#include "../../include/skelly_b200_dense.h"
 
 #include <cmath>
 #include <cstdint>
@@ -98,7 +99,7 @@ struct skb_flow {
     int n_items_A = 0, n_items_F = 0;
     size_t gemv_smem = 0, fvel_smem = 0;
     DevBuf op_A, op_F, op_xs, op_len, op_plus, op_class, op_classD, op_classP, items_A, items_F;
-    DevBuf x_fib, res_fib, vb;
+    DevBuf x_fib, res_fib, vb, res_shell;
     // staging
     DevBuf in_fib, in_shell, in_body, in_force, in_torque, vel, tmp;
     skb_flow_stats stats{};
@@ -373,7 +374,7 @@ int skb_flow_destroy(skb_flow *fl) {
     DevBuf *bufs[] = {&fl->fiber_offset, &fl->fiber_length, &fl->r_fib, &fl->r_shell, &fl->r_body, &fl->centers,
                       &fl->pt_pos, &fl->pt_force, &fl->pt_torque, &fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel, &fl->tmp,
                       &fl->op_A, &fl->op_F, &fl->op_xs, &fl->op_len, &fl->op_plus, &fl->op_class, &fl->op_classD,
-                      &fl->op_classP, &fl->items_A, &fl->items_F, &fl->x_fib, &fl->res_fib, &fl->vb};
+                      &fl->op_classP, &fl->items_A, &fl->items_F, &fl->x_fib, &fl->res_fib, &fl->vb, &fl->res_shell};
     for (DevBuf *b : bufs)
         b->release();
     fl->g_matvec.reset();
@@ -1052,10 +1053,13 @@ int skb_flow_fiber_matvec(skb_flow *fl, const double *x_fibers, const double *v_
     return finish_stats(fl);
 }
 
-int skb_flow_apply_matvec(skb_flow *fl, const double *x_fibers, const double *shell_density,
-                          const double *body_densities, const double *body_forces_torques,
-                          const double *fiber_link_conditions, double eta, double *res_fibers, double *v_shell,
-                          double *v_bodies) {
+} // extern "C"
+
+// shared body of skb_flow_apply_matvec / skb_flow_apply_matvec_dense; dn != NULL: out_shell = res_shell
+static int apply_matvec_impl(skb_flow *fl, skb_dense *dn, const double *x_fibers, const double *shell_density,
+                             const double *body_densities, const double *body_forces_torques,
+                             const double *fiber_link_conditions, double eta, double *res_fibers, double *v_shell,
+                             double *v_bodies) {
     if (!fl || !(eta > 0))
         return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec: bad arguments");
     SKB_TRY(need_ops(fl, "skb_flow_apply_matvec"));
@@ -1098,17 +1102,55 @@ int skb_flow_apply_matvec(skb_flow *fl, const double *x_fibers, const double *sh
     SKB_TRY(fiber_matvec_dev(fl, (const double *)fl->x_fib.ptr, (const double *)fl->vel.ptr,
                              fiber_link_conditions ? (const double *)fl->vb.ptr : nullptr,
                              (double *)fl->res_fib.ptr));
+    const double *d_shell_out = (const double *)fl->vel.ptr + 3 * nf;
+    if (dn && ns) {
+        // res_shell = shell.matvec(x_shell, v_shell) = stresslet_plus_complementary_ * x_shell + v_shell
+        // (system.cpp:319, periphery.cpp:38-47); x_shell is the density already on the device
+        SKB_TRY(fl->res_shell.ensure((size_t)ns * 24));
+        SKB_TRY(skb_dense_apply_device(dn, SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY, (const double *)fl->in_shell.ptr,
+                                       d_shell_out, (double *)fl->res_shell.ptr, fl->stream));
+        fl->launches += 1;
+        d_shell_out = (const double *)fl->res_shell.ptr;
+    }
     CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
     if (nf)
         CUDA_TRY(cudaMemcpyAsync(res_fibers, fl->res_fib.ptr, (size_t)nf * 32, cudaMemcpyDeviceToHost, fl->stream));
     if (ns)
-        CUDA_TRY(cudaMemcpyAsync(v_shell, (const double *)fl->vel.ptr + 3 * nf, (size_t)ns * 24,
-                                 cudaMemcpyDeviceToHost, fl->stream));
+        CUDA_TRY(cudaMemcpyAsync(v_shell, d_shell_out, (size_t)ns * 24, cudaMemcpyDeviceToHost, fl->stream));
     if (nb)
         CUDA_TRY(cudaMemcpyAsync(v_bodies, (const double *)fl->vel.ptr + 3 * (nf + ns), (size_t)nb * 24,
                                  cudaMemcpyDeviceToHost, fl->stream));
     CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
     return finish_stats(fl);
+}
+
+extern "C" {
+
+int skb_flow_apply_matvec(skb_flow *fl, const double *x_fibers, const double *shell_density,
+                          const double *body_densities, const double *body_forces_torques,
+                          const double *fiber_link_conditions, double eta, double *res_fibers, double *v_shell,
+                          double *v_bodies) {
+    return apply_matvec_impl(fl, nullptr, x_fibers, shell_density, body_densities, body_forces_torques,
+                             fiber_link_conditions, eta, res_fibers, v_shell, v_bodies);
+}
+
+int skb_flow_apply_matvec_dense(skb_flow *fl, skb_dense *dn, const double *x_fibers, const double *x_shell,
+                                const double *body_densities, const double *body_forces_torques,
+                                const double *fiber_link_conditions, double eta, double *res_fibers,
+                                double *res_shell, double *v_bodies) {
+    if (!fl || !dn)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec_dense: NULL handle");
+    if (fl->dev != 0) // a single-device skb_dense handle lives on device 0 (skb_dense_create)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec_dense: the flow is on device %d, the dense handle on "
+                                          "device 0", fl->dev);
+    int64_t rows = 0, cols = 0;
+    SKB_TRY(skb_dense_shape(dn, SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY, &rows, &cols));
+    if (rows != 3 * fl->n_shell || cols != 3 * fl->n_shell)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec_dense: stresslet_plus_complementary is %lld x %lld, the "
+                                          "periphery has %lld nodes (need %lld x %lld)", (long long)rows,
+                         (long long)cols, fl->n_shell, 3 * fl->n_shell, 3 * fl->n_shell);
+    return apply_matvec_impl(fl, dn, x_fibers, x_shell, body_densities, body_forces_torques, fiber_link_conditions,
+                             eta, res_fibers, res_shell, v_bodies);
 }
 
 int skb_flow_last_stats(const skb_flow *fl, skb_flow_stats *out) {

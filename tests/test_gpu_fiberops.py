@@ -159,3 +159,29 @@ def test_no_fibers():
         v_all = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), 1.0)
     assert res.shape == (0,)
     assert np.array_equal(v_s, v_all[:300]) and np.array_equal(v_b, v_all[300:])
+
+
+def test_apply_matvec_with_periphery_dense_operator():
+    """res_shell = stresslet_plus_complementary_ * x_shell + v_shell (periphery.cpp:38-47) formed on the device:
+    bit-identical to skb_dense_apply on the v_shell that skb_flow_apply_matvec returns."""
+    fib, shell, body = make_system(27, 40, 600, 300, 1, nodes=(8, 16, 32))
+    ops = make_ops(fib, 11)
+    rng = np.random.default_rng(12)
+    nf, ns = fib["pos"].shape[0], shell["pos"].shape[0]
+    x = rng.normal(size=4 * nf)
+    M = rng.normal(size=(3 * ns, 3 * ns)) / np.sqrt(3 * ns)
+    eta = 1.1
+    with skb.Flow(0) as fl, skb.Dense(1) as dn:
+        load(fl, fib, shell, body)
+        load_ops(fl, ops)
+        dn.set_matrix(skb.DENSE_STRESSLET_PLUS_COMPLEMENTARY, M)
+        res, v_s, v_b = fl.apply_matvec(x, shell["density"], body["density"], ft_of(body), eta)
+        res_d, res_shell, v_b_d = fl.apply_matvec(x, shell["density"], body["density"], ft_of(body), eta, dense=dn)
+        two_step = dn.apply(skb.DENSE_STRESSLET_PLUS_COMPLEMENTARY, shell["density"].reshape(-1), v_s.reshape(-1))
+        # wrong size is refused
+        dn.set_matrix(skb.DENSE_STRESSLET_PLUS_COMPLEMENTARY, M[:-3, :-3])
+        with pytest.raises(skb.SkbError, match="periphery has"):
+            fl.apply_matvec(x, shell["density"], body["density"], ft_of(body), eta, dense=dn)
+    assert np.array_equal(res, res_d) and np.array_equal(v_b, v_b_d)
+    assert np.array_equal(res_shell.reshape(-1), two_step)
+    _check(res_shell.reshape(-1), orc.periphery_dense_apply(M, shell["density"].reshape(-1), v_s.reshape(-1)))
