@@ -88,6 +88,13 @@ SKB_API int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double
  * fiber rows inside the window. */
 SKB_API int skb_flow_set_target_window(skb_flow *fl, int64_t begin, int64_t end);
 
+/* The reference's own MPI decomposition as three ranges (whole fibers [fiber_begin, fiber_end) of the container,
+ * fiber_container_finite_difference.cpp:102-120; periphery rows, periphery.cpp:387-400; body-node rows -- all on
+ * rank 0 in the reference): the target list of this flow becomes [own fiber nodes | own shell rows | own body rows]
+ * and v_all / d_v_window has that many rows in that order.  Replaces a window set earlier (and vice versa). */
+SKB_API int skb_flow_set_target_ranges(skb_flow *fl, int fiber_begin, int fiber_end, int64_t shell_begin,
+                                       int64_t shell_end, int64_t body_begin, int64_t body_end);
+
 /* Device-pointer form of skb_flow_matvec: all inputs and the output already on this flow's device; asynchronous on
  * `stream` (cudaStream_t as void*, used verbatim).  d_body_forces / d_body_torques are 3 x n_bodies each. */
 SKB_API int skb_flow_matvec_device(skb_flow *fl, const double *d_fib_forces, const double *d_shell_density,
@@ -116,6 +123,16 @@ SKB_API int skb_flow_apply_fiber_force(skb_flow *fl, const double *x_fibers, dou
  * (fiber_link_conditions of BodyContainer::calculate_link_conditions) or NULL for none (fcfd.cpp:216-232) */
 SKB_API int skb_flow_fiber_matvec(skb_flow *fl, const double *x_fibers, const double *v_fibers,
                                   const double *v_fib_boundary, double *res);
+/* One rank per GPU: under skb_flow_set_target_ranges (or a window that cuts no fiber) the resident operators are those
+ * of the rank's OWN fibers -- skb_flow_set_fiber_operators, skb_flow_apply_fiber_force and skb_flow_fiber_matvec then
+ * take / return the arrays of the own fibers only (x: 4 per own node, fw / v: 3 per own node, link conditions: 7 per
+ * own fiber), as the reference's local solution vectors do.  Device-pointer forms, asynchronous on `stream`:
+ *   d_fw_own = apply_fiber_force(d_x_own)  ->  [caller all-gathers fw]  ->  skb_flow_matvec_device  ->
+ *   d_res_own = fc.matvec(d_x_own, first own-fiber rows of d_v_window, d_link_own) */
+SKB_API int skb_flow_apply_fiber_force_device(skb_flow *fl, const double *d_x_fibers, double *d_fw, void *stream);
+SKB_API int skb_flow_fiber_matvec_device(skb_flow *fl, const double *d_x_fibers, const double *d_v_fibers,
+                                         const double *d_v_fib_boundary, double *d_res, void *stream);
+
 /* System::apply_matvec (system.cpp:269-324) with the fiber operators on the device:
  *   fw = apply_fiber_force(x_fibers); v_all = the fused flow of skb_flow_matvec;
  *   res_fibers = fc.matvec(x_fibers, v_fibers, fiber_link_conditions)

@@ -110,6 +110,9 @@ def library() -> C.CDLL:
         "skb_flow_set_background": ([ctxp, C.POINTER(C.c_int), _dp, _dp], C.c_int),
         "skb_flow_velocity_at_targets": ([ctxp, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_set_target_window": ([ctxp, C.c_int64, C.c_int64], C.c_int),
+        "skb_flow_set_target_ranges": ([ctxp, C.c_int, C.c_int] + [C.c_int64] * 4, C.c_int),
+        "skb_flow_apply_fiber_force_device": ([ctxp, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
+        "skb_flow_fiber_matvec_device": ([ctxp] + [C.c_void_p] * 5, C.c_int),
         "skb_flow_set_fiber_class": ([ctxp, C.c_int, _dp, _dp], C.c_int),
         "skb_flow_set_fiber_operators": ([ctxp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
         "skb_flow_apply_fiber_force": ([ctxp, _dp, _dp], C.c_int),
@@ -342,6 +345,7 @@ class Flow:
         _check(library().skb_flow_set_fibers(self._h, _p(r_fib), n_nodes.ctypes.data_as(C.POINTER(C.c_int)),
                                              _p(lengths), int(n_nodes.shape[0])))
         self.n_fib = r_fib.shape[0]
+        self._fiber_off = np.concatenate([[0], np.cumsum(n_nodes, dtype=np.int64)])
 
     def set_periphery(self, node_pos, node_normal):
         node_pos, node_normal = _arr(node_pos, 3), _arr(node_normal, 3)
@@ -399,8 +403,34 @@ class Flow:
     def set_target_window(self, begin: int, end: int = -1):
         """Evaluate only rows [begin, end) of [fibers | periphery | bodies] in matvec() (one rank's block)."""
         _check(library().skb_flow_set_target_window(self._h, int(begin), int(end)))
-        n_all = self.n_fib + self.n_shell + self.n_body
-        self._window = (min(begin, n_all), n_all if end < 0 else min(end, n_all))
+        self._window, self._ranges = (int(begin), int(end)), None
+
+    def set_target_ranges(self, fiber_begin, fiber_end, shell_begin, shell_end, body_begin, body_end):
+        """The reference's MPI decomposition: whole fibers [fiber_begin, fiber_end), periphery rows, body-node rows;
+        matvec() then returns [own fiber nodes | own shell rows | own body rows]."""
+        r = tuple(int(v) for v in (fiber_begin, fiber_end, shell_begin, shell_end, body_begin, body_end))
+        _check(library().skb_flow_set_target_ranges(self._h, *r))
+        self._ranges, self._window = r, None
+
+    def _pieces(self):
+        """(own fiber nodes, own shell rows, own body rows) of the current window / ranges."""
+        nf, ns, nb = self.n_fib, self.n_shell, self.n_body
+        cl = lambda x, lo, hi: min(max(x, lo), hi)
+        if getattr(self, "_ranges", None):
+            f0, f1, s0, s1, b0, b1 = self._ranges
+            off = getattr(self, "_fiber_off", np.zeros(1, dtype=np.int64))
+            nfib = len(off) - 1
+            f0 = cl(f0, 0, nfib)
+            f1 = cl(f1, f0, nfib)
+            s0 = cl(s0, 0, ns)
+            b0 = cl(b0, 0, nb)
+            return int(off[f1] - off[f0]), cl(s1, s0, ns) - s0, cl(b1, b0, nb) - b0
+        w0, w1 = getattr(self, "_window", None) or (0, -1)
+        n_all = nf + ns + nb
+        w0 = cl(w0, 0, n_all)
+        w1 = n_all if w1 < 0 else cl(w1, w0, n_all)
+        return (cl(w1, 0, nf) - cl(w0, 0, nf), cl(w1 - nf, 0, ns) - cl(w0 - nf, 0, ns),
+                cl(w1 - nf - ns, 0, nb) - cl(w0 - nf - ns, 0, nb))
 
     def matvec_device(self, d_fib_forces: int, d_shell_density: int, d_body_densities: int, d_body_forces: int,
                       d_body_torques: int, eta: float, d_v_window: int, stream: int = 0):
@@ -413,10 +443,7 @@ class Flow:
     def matvec(self, fib_forces, shell_density, body_densities, body_forces_torques, eta):
         a, b, c = _arr(fib_forces, 3), _arr(shell_density, 3), _arr(body_densities, 3)
         ft = _arr(body_forces_torques, 6)
-        n_all = self.n_fib + self.n_shell + self.n_body
-        w0, w1 = getattr(self, "_window", (0, n_all))
-        w1 = min(w1, n_all)
-        v = np.empty((max(w1 - w0, 0), 3))
+        v = np.empty((sum(self._pieces()), 3))
         _check(library().skb_flow_matvec(self._h, _p(a), _p(b), _p(c), _p(ft), float(eta), _p(v)))
         return v
 
@@ -439,15 +466,16 @@ class Flow:
         xs = _arr(xs, 3)
         lp = np.ascontiguousarray(length_prev, dtype=np.float64)
         pl = np.ascontiguousarray(plus_bc_velocity, dtype=np.int32)
-        assert xs.shape[0] == self.n_fib and lp.shape == pl.shape == (len(A_list),)
+        assert xs.shape[0] == self._pieces()[0] and lp.shape == pl.shape == (len(A_list),)
         _check(library().skb_flow_set_fiber_operators(self._h, _p(A), _p(F), _p(xs), _p(lp),
                                                       pl.ctypes.data_as(C.POINTER(C.c_int))))
 
     def apply_fiber_force(self, x_fibers):
         """fc.apply_fiber_force (fcfd.cpp:272-287): (4 N_f,) -> fw (N_f, 3)."""
         x = np.ascontiguousarray(x_fibers, dtype=np.float64).reshape(-1)
-        assert x.shape[0] == 4 * self.n_fib
-        fw = np.empty((self.n_fib, 3))
+        n_own = self._pieces()[0]
+        assert x.shape[0] == 4 * n_own
+        fw = np.empty((n_own, 3))
         _check(library().skb_flow_apply_fiber_force(self._h, _p(x), _p(fw)))
         return fw
 
@@ -455,11 +483,22 @@ class Flow:
         """fc.matvec (fcfd.cpp:216-232): x (4 N_f,), v (N_f,3), v_fib_boundary (n_fibers,7) or None -> res (4 N_f,)."""
         x = np.ascontiguousarray(x_fibers, dtype=np.float64).reshape(-1)
         v = _arr(v_fibers, 3)
-        assert x.shape[0] == 4 * self.n_fib and v.shape[0] == self.n_fib
+        n_own = self._pieces()[0]
+        assert x.shape[0] == 4 * n_own and v.shape[0] == n_own
         vb = None if v_fib_boundary is None else _arr(v_fib_boundary, 7)
-        res = np.empty(4 * self.n_fib)
+        res = np.empty(4 * n_own)
         _check(library().skb_flow_fiber_matvec(self._h, _p(x), _p(v), None if vb is None else _p(vb), _p(res)))
         return res
+
+    def apply_fiber_force_device(self, d_x_fibers: int, d_fw: int, stream: int = 0):
+        _check(library().skb_flow_apply_fiber_force_device(self._h, C.c_void_p(d_x_fibers), C.c_void_p(d_fw),
+                                                           C.c_void_p(stream)))
+
+    def fiber_matvec_device(self, d_x_fibers: int, d_v_fibers: int, d_v_fib_boundary: int, d_res: int,
+                            stream: int = 0):
+        _check(library().skb_flow_fiber_matvec_device(self._h, C.c_void_p(d_x_fibers), C.c_void_p(d_v_fibers),
+                                                      C.c_void_p(d_v_fib_boundary) if d_v_fib_boundary else None,
+                                                      C.c_void_p(d_res), C.c_void_p(stream)))
 
     def apply_matvec(self, x_fibers, shell_density, body_densities, body_forces_torques, eta,
                      fiber_link_conditions=None, dense=None):

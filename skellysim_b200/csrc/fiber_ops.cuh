@@ -76,7 +76,8 @@ __global__ void __launch_bounds__(kFiberGemvThreads)
     }
 }
 
-// One CTA per fiber.  res[4*off + r] += -(P vT)[r] (r < 4n-14) + xs_vT[r] + y_BC[r]   (ffd.cpp:276-312)
+// One CTA per fiber of the launch (fiber_offset points at the first of them; xs, v, res, v_boundary, length_prev,
+// plus_velocity and the class offsets are indexed from that fiber).  res[4*off + r] += -(P vT)[r] (r < 4n-14) + xs_vT[r] + y_BC[r]   (ffd.cpp:276-312)
 //   vT = [v_x; v_y; v_z; D_1^T (xs_x v_x + xs_y v_y + xs_z v_z)],  D_1 = D_1_0 * 2 / length_prev   (:280-293)
 //   xs_vT[bc+3] = v_0 . xs_0;  xs_vT[bc+10] = v_{n-1} . xs_{n-1} when the plus end has a velocity BC  (:298-309)
 //   y_BC[bc .. bc+7) = v_boundary(:, fiber)                                                           (:303-306)
@@ -90,8 +91,8 @@ __global__ void __launch_bounds__(256)
                           const double *__restrict__ v_boundary, double *__restrict__ res) {
     extern __shared__ double fv_smem[];
     const int f = blockIdx.x;
-    const long long off = fiber_offset[f];
-    const int n = (int)(fiber_offset[f + 1] - off);
+    const long long off = fiber_offset[f] - fiber_offset[0]; // node offset among the fibers of this launch
+    const int n = (int)(fiber_offset[f + 1] - fiber_offset[f]);
     double *vT = fv_smem;      // 4n
     double *s = fv_smem + 4 * n; // n
     const double *xs = xs_all + 3 * off, *v = v_all + 3 * off;

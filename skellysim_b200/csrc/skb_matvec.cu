@@ -64,7 +64,12 @@ struct skb_flow {
     TargetCache tc_fib, tc_shell, tc_body;
     bool mv_dirty = true;
     long long win_begin = 0, win_end = -1; // target window of the matvec in [fibers|shell|bodies] rows; -1 = all
-    long long fa = 0, fb = 0, ba = 0, bb = 0, w0 = 0, w1 = 0; // resolved window pieces (fiber rows, body rows)
+    bool use_ranges = false;               // skb_flow_set_target_ranges instead of a contiguous window
+    long long rq_f0 = 0, rq_f1 = 0, rq_s0 = 0, rq_s1 = 0, rq_b0 = 0, rq_b1 = 0; // requested (fiber indices, rows)
+    // resolved pieces of the matvec target list: fiber rows [fa,fb), shell rows [sa,sb), body rows [ba,bb);
+    // the output has n_win = (fb-fa)+(sb-sa)+(bb-ba) rows in that order
+    long long fa = 0, fb = 0, sa = 0, sb = 0, ba = 0, bb = 0, n_win = 0;
+    int op_f0 = 0, op_f1 = 0; // fibers [op_f0, op_f1) whose operators are resident (the fiber rows of the target list)
     cudaStream_t cur = nullptr;            // stream of the call in flight (own stream or the caller's)
     int n_points = 0;
     DevBuf pt_pos, pt_force, pt_torque;
@@ -683,32 +688,44 @@ int skb_flow_velocity_at_targets(skb_flow *fl, const double *r_trg, int64_t n_tr
     return finish_stats(fl);
 }
 
-// resolve the target window into its fiber / body pieces and (re)build the matvec target lists
+// resolve the target window / ranges into fiber, shell and body pieces and (re)build the matvec target lists
 static int prepare_matvec_targets(skb_flow *fl) {
     const long long nf = fl->n_fib, ns = fl->n_shell, nb = fl->n_body, n_all = nf + ns + nb;
     if (!fl->mv_dirty)
         return SKB_OK;
-    long long w0 = fl->win_begin, w1 = fl->win_end < 0 ? n_all : fl->win_end;
-    w0 = std::min(std::max(w0, 0LL), n_all);
-    w1 = std::min(std::max(w1, w0), n_all);
     auto clampi = [](long long x, long long lo, long long hi) { return std::min(std::max(x, lo), hi); };
-    fl->w0 = w0;
-    fl->w1 = w1;
-    fl->fa = clampi(w0, 0, nf);
-    fl->fb = clampi(w1, 0, nf);
-    fl->ba = clampi(w0 - nf - ns, 0, nb);
-    fl->bb = clampi(w1 - nf - ns, 0, nb);
+    if (fl->use_ranges) {
+        const long long f0 = clampi(fl->rq_f0, 0, fl->n_fibers), f1 = clampi(fl->rq_f1, f0, fl->n_fibers);
+        fl->fa = fl->n_fibers ? fl->h_fiber_off[(size_t)f0] : 0;
+        fl->fb = fl->n_fibers ? fl->h_fiber_off[(size_t)f1] : 0;
+        fl->sa = clampi(fl->rq_s0, 0, ns);
+        fl->sb = clampi(fl->rq_s1, fl->sa, ns);
+        fl->ba = clampi(fl->rq_b0, 0, nb);
+        fl->bb = clampi(fl->rq_b1, fl->ba, nb);
+    } else {
+        long long w0 = fl->win_begin, w1 = fl->win_end < 0 ? n_all : fl->win_end;
+        w0 = clampi(w0, 0, n_all);
+        w1 = clampi(w1, w0, n_all);
+        fl->fa = clampi(w0, 0, nf);
+        fl->fb = clampi(w1, 0, nf);
+        fl->sa = clampi(w0 - nf, 0, ns);
+        fl->sb = clampi(w1 - nf, 0, ns);
+        fl->ba = clampi(w0 - nf - ns, 0, nb);
+        fl->bb = clampi(w1 - nf - ns, 0, nb);
+    }
+    const long long n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba;
+    fl->n_win = n_fw + n_sw + n_bw;
     // target lists of apply_matvec: r_all = [fibers | shell | bodies] (system.cpp:284-291),
-    // r_fibbody = [fibers | bodies] (system.cpp:301-303), both restricted to the window
-    std::vector<double> r_all((size_t)n_all * 3);
-    std::copy(fl->h_r_fib.begin(), fl->h_r_fib.end(), r_all.begin());
-    std::copy(fl->h_r_shell.begin(), fl->h_r_shell.end(), r_all.begin() + 3 * nf);
-    std::copy(fl->h_r_body.begin(), fl->h_r_body.end(), r_all.begin() + 3 * (nf + ns));
-    std::vector<double> r_fb;
+    // r_fibbody = [fibers | bodies] (system.cpp:301-303), both restricted to this rank's pieces
+    std::vector<double> r_win, r_fb;
+    r_win.reserve((size_t)fl->n_win * 3);
+    r_win.insert(r_win.end(), fl->h_r_fib.begin() + 3 * fl->fa, fl->h_r_fib.begin() + 3 * fl->fb);
+    r_win.insert(r_win.end(), fl->h_r_shell.begin() + 3 * fl->sa, fl->h_r_shell.begin() + 3 * fl->sb);
+    r_win.insert(r_win.end(), fl->h_r_body.begin() + 3 * fl->ba, fl->h_r_body.begin() + 3 * fl->bb);
     r_fb.insert(r_fb.end(), fl->h_r_fib.begin() + 3 * fl->fa, fl->h_r_fib.begin() + 3 * fl->fb);
     r_fb.insert(r_fb.end(), fl->h_r_body.begin() + 3 * fl->ba, fl->h_r_body.begin() + 3 * fl->bb);
-    SKB_TRY(skb_set_targets(fl->fib[1], r_all.data() + 3 * w0, w1 - w0));
-    SKB_TRY(skb_set_targets(fl->body[1], r_all.data() + 3 * w0, w1 - w0));
+    SKB_TRY(skb_set_targets(fl->fib[1], r_win.data(), fl->n_win));
+    SKB_TRY(skb_set_targets(fl->body[1], r_win.data(), fl->n_win));
     SKB_TRY(skb_set_targets(fl->shell[1], r_fb.data(), (long long)r_fb.size() / 3));
     fl->mv_dirty = false;
     return SKB_OK;
@@ -717,12 +734,12 @@ static int prepare_matvec_targets(skb_flow *fl) {
 // device-side matvec flow on fl->cur: all strengths resident, d_v = window rows of v_all
 static int matvec_core(skb_flow *fl, const double *d_ff, const double *d_sd, const double *d_bd, const double *d_f,
                        const double *d_t, double eta, double *d_v) {
-    const long long nf = fl->n_fib, ns = fl->n_shell;
-    const long long n_win = fl->w1 - fl->w0, n_fw = fl->fb - fl->fa, n_bw = fl->bb - fl->ba;
+    const long long ns = fl->n_shell;
+    const long long n_win = fl->n_win, n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba;
     if (n_win == 0)
         return SKB_OK;
     // v_all = fc.flow(r_all, fw, eta)                                  system.cpp:299
-    // (the window's fiber rows come first, so the self term applies to targets [0, n_fw) of the window)
+    // (this rank's fiber rows come first, so the self term applies to targets [0, n_fw) of its list)
     SKB_TRY(fibers_dev(fl, fl->fib[1], d_ff, eta, n_fw > 0, d_v, 0, fl->fa, fl->fb));
     // v_fibers, v_bodies += shell.flow(r_fibbody, x_shell, eta)         system.cpp:304,313-315
     if (ns > 0 && n_fw + n_bw > 0) {
@@ -731,14 +748,13 @@ static int matvec_core(skb_flow *fl, const double *d_ff, const double *d_sd, con
         SKB_TRY(periphery_dev(fl, fl->shell[1], d_sd, eta, d_tmp, 0));
         const int bs = 256;
         if (n_fw > 0) {
-            add_inplace_kernel<<<(unsigned)((3 * n_fw + bs - 1) / bs), bs, 0, fl->cur>>>(d_v + 3 * (fl->fa - fl->w0),
-                                                                                        d_tmp, 3 * n_fw);
+            add_inplace_kernel<<<(unsigned)((3 * n_fw + bs - 1) / bs), bs, 0, fl->cur>>>(d_v, d_tmp, 3 * n_fw);
             count_launch(1);
             fl->launches += 1;
         }
         if (n_bw > 0) {
             add_inplace_kernel<<<(unsigned)((3 * n_bw + bs - 1) / bs), bs, 0, fl->cur>>>(
-                d_v + 3 * (nf + ns + fl->ba - fl->w0), d_tmp + 3 * n_fw, 3 * n_bw);
+                d_v + 3 * (n_fw + n_sw), d_tmp + 3 * n_fw, 3 * n_bw);
             count_launch(1);
             fl->launches += 1;
         }
@@ -755,7 +771,27 @@ int skb_flow_set_target_window(skb_flow *fl, int64_t begin, int64_t end) {
                          (long long)end);
     fl->win_begin = begin;
     fl->win_end = end;
+    fl->use_ranges = false;
     fl->mv_dirty = true;
+    fl->ops_ready = false; // resident fiber operators belong to one set of fiber rows
+    fl->geom_version++;
+    return SKB_OK;
+}
+
+int skb_flow_set_target_ranges(skb_flow *fl, int fiber_begin, int fiber_end, int64_t shell_begin, int64_t shell_end,
+                               int64_t body_begin, int64_t body_end) {
+    if (!fl || fiber_begin < 0 || fiber_end < fiber_begin || shell_begin < 0 || shell_end < shell_begin ||
+        body_begin < 0 || body_end < body_begin)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_target_ranges: bad ranges");
+    fl->rq_f0 = fiber_begin;
+    fl->rq_f1 = fiber_end;
+    fl->rq_s0 = shell_begin;
+    fl->rq_s1 = shell_end;
+    fl->rq_b0 = body_begin;
+    fl->rq_b1 = body_end;
+    fl->use_ranges = true;
+    fl->mv_dirty = true;
+    fl->ops_ready = false;
     fl->geom_version++;
     return SKB_OK;
 }
@@ -773,7 +809,7 @@ int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double *shell_
     if (n_all == 0)
         return SKB_OK;
     SKB_TRY(prepare_matvec_targets(fl));
-    const long long n_win = fl->w1 - fl->w0;
+    const long long n_win = fl->n_win;
     if (n_win == 0)
         return SKB_OK;
     std::vector<double> f, t;
@@ -793,8 +829,8 @@ int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double *shell_
         if (!f.empty()) std::memcpy(h_f, f.data(), f.size() * 8);
         if (!t.empty()) std::memcpy(h_t, t.data(), t.size() * 8);
         SKB_TRY(fl->vel.ensure((size_t)n_win * 24));
-        unsigned long long key = mix_key(fl->geom_version, (unsigned long long)fl->w0);
-        key = mix_key(key, (unsigned long long)fl->w1);
+        unsigned long long key = mix_key(fl->geom_version, (unsigned long long)fl->fa);
+        key = mix_key(key, (unsigned long long)fl->n_win);
         key = mix_key(key, dbl_bits(eta));
         key = mix_key(key, buffer_key(fl, 1));
         const size_t nfs = f.size();
@@ -850,7 +886,7 @@ int skb_flow_matvec_device(skb_flow *fl, const double *d_fib_forces, const doubl
     if (n_all == 0)
         return SKB_OK;
     SKB_TRY(prepare_matvec_targets(fl));
-    if (fl->w1 - fl->w0 > 0 && !d_v_window)
+    if (fl->n_win > 0 && !d_v_window)
         return set_error(SKB_ERR_INVALID, "skb_flow_matvec_device: NULL output");
     fl->cur = (cudaStream_t)stream;
     SKB_TRY(matvec_core(fl, d_fib_forces, d_shell_density, d_body_densities, d_body_forces, d_body_torques, eta,
@@ -881,8 +917,23 @@ int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *fo
                                  const double *length_prev, const int *plus_bc_velocity) {
     if (!fl)
         return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_operators: NULL flow");
-    const int nfib = fl->n_fibers;
     fl->ops_ready = false;
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    // the resident operators are those of the fibers whose rows are in this flow's target list: all of them, or the
+    // rank's own fibers under skb_flow_set_target_ranges / an aligned skb_flow_set_target_window
+    SKB_TRY(prepare_matvec_targets(fl));
+    int f0 = 0, f1 = 0;
+    if (fl->n_fibers > 0) {
+        const auto &off = fl->h_fiber_off;
+        f0 = (int)(std::lower_bound(off.begin(), off.end(), fl->fa) - off.begin());
+        f1 = (int)(std::lower_bound(off.begin(), off.end(), fl->fb) - off.begin());
+        if (off[(size_t)f0] != fl->fa || off[(size_t)f1] != fl->fb)
+            return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_operators: the target window [%lld, %lld) cuts a "
+                                              "fiber; use skb_flow_set_target_ranges (whole fibers)", fl->fa, fl->fb);
+    }
+    fl->op_f0 = f0;
+    fl->op_f1 = f1;
+    const int nfib = f1 - f0;
     if (nfib == 0) {
         fl->n_items_A = fl->n_items_F = 0;
         fl->ops_ready = true;
@@ -890,7 +941,6 @@ int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *fo
     }
     if (!A || !force_operator || !xs || !length_prev || !plus_bc_velocity)
         return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_operators: NULL argument");
-    CUDA_TRY(cudaSetDevice(fl->dev));
     // class matrices -> one device buffer, per-fiber offsets into it
     std::vector<double> h_class;
     std::map<int, std::pair<long long, long long>> class_off;
@@ -903,18 +953,19 @@ int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *fo
     std::vector<FiberGemvItem> itA, itF;
     long long offA = 0, offF = 0;
     int max_n = 0;
+    const long long node0 = fl->h_fiber_off[(size_t)f0]; // x / fw / v / res of the own fibers are indexed from here
     for (int f = 0; f < nfib; ++f) {
-        const int n = fl->h_fiber_n[f];
+        const int n = fl->h_fiber_n[(size_t)(f0 + f)];
         auto it = class_off.find(n);
         if (it == class_off.end())
             return set_error(SKB_ERR_INVALID, "fiber %d has %d nodes but skb_flow_set_fiber_class(%d, ...) was never "
-                                              "called", f, n, n);
+                                              "called", f0 + f, n, n);
         if (!(length_prev[f] > 0))
-            return set_error(SKB_ERR_INVALID, "fiber %d: length_prev = %g", f, length_prev[f]);
+            return set_error(SKB_ERR_INVALID, "fiber %d: length_prev = %g", f0 + f, length_prev[f]);
         cD[f] = it->second.first;
         cP[f] = it->second.second;
         max_n = std::max(max_n, n);
-        const long long node_off = fl->h_fiber_off[f];
+        const long long node_off = fl->h_fiber_off[(size_t)(f0 + f)] - node0;
         for (int r0 = 0; r0 < 4 * n; r0 += kFiberGemvRows)
             itA.push_back(FiberGemvItem{offA, 4 * node_off, 4 * node_off, 4 * n, 4 * n, r0, n});
         for (int r0 = 0; r0 < 3 * n; r0 += kFiberGemvRows)
@@ -935,7 +986,7 @@ int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *fo
     if (fl->fvel_smem > 48 * 1024)
         CUDA_TRY(cudaFuncSetAttribute(fiber_velocity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)fl->fvel_smem));
-    const long long nf = fl->n_fib;
+    const long long nf = fl->fb - fl->fa; // nodes of the own fibers
     auto put = [&](DevBuf &b, const void *h, size_t bytes) -> int {
         SKB_TRY(b.ensure(bytes));
         CUDA_TRY(cudaMemcpyAsync(b.ptr, h, bytes, cudaMemcpyHostToDevice, fl->stream));
@@ -989,8 +1040,8 @@ static int fiber_matvec_dev(skb_flow *fl, const double *d_x, const double *d_v, 
     fiber_gemv_kernel<0><<<fl->n_items_A, kFiberGemvThreads, fl->gemv_smem, fl->cur>>>(
         (const FiberGemvItem *)fl->items_A.ptr, (const double *)fl->op_A.ptr, d_x, d_res);
     CUDA_TRY(cudaGetLastError());
-    fiber_velocity_kernel<<<fl->n_fibers, 256, fl->fvel_smem, fl->cur>>>(
-        (const long long *)fl->fiber_offset.ptr, (const double *)fl->op_xs.ptr, d_v, (const double *)fl->op_len.ptr,
+    fiber_velocity_kernel<<<fl->op_f1 - fl->op_f0, 256, fl->fvel_smem, fl->cur>>>(
+        (const long long *)fl->fiber_offset.ptr + fl->op_f0, (const double *)fl->op_xs.ptr, d_v, (const double *)fl->op_len.ptr,
         (const int *)fl->op_plus.ptr, (const double *)fl->op_class.ptr, (const long long *)fl->op_classD.ptr,
         (const long long *)fl->op_classP.ptr, d_vb, d_res);
     CUDA_TRY(cudaGetLastError());
@@ -1005,7 +1056,7 @@ int skb_flow_apply_fiber_force(skb_flow *fl, const double *x_fibers, double *fw)
     if (!fl)
         return set_error(SKB_ERR_INVALID, "skb_flow_apply_fiber_force: NULL flow");
     SKB_TRY(need_ops(fl, "skb_flow_apply_fiber_force"));
-    const long long nf = fl->n_fib;
+    const long long nf = fl->fb - fl->fa; // nodes of the own fibers (all of them without a window)
     begin_stats(fl);
     if (nf == 0)
         return SKB_OK;
@@ -1029,7 +1080,7 @@ int skb_flow_fiber_matvec(skb_flow *fl, const double *x_fibers, const double *v_
     if (!fl)
         return set_error(SKB_ERR_INVALID, "skb_flow_fiber_matvec: NULL flow");
     SKB_TRY(need_ops(fl, "skb_flow_fiber_matvec"));
-    const long long nf = fl->n_fib;
+    const long long nf = fl->fb - fl->fa;
     begin_stats(fl);
     if (nf == 0)
         return SKB_OK;
@@ -1042,7 +1093,7 @@ int skb_flow_fiber_matvec(skb_flow *fl, const double *x_fibers, const double *v_
     SKB_TRY(fl->vel.ensure((size_t)nf * 24));
     CUDA_TRY(cudaMemcpyAsync(fl->vel.ptr, v_fibers, (size_t)nf * 24, cudaMemcpyHostToDevice, fl->stream));
     if (v_fib_boundary)
-        CUDA_TRY(cudaMemcpyAsync(fl->vb.ptr, v_fib_boundary, (size_t)fl->n_fibers * 56, cudaMemcpyHostToDevice,
+        CUDA_TRY(cudaMemcpyAsync(fl->vb.ptr, v_fib_boundary, (size_t)(fl->op_f1 - fl->op_f0) * 56, cudaMemcpyHostToDevice,
                                  fl->stream));
     CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
     SKB_TRY(fiber_matvec_dev(fl, (const double *)fl->x_fib.ptr, (const double *)fl->vel.ptr,
@@ -1051,6 +1102,43 @@ int skb_flow_fiber_matvec(skb_flow *fl, const double *x_fibers, const double *v_
     CUDA_TRY(cudaMemcpyAsync(res, fl->res_fib.ptr, (size_t)nf * 32, cudaMemcpyDeviceToHost, fl->stream));
     CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
     return finish_stats(fl);
+}
+
+int skb_flow_apply_fiber_force_device(skb_flow *fl, const double *d_x_fibers, double *d_fw, void *stream) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_fiber_force_device: NULL flow");
+    SKB_TRY(need_ops(fl, "skb_flow_apply_fiber_force_device"));
+    begin_stats(fl);
+    if (fl->n_items_F == 0)
+        return SKB_OK;
+    if (!d_x_fibers || !d_fw)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_fiber_force_device: NULL argument");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    fl->cur = (cudaStream_t)stream;
+    SKB_TRY(fiber_force_dev(fl, d_x_fibers, d_fw));
+    fl->stats.device_ms = fl->stats.total_ms = 0;
+    fl->stats.n_pairs = 0;
+    fl->stats.launches = fl->launches;
+    return SKB_OK;
+}
+
+int skb_flow_fiber_matvec_device(skb_flow *fl, const double *d_x_fibers, const double *d_v_fibers,
+                                 const double *d_v_fib_boundary, double *d_res, void *stream) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_fiber_matvec_device: NULL flow");
+    SKB_TRY(need_ops(fl, "skb_flow_fiber_matvec_device"));
+    begin_stats(fl);
+    if (fl->n_items_A == 0)
+        return SKB_OK;
+    if (!d_x_fibers || !d_v_fibers || !d_res)
+        return set_error(SKB_ERR_INVALID, "skb_flow_fiber_matvec_device: NULL argument");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    fl->cur = (cudaStream_t)stream;
+    SKB_TRY(fiber_matvec_dev(fl, d_x_fibers, d_v_fibers, d_v_fib_boundary, d_res));
+    fl->stats.device_ms = fl->stats.total_ms = 0;
+    fl->stats.n_pairs = 0;
+    fl->stats.launches = fl->launches;
+    return SKB_OK;
 }
 
 } // extern "C"
@@ -1072,9 +1160,9 @@ static int apply_matvec_impl(skb_flow *fl, skb_dense *dn, const double *x_fibers
     if (n_all == 0)
         return SKB_OK;
     SKB_TRY(prepare_matvec_targets(fl));
-    if (fl->w0 != 0 || fl->w1 != n_all)
-        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec needs the full target window (have [%lld, %lld) of "
-                                          "%lld)", fl->w0, fl->w1, n_all);
+    if (fl->n_win != n_all)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec needs the full target window (have %lld of %lld "
+                                          "rows); with one rank per GPU use the *_device calls", fl->n_win, n_all);
     std::vector<double> f, t;
     if (fl->n_bodies > 0)
         split_forces_torques(body_forces_torques, fl->n_bodies, f, t);
@@ -1083,7 +1171,7 @@ static int apply_matvec_impl(skb_flow *fl, skb_dense *dn, const double *x_fibers
     if (nf)
         CUDA_TRY(cudaMemcpyAsync(fl->x_fib.ptr, x_fibers, (size_t)nf * 32, cudaMemcpyHostToDevice, fl->stream));
     if (nf && fiber_link_conditions)
-        CUDA_TRY(cudaMemcpyAsync(fl->vb.ptr, fiber_link_conditions, (size_t)fl->n_fibers * 56,
+        CUDA_TRY(cudaMemcpyAsync(fl->vb.ptr, fiber_link_conditions, (size_t)(fl->op_f1 - fl->op_f0) * 56,
                                  cudaMemcpyHostToDevice, fl->stream));
     SKB_TRY(upload(fl, fl->in_shell, shell_density, (size_t)ns * 3));
     SKB_TRY(upload(fl, fl->in_body, body_densities, (size_t)nb * 3));

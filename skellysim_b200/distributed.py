@@ -66,3 +66,40 @@ def sym_block_pairs(n_blocks: int, part: int, n_parts: int):
         yield i, i
         for j in range(i + 1, n_blocks):
             yield i, j
+
+
+def reference_counts(n: int, world: int):
+    """Block sizes of the reference's MPI decompositions: n // world each, the first n % world ranks one more
+    (fibers: fiber_container_finite_difference.cpp:102-108; periphery nodes: periphery.cpp:387-400)."""
+    return [n // world + (1 if r < n % world else 0) for r in range(world)]
+
+
+def reference_rank_ranges(n_fibers: int, n_shell_nodes: int, n_body_nodes: int, rank: int, world: int):
+    """The rows of [fibers | shell | bodies] one MPI rank of the reference owns, as the six arguments of
+    skb_flow_set_target_ranges: whole fibers [f0, f1), periphery nodes [s0, s1), and all body nodes on rank 0
+    (body_container.cpp keeps the bodies on world_rank_ 0)."""
+    def block(n):
+        c = reference_counts(n, world)
+        b = sum(c[:rank])
+        return b, b + c[rank]
+    f0, f1 = block(n_fibers)
+    s0, s1 = block(n_shell_nodes)
+    b0, b1 = (0, n_body_nodes) if rank == 0 else (0, 0)
+    return f0, f1, s0, s1, b0, b1
+
+
+def allgatherv_rows(local, counts, group=None):
+    """All-gather of per-rank row blocks of unequal length (fw of the own fibers -> fw of all fibers): pads every
+    block to max(counts) rows, one all_gather_into_tensor, returns the concatenation without the padding.
+    `local` is a (counts[rank], d) tensor; NCCL on GPUs, gloo on CPU."""
+    import torch
+    import torch.distributed as dist
+    world = len(counts)
+    if world == 1 or not dist.is_initialized():
+        return local
+    m = max(counts)
+    pad = torch.zeros((m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    pad[:local.shape[0]] = local
+    out = torch.empty((world * m,) + tuple(local.shape[1:]), dtype=local.dtype, device=local.device)
+    dist.all_gather_into_tensor(out, pad, group=group)
+    return torch.cat([out[r * m:r * m + counts[r]] for r in range(world)])

@@ -127,3 +127,92 @@ def test_sym_row_owner_is_balanced_and_complete():
             assert len(seen) == nb * (nb + 1) // 2          # every unordered block pair exactly once
             if nb >= 8 * parts:
                 assert max(load) - min(load) <= 0.05 * max(load) + parts
+
+
+# ---- the reference's own rank decomposition (whole fibers | periphery nodes | bodies on rank 0) for the full
+# ---- apply_matvec with per-fiber operators: skb_flow_set_target_ranges + allgatherv of fw
+
+def _small_system(seed=3, n_fibers=5):
+    rng = np.random.default_rng(seed)
+    n_nodes = [int(n) for n in rng.choice([4, 6, 8], size=n_fibers)]
+    pos = []
+    for n in n_nodes:
+        x0, d = rng.uniform(-2, 2, 3), rng.normal(size=3)
+        pos.append(x0 + np.linspace(0, 1, n)[:, None] * d / np.linalg.norm(d))
+    fib = dict(pos=np.concatenate(pos), n_nodes=n_nodes, lengths=[1.0] * n_fibers)
+    d = rng.normal(size=(31, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    shell = dict(pos=6 * d, normals=-d, density=rng.normal(size=(31, 3)))
+    e = rng.normal(size=(10, 3))
+    e /= np.linalg.norm(e, axis=1)[:, None]
+    body = dict(pos=0.3 * e, normals=e, density=rng.normal(size=(10, 3)), centers=np.zeros((1, 3)),
+                forces=rng.normal(size=(1, 3)), torques=rng.normal(size=(1, 3)))
+    ops = dict(n_nodes=n_nodes, A=[], force=[], D_1_0={}, P={}, length_prev=[], plus=[])
+    xs = []
+    for n in n_nodes:
+        ops["A"].append(rng.normal(size=(4 * n, 4 * n)))
+        ops["force"].append(rng.normal(size=(3 * n, 4 * n)))
+        xs.append(rng.normal(size=(n, 3)))
+        ops["length_prev"].append(1.0)
+        ops["plus"].append(int(rng.integers(0, 2)))
+        ops["D_1_0"].setdefault(n, rng.normal(size=(n, n)))
+        ops["P"].setdefault(n, rng.normal(size=(4 * n - 14, 4 * n)))
+    ops["xs"] = np.concatenate(xs)
+    x = rng.normal(size=4 * sum(n_nodes))
+    link = rng.normal(size=(n_fibers, 7))
+    return fib, shell, body, ops, x, link
+
+
+def _rank_matvec_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import oracle as orc
+    from skellysim_b200.distributed import allgatherv_rows, reference_rank_ranges
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fib, shell, body, ops, x, link = _small_system()
+    n_nodes = ops["n_nodes"]
+    off = np.concatenate([[0], np.cumsum(n_nodes)])
+    nf, ns, nb = off[-1], shell["pos"].shape[0], body["pos"].shape[0]
+    ranges = [reference_rank_ranges(len(n_nodes), ns, nb, r, world) for r in range(world)]
+    f0, f1, s0, s1, b0, b1 = ranges[rank]
+    # own fibers: fw_own = force_operator_ * x_own, then the exchange the reference does inside fc.flow
+    x_own = x[4 * off[f0]:4 * off[f1]]
+    fw_own = orc.apply_fiber_force(ops["force"][f0:f1], x_own, n_nodes[f0:f1])
+    counts = [int(off[r[1]] - off[r[0]]) for r in ranges]
+    fw_all = allgatherv_rows(torch.from_numpy(fw_own), counts).numpy()
+    assert np.array_equal(fw_all, orc.apply_fiber_force(ops["force"], x, n_nodes))
+    # the rank's rows of v_all (every rank evaluates only its own targets; sliced from the full oracle result here)
+    v_all = orc.matvec_flow(dict(fib, forces=fw_all), shell, body, 0.9)
+    v_own = np.concatenate([v_all[off[f0]:off[f1]], v_all[nf + s0:nf + s1], v_all[nf + ns + b0:nf + ns + b1]])
+    own = dict(ops, n_nodes=n_nodes[f0:f1], A=ops["A"][f0:f1], xs=ops["xs"][off[f0]:off[f1]],
+               length_prev=ops["length_prev"][f0:f1], plus=ops["plus"][f0:f1])
+    res_own = orc.fiber_container_matvec(own, x_own, v_own[:off[f1] - off[f0]], link[f0:f1])
+    np.savez(os.path.join(out_dir, f"rank_{rank}.npz"), res=res_own, v=v_own, ranges=np.array(ranges[rank]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_reference_rank_decomposition_tiles_apply_matvec(tmp_path, world):
+    import oracle as orc
+    from skellysim_b200.distributed import reference_counts, reference_rank_ranges
+    assert reference_counts(7, 3) == [3, 2, 2] and reference_counts(2, 4) == [1, 1, 0, 0]
+    assert reference_rank_ranges(5, 31, 10, 0, 2) == (0, 3, 0, 16, 0, 10)
+    assert reference_rank_ranges(5, 31, 10, 1, 2) == (3, 5, 16, 31, 0, 0)
+    port = _free_port()
+    mp.spawn(_rank_matvec_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    fib, shell, body, ops, x, link = _small_system()
+    ref_res, ref_v = orc.apply_matvec_fibers(fib, shell, body, ops, x, 0.9, link)
+    nf, ns = fib["pos"].shape[0], shell["pos"].shape[0]
+    parts = [np.load(tmp_path / f"rank_{r}.npz") for r in range(world)]
+    assert np.array_equal(np.concatenate([p["res"] for p in parts]), ref_res)
+    # fiber, shell and body pieces of every rank tile v_all
+    off = np.concatenate([[0], np.cumsum(ops["n_nodes"])])
+    v_f, v_s, v_b = [], [], []
+    for p in parts:
+        f0, f1, s0, s1, b0, b1 = p["ranges"]
+        nfo, nso = off[f1] - off[f0], s1 - s0
+        v_f.append(p["v"][:nfo])
+        v_s.append(p["v"][nfo:nfo + nso])
+        v_b.append(p["v"][nfo + nso:])
+    assert np.array_equal(np.concatenate(v_f + v_s + v_b), ref_v)

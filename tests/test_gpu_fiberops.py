@@ -143,7 +143,13 @@ def test_operator_errors():
         with pytest.raises(skb.SkbError, match="set_fiber_operators"):
             fl.fiber_matvec(x, np.zeros((fib["pos"].shape[0], 3)))
         load_ops(fl, ops)
-        fl.set_target_window(0, 10)
+        # a window drops the resident operators (they belong to the fiber rows of the target list) ...
+        n0 = ops["n_nodes"][0]
+        fl.set_target_window(0, n0)
+        with pytest.raises(skb.SkbError, match="set_fiber_operators"):
+            fl.apply_matvec(x, shell["density"], body["density"], ft_of(body), 1.0)
+        # ... and the one-call host form needs every row
+        fl.set_fiber_operators(ops["A"][:1], ops["force"][:1], ops["xs"][:n0], ops["length_prev"][:1], ops["plus"][:1])
         with pytest.raises(skb.SkbError, match="full target window"):
             fl.apply_matvec(x, shell["density"], body["density"], ft_of(body), 1.0)
         with pytest.raises((skb.SkbError, ValueError)):
@@ -185,3 +191,92 @@ def test_apply_matvec_with_periphery_dense_operator():
     assert np.array_equal(res, res_d) and np.array_equal(v_b, v_b_d)
     assert np.array_equal(res_shell.reshape(-1), two_step)
     _check(res_shell.reshape(-1), orc.periphery_dense_apply(M, shell["density"].reshape(-1), v_s.reshape(-1)))
+
+
+# ---- one rank per GPU, simulated rank by rank on one device: the reference's MPI decomposition as target ranges ----
+
+def _own_ops(ops, off, f0, f1):
+    return dict(ops, n_nodes=ops["n_nodes"][f0:f1], A=ops["A"][f0:f1], force=ops["force"][f0:f1],
+                xs=ops["xs"][off[f0]:off[f1]], length_prev=ops["length_prev"][f0:f1], plus=ops["plus"][f0:f1])
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_target_ranges_rank_decomposition(world):
+    from skellysim_b200.distributed import reference_rank_ranges
+    fib, shell, body = make_system(28, 23, 500, 240, 2, nodes=(8, 16, 32))
+    ops = make_ops(fib, 13)
+    rng = np.random.default_rng(14)
+    n_nodes = ops["n_nodes"]
+    off = np.concatenate([[0], np.cumsum(n_nodes)])
+    nf, ns, nb = int(off[-1]), shell["pos"].shape[0], body["pos"].shape[0]
+    x = rng.normal(size=4 * nf)
+    link = rng.normal(size=(len(n_nodes), 7))
+    eta = 1.2
+    ref_res, ref_v = orc.apply_matvec_fibers(fib, shell, body, ops, x, eta, link)
+    ref_fw = orc.apply_fiber_force(ops["force"], x, n_nodes)
+    res_parts, v_f, v_s, v_b = [], [], [], []
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        for n in ops["D_1_0"]:
+            fl.set_fiber_class(n, ops["D_1_0"][n], ops["P"][n])
+        fw_parts = []
+        for rank in range(world):
+            f0, f1, s0, s1, b0, b1 = reference_rank_ranges(len(n_nodes), ns, nb, rank, world)
+            fl.set_target_ranges(f0, f1, s0, s1, b0, b1)
+            own = _own_ops(ops, off, f0, f1)
+            fl.set_fiber_operators(own["A"], own["force"], own["xs"], own["length_prev"], own["plus"])
+            fw_parts.append(fl.apply_fiber_force(x[4 * off[f0]:4 * off[f1]]))
+        fw_all = np.concatenate(fw_parts)            # the all-gather of the ranks
+        _check(fw_all, ref_fw)
+        for rank in range(world):
+            f0, f1, s0, s1, b0, b1 = reference_rank_ranges(len(n_nodes), ns, nb, rank, world)
+            fl.set_target_ranges(f0, f1, s0, s1, b0, b1)
+            own = _own_ops(ops, off, f0, f1)
+            fl.set_fiber_operators(own["A"], own["force"], own["xs"], own["length_prev"], own["plus"])
+            v_own = fl.matvec(fw_all, shell["density"], body["density"], ft_of(body), eta)
+            n_own = int(off[f1] - off[f0])
+            assert v_own.shape[0] == n_own + (s1 - s0) + (b1 - b0)
+            res_parts.append(fl.fiber_matvec(x[4 * off[f0]:4 * off[f1]], v_own[:n_own], link[f0:f1]))
+            v_f.append(v_own[:n_own])
+            v_s.append(v_own[n_own:n_own + s1 - s0])
+            v_b.append(v_own[n_own + s1 - s0:])
+            with pytest.raises(skb.SkbError, match="full target window"):
+                fl.apply_matvec(x, shell["density"], body["density"], ft_of(body), eta)
+    _check(np.concatenate(v_f + v_s + v_b), ref_v)
+    _check(np.concatenate(res_parts), ref_res)
+
+
+def test_fiber_operator_device_pointer_forms():
+    torch = pytest.importorskip("torch")
+    fib, shell, body = make_system(29, 19, 0, 0, 0, nodes=(8, 16, 17))
+    ops = make_ops(fib, 15)
+    rng = np.random.default_rng(16)
+    off = np.concatenate([[0], np.cumsum(ops["n_nodes"])])
+    f0, f1 = 4, 15
+    own = _own_ops(ops, off, f0, f1)
+    n_own = int(off[f1] - off[f0])
+    x, v, link = rng.normal(size=4 * n_own), rng.normal(size=(n_own, 3)), rng.normal(size=(f1 - f0, 7))
+    dev = torch.device("cuda:0")
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+    d_x, d_v, d_link = t(x), t(v), t(link)
+    d_fw = torch.empty((n_own, 3), dtype=torch.float64, device=dev)
+    d_res = torch.empty(4 * n_own, dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        for n in ops["D_1_0"]:
+            fl.set_fiber_class(n, ops["D_1_0"][n], ops["P"][n])
+        fl.set_target_ranges(f0, f1, 0, 0, 0, 0)
+        fl.set_fiber_operators(own["A"], own["force"], own["xs"], own["length_prev"], own["plus"])
+        fl.apply_fiber_force_device(d_x.data_ptr(), d_fw.data_ptr(), stream)
+        fl.fiber_matvec_device(d_x.data_ptr(), d_v.data_ptr(), d_link.data_ptr(), d_res.data_ptr(), stream)
+        torch.cuda.synchronize()
+        fw_h = fl.apply_fiber_force(x)
+        res_h = fl.fiber_matvec(x, v, link)
+        # a window that cuts a fiber cannot hold per-fiber operators
+        fl.set_target_window(3, int(off[-1]))
+        with pytest.raises(skb.SkbError, match="cuts a fiber"):
+            fl.set_fiber_operators(ops["A"], ops["force"], ops["xs"][3:], ops["length_prev"], ops["plus"])
+    assert np.array_equal(d_fw.cpu().numpy(), fw_h) and np.array_equal(d_res.cpu().numpy(), res_h)
+    _check(fw_h, orc.apply_fiber_force(own["force"], x, own["n_nodes"]))
+    _check(res_h, orc.fiber_container_matvec(own, x, v, link))
