@@ -411,7 +411,7 @@ def fiber_ops_leg(skb, hbm_peak_gbs, reps=10):
         fl.set_fiber_class(n, D, P)
         t0 = time.perf_counter()
         # (the binding lays every matrix out column-major, as Eigen's .data())
-        fl.set_fiber_operators(list(A), list(F), xs, lprev, plus)
+        fl.set_fiber_operators(A, F, xs, lprev, plus)
         set_ms = 1e3 * (time.perf_counter() - t0)
         _log("fiber ops: uploaded")
         res, v_s, v_b = fl.apply_matvec(x, g["sd"], g["bd"], ft, eta, link)
@@ -429,6 +429,12 @@ def fiber_ops_leg(skb, hbm_peak_gbs, reps=10):
             k_force.append(fl.stats()["device_ms"])
             fl.fiber_matvec(x, v_fib, link)
             k_mv.append(fl.stats()["device_ms"])
+        # fc.apply_preconditioner as a GEMV over explicit inverses (timing only: A itself stands in for A^-1)
+        fl.set_fiber_preconditioner(A)
+        k_pc = []
+        for _ in range(reps):
+            fl.apply_fiber_preconditioner(x)
+            k_pc.append(fl.stats()["device_ms"])
         # accuracy: sampled fibers against the oracle, the velocities taken from the (separately gated) flow matvec
         v_all = fl.matvec(fw, g["sd"], g["bd"], ft, eta)
     sel = rng.choice(n_fibers, 16, replace=False)
@@ -454,6 +460,8 @@ def fiber_ops_leg(skb, hbm_peak_gbs, reps=10):
             "apply_matvec_device_ms": float(np.median(dev)), "apply_matvec_e2e_ms": float(np.median(wall)),
             "launches": int(launches), "set_operators_ms": set_ms,
             "fiber_force_kernel_ms": float(np.median(k_force)), "fiber_matvec_kernels_ms": float(np.median(k_mv)),
+            "fiber_preconditioner_kernel_ms": float(np.median(k_pc)),
+            "fiber_preconditioner_GBs": A.nbytes / (float(np.median(k_pc)) * 1e-3) / 1e9,
             "operator_bytes": int(mat_bytes), "host_blas_gemv_ms": cpu_ms,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s",
                          "frac": gbs / hbm_peak_gbs},

@@ -123,6 +123,30 @@ template <class M> class FlowEngineT {
                                            plus_bc_velocity.data()),
               "skb_flow_set_fiber_operators");
     }
+    /// A_inv[f] points at the column-major 4n x 4n inverse of fiber f's A_ (e.g. MatrixXd(fib.A_LU_.inverse()).data())
+    void set_fiber_preconditioner(const std::vector<const double *> &A_inv) {
+        const size_t nf = st_->n_nodes.size();
+        if (A_inv.size() != nf)
+            throw std::runtime_error("skelly_b200: set_fiber_preconditioner needs one entry per fiber of set_fibers");
+        size_t na = 0;
+        for (int n : st_->n_nodes)
+            na += (size_t)16 * n * n;
+        std::vector<double> a(na);
+        size_t oa = 0;
+        for (size_t f = 0; f < nf; ++f) {
+            const size_t n = (size_t)st_->n_nodes[f];
+            std::copy(A_inv[f], A_inv[f] + 16 * n * n, a.begin() + oa);
+            oa += 16 * n * n;
+        }
+        check(skb_flow_set_fiber_preconditioner(st_->fl, a.data()), "skb_flow_set_fiber_preconditioner");
+    }
+    /// FiberContainerFiniteDifference::apply_preconditioner (fcfd.cpp:331-339): y = A_^-1 x per fiber
+    M apply_fiber_preconditioner(const M &x_fibers) const {
+        M y = M::Zero(4 * st_->n_fib, 1);
+        check(skb_flow_apply_fiber_preconditioner(st_->fl, x_fibers.data(), y.data()),
+              "skb_flow_apply_fiber_preconditioner");
+        return y;
+    }
     /// FiberContainerFiniteDifference::apply_fiber_force (fcfd.cpp:272-287): x_fibers (4 N_f) -> 3 x N_f
     M apply_fiber_force(const M &x_fibers) const {
         M fw = M::Zero(3, st_->n_fib);

@@ -133,6 +133,17 @@ SKB_API int skb_flow_apply_fiber_force_device(skb_flow *fl, const double *d_x_fi
 SKB_API int skb_flow_fiber_matvec_device(skb_flow *fl, const double *d_x_fibers, const double *d_v_fibers,
                                          const double *d_v_fib_boundary, double *d_res, void *stream);
 
+/* The fiber block of System::apply_preconditioner (system.cpp:248-262): FiberContainerFiniteDifference::
+ * apply_preconditioner (fcfd.cpp:331-339) is `A_LU_.solve(x)` per fiber; here the solve is a GEMV over the explicit
+ * inverse, `fib.A_LU_.inverse()` (column-major 4n x 4n per fiber, concatenated in the order of
+ * skb_flow_set_fiber_operators), uploaded once per timestep.  As a preconditioner it is a fixed linear operator, so
+ * GMRES is indifferent to the rounding difference between LU substitution and the inverse.  (The shell block is
+ * skb_dense_apply(SKB_DENSE_M_INV); bodies stay on the host.) */
+SKB_API int skb_flow_set_fiber_preconditioner(skb_flow *fl, const double *A_inv);
+SKB_API int skb_flow_apply_fiber_preconditioner(skb_flow *fl, const double *x_fibers, double *y);
+SKB_API int skb_flow_apply_fiber_preconditioner_device(skb_flow *fl, const double *d_x_fibers, double *d_y,
+                                                       void *stream);
+
 /* System::apply_matvec (system.cpp:269-324) with the fiber operators on the device:
  *   fw = apply_fiber_force(x_fibers); v_all = the fused flow of skb_flow_matvec;
  *   res_fibers = fc.matvec(x_fibers, v_fibers, fiber_link_conditions)

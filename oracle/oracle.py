@@ -326,6 +326,19 @@ def fiber_container_matvec(ops, x_fibers, v_fibers, v_fib_boundary=None):
     return res
 
 
+def fiber_apply_preconditioner(A_list, x_fibers, n_nodes):
+    """FiberContainerFiniteDifference::apply_preconditioner (fiber_container_finite_difference.cpp:331-339):
+    y_f = A_LU_.solve(x_f) per fiber, A_LU_ = PartialPivLU(A_) (fiber_finite_difference.cpp:340) -- LAPACK's
+    partial-pivoting solve here."""
+    x_fibers = np.asarray(x_fibers, dtype=np.float64).reshape(-1)
+    y = np.empty_like(x_fibers)
+    off = 0
+    for A, n in zip(A_list, n_nodes):
+        y[4 * off:4 * off + 4 * n] = np.linalg.solve(np.asarray(A), x_fibers[4 * off:4 * off + 4 * n])
+        off += n
+    return y
+
+
 def fiber_velocity_operator(D_1_0, P_downsample_bc, xs, length_prev, plus_bc_velocity):
     """The (4n x 3n) matrix V with fiber_matvec(...) == A x + V vec(v) + y_BC, vec(v) = AoS [v_0x v_0y v_0z v_1x ...].
     An independent assembly of ffd.cpp:280-309 used to cross-check fiber_matvec."""

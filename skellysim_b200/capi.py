@@ -116,6 +116,9 @@ def library() -> C.CDLL:
         "skb_flow_set_fiber_class": ([ctxp, C.c_int, _dp, _dp], C.c_int),
         "skb_flow_set_fiber_operators": ([ctxp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
         "skb_flow_apply_fiber_force": ([ctxp, _dp, _dp], C.c_int),
+        "skb_flow_set_fiber_preconditioner": ([ctxp, _dp], C.c_int),
+        "skb_flow_apply_fiber_preconditioner": ([ctxp, _dp, _dp], C.c_int),
+        "skb_flow_apply_fiber_preconditioner_device": ([ctxp, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "skb_flow_fiber_matvec": ([ctxp, _dp, _dp, _dp, _dp], C.c_int),
         "skb_flow_apply_matvec": ([ctxp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp], C.c_int),
         "skb_flow_apply_matvec_dense": ([ctxp, ctxp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp], C.c_int),
@@ -457,18 +460,43 @@ class Flow:
             raise ValueError(f"class matrices for n={n}: got {D.shape}, {P.shape}")
         _check(library().skb_flow_set_fiber_class(self._h, n, _p(D), _p(P)))
 
+    @staticmethod
+    def _colmajor_concat(mats):
+        """Per-fiber matrices -> one buffer, every matrix column-major (Eigen's .data()).  A 3-D C-ordered stack of
+        equal shapes is transposed in one pass; a list may be ragged."""
+        if isinstance(mats, np.ndarray) and mats.ndim == 3:
+            return np.ascontiguousarray(np.asarray(mats, dtype=np.float64).transpose(0, 2, 1)).reshape(-1)
+        if len(mats) == 0:
+            return np.zeros(0)
+        return np.concatenate([np.asarray(m, dtype=np.float64).ravel(order="F") for m in mats])
+
     def set_fiber_operators(self, A_list, force_list, xs, length_prev, plus_bc_velocity):
-        """A_ (4n,4n) and force_operator_ (3n,4n) per fiber, tangents xs (N_f,3), length_prev_, plus-end velocity BC."""
-        A = np.concatenate([np.asfortranarray(a, dtype=np.float64).ravel(order="F") for a in A_list]) \
-            if len(A_list) else np.zeros(0)
-        F = np.concatenate([np.asfortranarray(f, dtype=np.float64).ravel(order="F") for f in force_list]) \
-            if len(force_list) else np.zeros(0)
+        """A_ (4n,4n) and force_operator_ (3n,4n) per fiber (lists, or (n_fibers, rows, cols) stacks), tangents xs
+        (N_f,3), length_prev_, plus-end velocity BC -- of the OWN fibers when target ranges are set."""
+        A, F = self._colmajor_concat(A_list), self._colmajor_concat(force_list)
         xs = _arr(xs, 3)
         lp = np.ascontiguousarray(length_prev, dtype=np.float64)
         pl = np.ascontiguousarray(plus_bc_velocity, dtype=np.int32)
         assert xs.shape[0] == self._pieces()[0] and lp.shape == pl.shape == (len(A_list),)
         _check(library().skb_flow_set_fiber_operators(self._h, _p(A), _p(F), _p(xs), _p(lp),
                                                       pl.ctypes.data_as(C.POINTER(C.c_int))))
+
+    def set_fiber_preconditioner(self, A_inv_list):
+        """Explicit inverses of A_ (fib.A_LU_.inverse()), same fibers and order as set_fiber_operators."""
+        Ai = self._colmajor_concat(A_inv_list)
+        _check(library().skb_flow_set_fiber_preconditioner(self._h, _p(Ai)))
+
+    def apply_fiber_preconditioner(self, x_fibers):
+        """fc.apply_preconditioner (fcfd.cpp:331-339): y = A_^-1 x per (own) fiber."""
+        x = np.ascontiguousarray(x_fibers, dtype=np.float64).reshape(-1)
+        assert x.shape[0] == 4 * self._pieces()[0]
+        y = np.empty_like(x)
+        _check(library().skb_flow_apply_fiber_preconditioner(self._h, _p(x), _p(y)))
+        return y
+
+    def apply_fiber_preconditioner_device(self, d_x_fibers: int, d_y: int, stream: int = 0):
+        _check(library().skb_flow_apply_fiber_preconditioner_device(self._h, C.c_void_p(d_x_fibers), C.c_void_p(d_y),
+                                                                    C.c_void_p(stream)))
 
     def apply_fiber_force(self, x_fibers):
         """fc.apply_fiber_force (fcfd.cpp:272-287): (4 N_f,) -> fw (N_f, 3)."""

@@ -104,7 +104,9 @@ struct skb_flow {
     int n_items_A = 0, n_items_F = 0;
     size_t gemv_smem = 0, fvel_smem = 0;
     DevBuf op_A, op_F, op_xs, op_len, op_plus, op_class, op_classD, op_classP, items_A, items_F;
-    DevBuf x_fib, res_fib, vb, res_shell;
+    DevBuf x_fib, res_fib, vb, res_shell, op_Ainv;
+    long long op_A_elems = 0;               // elements of the concatenated A_ (and of A_^-1)
+    unsigned long long ops_gen = 0, precond_gen = 0; // the preconditioner belongs to one set of operators
     // staging
     DevBuf in_fib, in_shell, in_body, in_force, in_torque, vel, tmp;
     skb_flow_stats stats{};
@@ -379,7 +381,7 @@ int skb_flow_destroy(skb_flow *fl) {
     DevBuf *bufs[] = {&fl->fiber_offset, &fl->fiber_length, &fl->r_fib, &fl->r_shell, &fl->r_body, &fl->centers,
                       &fl->pt_pos, &fl->pt_force, &fl->pt_torque, &fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel, &fl->tmp,
                       &fl->op_A, &fl->op_F, &fl->op_xs, &fl->op_len, &fl->op_plus, &fl->op_class, &fl->op_classD,
-                      &fl->op_classP, &fl->items_A, &fl->items_F, &fl->x_fib, &fl->res_fib, &fl->vb, &fl->res_shell};
+                      &fl->op_classP, &fl->items_A, &fl->items_F, &fl->x_fib, &fl->res_fib, &fl->vb, &fl->res_shell, &fl->op_Ainv};
     for (DevBuf *b : bufs)
         b->release();
     fl->g_matvec.reset();
@@ -1008,7 +1010,28 @@ int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *fo
     CUDA_TRY(cudaStreamSynchronize(fl->stream)); // the host vectors above go out of scope
     fl->n_items_A = (int)itA.size();
     fl->n_items_F = (int)itF.size();
+    fl->op_A_elems = offA;
+    fl->ops_gen++;
     fl->ops_ready = true;
+    return SKB_OK;
+}
+
+int skb_flow_set_fiber_preconditioner(skb_flow *fl, const double *A_inv) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_preconditioner: NULL flow");
+    if (!fl->ops_ready)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_preconditioner: call skb_flow_set_fiber_operators "
+                                          "first (it defines the fibers and their order)");
+    if (fl->op_A_elems > 0) {
+        if (!A_inv)
+            return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_preconditioner: NULL argument");
+        CUDA_TRY(cudaSetDevice(fl->dev));
+        SKB_TRY(fl->op_Ainv.ensure((size_t)fl->op_A_elems * 8));
+        CUDA_TRY(cudaMemcpyAsync(fl->op_Ainv.ptr, A_inv, (size_t)fl->op_A_elems * 8, cudaMemcpyHostToDevice,
+                                 fl->stream));
+        CUDA_TRY(cudaStreamSynchronize(fl->stream));
+    }
+    fl->precond_gen = fl->ops_gen;
     return SKB_OK;
 }
 
@@ -1050,7 +1073,68 @@ static int fiber_matvec_dev(skb_flow *fl, const double *d_x, const double *d_v, 
     return SKB_OK;
 }
 
+// y = A_^-1 x per fiber: FiberContainerFiniteDifference::apply_preconditioner (fcfd.cpp:331-339) with the LU solve
+// replaced by a GEMV over the explicit inverse (same shapes and item list as A_); on fl->cur
+static int fiber_precond_dev(skb_flow *fl, const double *d_x, double *d_y) {
+    if (fl->n_items_A == 0)
+        return SKB_OK;
+    fiber_gemv_kernel<0><<<fl->n_items_A, kFiberGemvThreads, fl->gemv_smem, fl->cur>>>(
+        (const FiberGemvItem *)fl->items_A.ptr, (const double *)fl->op_Ainv.ptr, d_x, d_y);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    fl->launches += 1;
+    return SKB_OK;
+}
+
+static int need_precond(const skb_flow *fl, const char *who) {
+    SKB_TRY(need_ops(fl, who));
+    if (fl->precond_gen != fl->ops_gen)
+        return set_error(SKB_ERR_INVALID, "%s: call skb_flow_set_fiber_preconditioner after "
+                                          "skb_flow_set_fiber_operators first", who);
+    return SKB_OK;
+}
+
 extern "C" {
+
+int skb_flow_apply_fiber_preconditioner(skb_flow *fl, const double *x_fibers, double *y) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_fiber_preconditioner: NULL flow");
+    SKB_TRY(need_precond(fl, "skb_flow_apply_fiber_preconditioner"));
+    const long long nf = fl->fb - fl->fa;
+    begin_stats(fl);
+    if (nf == 0)
+        return SKB_OK;
+    if (!x_fibers || !y)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_fiber_preconditioner: NULL argument");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    fl->cur = fl->stream;
+    CUDA_TRY(cudaEventRecord(fl->evt0, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(fl->x_fib.ptr, x_fibers, (size_t)nf * 32, cudaMemcpyHostToDevice, fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
+    SKB_TRY(fiber_precond_dev(fl, (const double *)fl->x_fib.ptr, (double *)fl->res_fib.ptr));
+    CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
+    CUDA_TRY(cudaMemcpyAsync(y, fl->res_fib.ptr, (size_t)nf * 32, cudaMemcpyDeviceToHost, fl->stream));
+    CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
+    return finish_stats(fl);
+}
+
+int skb_flow_apply_fiber_preconditioner_device(skb_flow *fl, const double *d_x_fibers, double *d_y, void *stream) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_fiber_preconditioner_device: NULL flow");
+    SKB_TRY(need_precond(fl, "skb_flow_apply_fiber_preconditioner_device"));
+    begin_stats(fl);
+    if (fl->n_items_A == 0)
+        return SKB_OK;
+    if (!d_x_fibers || !d_y)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_fiber_preconditioner_device: NULL argument");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    fl->cur = (cudaStream_t)stream;
+    SKB_TRY(fiber_precond_dev(fl, d_x_fibers, d_y));
+    fl->stats.device_ms = fl->stats.total_ms = 0;
+    fl->stats.n_pairs = 0;
+    fl->stats.launches = fl->launches;
+    return SKB_OK;
+}
 
 int skb_flow_apply_fiber_force(skb_flow *fl, const double *x_fibers, double *fw) {
     if (!fl)

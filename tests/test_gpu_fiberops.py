@@ -280,3 +280,36 @@ def test_fiber_operator_device_pointer_forms():
     assert np.array_equal(d_fw.cpu().numpy(), fw_h) and np.array_equal(d_res.cpu().numpy(), res_h)
     _check(fw_h, orc.apply_fiber_force(own["force"], x, own["n_nodes"]))
     _check(res_h, orc.fiber_container_matvec(own, x, v, link))
+
+
+def test_fiber_preconditioner():
+    """fc.apply_preconditioner (fcfd.cpp:331-339): the per-fiber LU solve as a GEMV over the explicit inverse.
+    Well-conditioned A_ (I + small perturbation) so that inverse-vs-substitution rounding stays below the gate."""
+    fib, shell, body = make_system(30, 33, 0, 0, 0, nodes=NODES)
+    ops = make_ops(fib, 17)
+    rng = np.random.default_rng(18)
+    ops["A"] = [np.eye(4 * n) + 0.3 * rng.normal(size=(4 * n, 4 * n)) / np.sqrt(4 * n) for n in ops["n_nodes"]]
+    A_inv = [np.linalg.inv(a) for a in ops["A"]]
+    nf = fib["pos"].shape[0]
+    x = rng.normal(size=4 * nf)
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        for n in ops["D_1_0"]:
+            fl.set_fiber_class(n, ops["D_1_0"][n], ops["P"][n])
+        with pytest.raises(skb.SkbError, match="set_fiber_operators"):
+            fl.set_fiber_preconditioner(A_inv)
+        fl.set_fiber_operators(ops["A"], ops["force"], ops["xs"], ops["length_prev"], ops["plus"])
+        with pytest.raises(skb.SkbError, match="set_fiber_preconditioner"):
+            fl.apply_fiber_preconditioner(x)
+        fl.set_fiber_preconditioner(A_inv)
+        y = fl.apply_fiber_preconditioner(x)
+        assert fl.stats()["launches"] == 1
+        # P^-1 (A x) = x through the two device operators
+        ax = fl.fiber_matvec(x, np.zeros((nf, 3)))        # v = 0, no link conditions: res = A_ x
+        back = fl.apply_fiber_preconditioner(ax)
+        # new operators invalidate the preconditioner
+        fl.set_fiber_operators(ops["A"], ops["force"], ops["xs"], ops["length_prev"], ops["plus"])
+        with pytest.raises(skb.SkbError, match="set_fiber_preconditioner"):
+            fl.apply_fiber_preconditioner(x)
+    _check(y, orc.fiber_apply_preconditioner(ops["A"], x, ops["n_nodes"]), tol=1e-12)
+    _check(back, x, tol=1e-12)

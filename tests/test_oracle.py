@@ -231,3 +231,13 @@ def test_fiber_container_matvec_is_blockwise():
                                ops["length_prev"][i], ops["plus"][i], x[4 * off:4 * off + 4 * n], v[off:off + n], vb[i])
         assert np.array_equal(res[4 * off:4 * off + 4 * n], one)
         off += n
+
+
+def test_fiber_preconditioner_inverts_the_fiber_block():
+    # apply_preconditioner (fcfd.cpp:331-339) is the inverse of the x-part of fc.matvec (v = 0, no link conditions)
+    rng = np.random.default_rng(11)
+    n_nodes = [5, 8]
+    A = [np.eye(4 * n) + 0.2 * rng.normal(size=(4 * n, 4 * n)) for n in n_nodes]
+    x = rng.normal(size=4 * sum(n_nodes))
+    ax = np.concatenate([A[0] @ x[:20], A[1] @ x[20:]])
+    assert rel_max(orc.fiber_apply_preconditioner(A, ax, n_nodes), x) < 1e-12
