@@ -106,40 +106,75 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     const double scale = 2.0 / length_prev[f];
     const double *D = class_mats + class_D[f];
-    for (int j = threadIdx.x; j < n; j += blockDim.x) {
-        const double *col = D + (long long)j * n; // (D_1^T s)[j] = sum_i D_1(i, j) s_i
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
+    for (int j = warp; j < n; j += n_warps) { // one warp per entry: (D_1^T s)[j] = sum_i D_1(i, j) s_i, column j contiguous
+        const double *col = D + (long long)j * n;
         double acc = 0.0;
-        for (int i = 0; i < n; ++i)
+        for (int i = lane; i < n; i += 32)
             acc = fma(col[i], s[i], acc);
-        vT[3 * n + j] = scale * acc;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1)
+            acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0)
+            vT[3 * n + j] = scale * acc;
     }
     __syncthreads();
-    const int bc = 4 * n - 14;
+    // -(P vT): row r of P_downsample_bc by thread lr of column slice sl; S slices when the rows leave threads idle
+    const int bc = 4 * n - 14, n4 = 4 * n;
     const double *P = class_mats + class_P[f];
-    for (int r = threadIdx.x; r < 4 * n; r += blockDim.x) {
-        double val = 0.0;
-        if (r < bc) {
+    const int rp32 = (bc + 31) & ~31;
+    const int S = 2 * rp32 <= (int)blockDim.x ? (int)blockDim.x / rp32 : 1; // column slices per row
+    const int rp = S == 1 ? (int)blockDim.x : rp32;                         // threads per slice
+    const int sl = threadIdx.x / rp, lr = threadIdx.x - sl * rp;
+    double *part = fv_smem + 5 * n;                        // S x rp <= blockDim.x partial sums
+    double *out = res + 4 * off;
+    if (S == 1) {
+        for (int r = lr; r < bc; r += rp) {
             const double *p = P + r;
             double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            int j = 0;
-            for (; j + 3 < 4 * n; j += 4) {
+            for (int j = 0; j + 3 < n4; j += 4) {
                 a0 = fma(p[(long long)j * bc], vT[j], a0);
                 a1 = fma(p[(long long)(j + 1) * bc], vT[j + 1], a1);
                 a2 = fma(p[(long long)(j + 2) * bc], vT[j + 2], a2);
                 a3 = fma(p[(long long)(j + 3) * bc], vT[j + 3], a3);
             }
-            val = -((a0 + a1) + (a2 + a3));
-        } else {
-            if (r == bc + 3)
-                val += v[0] * xs[0] + v[1] * xs[1] + v[2] * xs[2];
-            if (v_boundary && r < bc + 7)
-                val += v_boundary[7 * (long long)f + (r - bc)];
-            if (r == bc + 10 && plus_velocity[f]) {
-                const int e = 3 * (n - 1);
-                val += v[e] * xs[e] + v[e + 1] * xs[e + 1] + v[e + 2] * xs[e + 2];
-            }
+            out[r] -= (a0 + a1) + (a2 + a3);
         }
-        res[4 * off + r] += val;
+    } else {
+        double a0 = 0.0, a1 = 0.0;
+        if (sl < S && lr < bc) {
+            const double *p = P + lr;
+            int j = sl;
+            for (; j + S < n4; j += 2 * S) {
+                a0 = fma(p[(long long)j * bc], vT[j], a0);
+                a1 = fma(p[(long long)(j + S) * bc], vT[j + S], a1);
+            }
+            if (j < n4)
+                a0 = fma(p[(long long)j * bc], vT[j], a0);
+        }
+        if (sl < S)
+            part[sl * rp + lr] = a0 + a1;
+        __syncthreads();
+        if (sl == 0 && lr < bc) {
+            double sum = part[lr];
+            for (int u = 1; u < S; ++u)
+                sum += part[u * rp + lr];
+            out[lr] -= sum;
+        }
+    }
+    // the 14 boundary rows: xs_vT and y_BC
+    if (threadIdx.x < 14) {
+        const int t = threadIdx.x;
+        double val = 0.0;
+        if (t == 3)
+            val += v[0] * xs[0] + v[1] * xs[1] + v[2] * xs[2];
+        if (v_boundary && t < 7)
+            val += v_boundary[7 * (long long)f + t];
+        if (t == 10 && plus_velocity[f]) {
+            const int e = 3 * (n - 1);
+            val += v[e] * xs[e] + v[e + 1] * xs[e + 1] + v[e + 2] * xs[e + 2];
+        }
+        out[bc + t] += val;
     }
 }
 

@@ -976,7 +976,7 @@ int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *fo
         offF += 12LL * n * n;
     }
     fl->gemv_smem = ((size_t)((4 * max_n + 1) & ~1) + kFiberGemvThreads) * sizeof(double);
-    fl->fvel_smem = (size_t)5 * max_n * sizeof(double);
+    fl->fvel_smem = ((size_t)5 * max_n + 256) * sizeof(double); // vT, s, column-slice partials
     if (fl->gemv_smem > 200 * 1024)
         return set_error(SKB_ERR_INVALID, "fiber with %d nodes exceeds the shared-memory fiber operator kernels", max_n);
     if (fl->gemv_smem > 48 * 1024) {
