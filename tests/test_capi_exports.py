@@ -67,3 +67,43 @@ def test_product_never_imports_oracle():
                     if re.search(r"\boracle\b", txt):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_null_handles_are_refused_before_any_cuda_call():
+    # argument errors come back as codes with a message (never a crash), GPU or not
+    L = capi.library()
+    null = C.c_void_p()
+    calls = [
+        lambda: L.skb_flow_set_fiber_class(null, 8, None, None),
+        lambda: L.skb_flow_set_fiber_operators(null, None, None, None, None, None),
+        lambda: L.skb_flow_set_fiber_preconditioner(null, None),
+        lambda: L.skb_flow_apply_fiber_force(null, None, None),
+        lambda: L.skb_flow_fiber_matvec(null, None, None, None, None),
+        lambda: L.skb_flow_apply_fiber_preconditioner(null, None, None),
+        lambda: L.skb_flow_apply_matvec(null, None, None, None, None, None, 1.0, None, None, None),
+        lambda: L.skb_flow_apply_matvec_dense(null, null, None, None, None, None, None, 1.0, None, None, None),
+        lambda: L.skb_flow_set_target_ranges(null, 0, 0, 0, 0, 0, 0),
+        lambda: L.skb_flow_apply_fiber_force_device(null, None, None, None),
+        lambda: L.skb_flow_fiber_matvec_device(null, None, None, None, None, None),
+        lambda: L.skb_dense_apply_device(null, 0, None, None, None, None),
+    ]
+    for call in calls:
+        assert call() != 0
+        assert len(L.skb_last_error_string()) > 0
+
+
+def test_flow_piece_bookkeeping_of_the_binding():
+    # capi.Flow._pieces mirrors prepare_matvec_targets (skb_matvec.cu): window and range modes
+    f = capi.Flow.__new__(capi.Flow)
+    f._h = None
+    f.n_fib, f.n_shell, f.n_body = 100, 50, 20
+    f._fiber_off = np.array([0, 10, 30, 60, 100])
+    assert f._pieces() == (100, 50, 20)
+    f._window, f._ranges = (5, 120), None
+    assert f._pieces() == (95, 20, 0)
+    f._window = (110, -1)
+    assert f._pieces() == (0, 40, 20)
+    f._ranges, f._window = (1, 3, 10, 20, 0, 20), None
+    assert f._pieces() == (50, 10, 20)
+    f._ranges = (2, 9, 40, 90, 5, 5)
+    assert f._pieces() == (70, 10, 0)
