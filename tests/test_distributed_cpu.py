@@ -216,3 +216,92 @@ def test_reference_rank_decomposition_tiles_apply_matvec(tmp_path, world):
         v_s.append(p["v"][nfo:nfo + nso])
         v_b.append(p["v"][nfo + nso:])
     assert np.array_equal(np.concatenate(v_f + v_s + v_b), ref_v)
+
+
+# ---- RankApplyMatvec: the sequencing + collectives of one rank's apply_matvec, with a stand-in for capi.Flow whose
+# ---- *_device methods read/write the same raw addresses but compute with the CPU oracle (no GPU here)
+
+class _FakeFlow:
+    def __init__(self, fib, shell, body, ops, ranges):
+        import ctypes
+        self.C, self.fib, self.shell, self.body, self.ops = ctypes, fib, shell, body, ops
+        self.off = np.concatenate([[0], np.cumsum(ops["n_nodes"])])
+        self.f0, self.f1, self.s0, self.s1, self.b0, self.b1 = ranges
+        self.calls = []
+
+    def _view(self, ptr, n):
+        return np.ctypeslib.as_array((self.C.c_double * n).from_address(ptr))
+
+    def _own(self):
+        o, f0, f1 = self.ops, self.f0, self.f1
+        return dict(o, n_nodes=o["n_nodes"][f0:f1], A=o["A"][f0:f1], force=o["force"][f0:f1],
+                    xs=o["xs"][self.off[f0]:self.off[f1]], length_prev=o["length_prev"][f0:f1], plus=o["plus"][f0:f1])
+
+    def apply_fiber_force_device(self, px, pfw, stream):
+        import oracle as orc
+        own = self._own()
+        n = int(self.off[self.f1] - self.off[self.f0])
+        self._view(pfw, 3 * n)[:] = orc.apply_fiber_force(own["force"], self._view(px, 4 * n), own["n_nodes"]).reshape(-1)
+        self.calls.append("force")
+
+    def matvec_device(self, pff, psd, pbd, pf, pt, eta, pv, stream):
+        import oracle as orc
+        nf, ns, nb = int(self.off[-1]), self.shell["pos"].shape[0], self.body["pos"].shape[0]
+        fib = dict(self.fib, forces=self._view(pff, 3 * nf).reshape(nf, 3).copy())
+        shell = dict(self.shell, density=self._view(psd, 3 * ns).reshape(ns, 3).copy())
+        body = dict(self.body, density=self._view(pbd, 3 * nb).reshape(nb, 3).copy(),
+                    forces=self._view(pf, 3).reshape(1, 3).copy(), torques=self._view(pt, 3).reshape(1, 3).copy())
+        v = orc.matvec_flow(fib, shell, body, eta)
+        a, b = self.off[self.f0], self.off[self.f1]
+        own = np.concatenate([v[a:b], v[nf + self.s0:nf + self.s1], v[nf + ns + self.b0:nf + ns + self.b1]])
+        self._view(pv, own.size)[:] = own.reshape(-1)
+        self.calls.append("flow")
+
+    def fiber_matvec_device(self, px, pv, plink, pres, stream):
+        import oracle as orc
+        own = self._own()
+        n = int(self.off[self.f1] - self.off[self.f0])
+        link = self._view(plink, 7 * (self.f1 - self.f0)).reshape(-1, 7) if plink else None
+        self._view(pres, 4 * n)[:] = orc.fiber_container_matvec(own, self._view(px, 4 * n),
+                                                                self._view(pv, 3 * n).reshape(n, 3), link)
+        self.calls.append("fiber_matvec")
+
+
+def _rank_apply_worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    from skellysim_b200.distributed import RankApplyMatvec
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    fib, shell, body, ops, x, link = _small_system()
+    ns, nb = shell["pos"].shape[0], body["pos"].shape[0]
+    ram = RankApplyMatvec(None, ops["n_nodes"], ns, nb, 1, rank, world)
+    ram.flow = _FakeFlow(fib, shell, body, ops, ram.ranges)
+    off = np.concatenate([[0], np.cumsum(ops["n_nodes"])])
+    f0, f1, s0, s1, b0, b1 = ram.ranges
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64))
+    x_own = t(x[4 * off[f0]:4 * off[f1]])
+    xs_own = t(shell["density"][s0:s1])
+    # only rank 0 knows the body unknowns; the others pass receive buffers
+    z = lambda a: t(a) if rank == 0 else torch.zeros(a.shape, dtype=torch.float64)
+    bd, bf, bt = z(body["density"]), z(body["forces"]), z(body["torques"])
+    link_own = t(link[f0:f1])
+    for _ in range(2):  # twice: the preallocated buffers are reused
+        res, v_s, v_b = ram.apply(x_own, xs_own, bd, bf, bt, link_own, 0.9)
+    assert ram.flow.calls[-3:] == ["force", "flow", "fiber_matvec"]
+    np.savez(os.path.join(out_dir, f"ram_{rank}.npz"), res=res.numpy(), v_s=v_s.numpy(), v_b=v_b.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_rank_apply_matvec_sequencing_and_collectives(tmp_path, world):
+    import oracle as orc
+    port = _free_port()
+    mp.spawn(_rank_apply_worker, args=(world, port, str(tmp_path)), nprocs=world, join=True)
+    fib, shell, body, ops, x, link = _small_system()
+    ref_res, ref_v = orc.apply_matvec_fibers(fib, shell, body, ops, x, 0.9, link)
+    nf, ns = fib["pos"].shape[0], shell["pos"].shape[0]
+    parts = [np.load(tmp_path / f"ram_{r}.npz") for r in range(world)]
+    assert np.array_equal(np.concatenate([p["res"] for p in parts]), ref_res)
+    assert np.array_equal(np.concatenate([p["v_s"] for p in parts]), ref_v[nf:nf + ns])
+    assert np.array_equal(np.concatenate([p["v_b"] for p in parts]), ref_v[nf + ns:])
