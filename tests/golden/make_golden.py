@@ -107,7 +107,42 @@ def main():
               f"({os.path.getsize(out)} B)")
 
 
+def regularised():
+    """Second fixture: the regularised branch (0 < r < epsilon_distance = 1e-5 -> r := sqrt(r^2 + reg^2), reg = 5e-3) of
+    the helpers the flow layer uses next to the big sums -- `oseen_kernel_source_target_numba` (:271-321, the same rule
+    as kernels::oseen_tensor_contract_direct, kernels.cpp:146-195, for every r > 0), `rotlet_kernel_source_target_numba`
+    (:335-384 == kernels::rotlet, kernels.cpp:206-242, including r == 0) and the self form
+    `oseen_kernel_times_density_numba` (:196-268, diagonal skipped like `dr2 == 0 -> continue` in the C++)."""
+    K = load_ref()
+    rng = np.random.default_rng(11)
+    src = straight_fibers(rng, 2, 16, 1.0, 1.0)
+    n = src.shape[0]
+    dirs = rng.normal(size=(n, 3))
+    dirs /= np.linalg.norm(dirs, axis=1)[:, None]
+    # one target per source at a controlled distance: inside the regularised ball, just outside, far
+    dist = np.concatenate([np.full(10, 3e-6), np.full(6, 8e-6), np.full(6, 1.5e-5), np.full(n - 22, 2e-2)])
+    trg = src + dirs * dist[:, None]
+    # rotlet only: two targets exactly ON sources (contribution 0 in both implementations)
+    trg_rot = np.concatenate([trg, src[:2]])
+    f, t = rng.uniform(-1, 1, (n, 3)), rng.uniform(-1, 1, (n, 3))
+    eta = 0.8
+    u_oseen = K.oseen_kernel_source_target_numba(src.ravel(), trg.ravel(), f.ravel(), eta=eta).reshape(-1, 3)
+    u_rot = K.rotlet_kernel_source_target_numba(src.ravel(), trg_rot.ravel(), t.ravel(), eta=eta).reshape(-1, 3)
+    # self form: a fiber whose nodes 3/4 and 9/10 are closer than epsilon_distance
+    x = straight_fibers(rng, 1, 12, 1.0, 0.5)
+    x[4] = x[3] + 4e-6 * dirs[0]
+    x[10] = x[9] + 9e-6 * dirs[1]
+    fs = rng.uniform(-1, 1, x.shape)
+    u_self = K.oseen_kernel_times_density_numba(x.ravel(), fs.ravel(), eta=eta).reshape(-1, 3)
+    out = os.path.join(HERE, "ref_numba_regularised.npz")
+    np.savez_compressed(out, r_src=src, r_trg=trg, r_trg_rotlet=trg_rot, f=f, torque=t, eta=eta, u_oseen=u_oseen,
+                        u_rotlet=u_rot, x_self=x, f_self=fs, u_self=u_self, dist=dist)
+    print(f"regularised: {n} sources, {int((dist < 1e-5).sum())} pairs inside the regularised ball -> "
+          f"{os.path.basename(out)} ({os.path.getsize(out)} B)")
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         sys.exit("reference tree not present: golden vectors can only be regenerated in the build container")
     main()
+    regularised()

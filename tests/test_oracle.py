@@ -241,3 +241,23 @@ def test_fiber_preconditioner_inverts_the_fiber_block():
     x = rng.normal(size=4 * sum(n_nodes))
     ax = np.concatenate([A[0] @ x[:20], A[1] @ x[20:]])
     assert rel_max(orc.fiber_apply_preconditioner(A, ax, n_nodes), x) < 1e-12
+
+
+def test_regularised_helpers_match_reference_numba_golden(golden_cases):
+    # the r <= epsilon_distance branch of kernels::oseen_tensor_contract_direct (kernels.cpp:146-195) and
+    # kernels::rotlet (kernels.cpp:206-242) -- the fiber self term, the body rotlet and the point sources go through
+    # it -- pinned on outputs of the reference's numba kernels (tests/golden/make_golden.py::regularised)
+    g = golden_cases["regularised"]
+    eta = float(g["eta"])
+    assert int((g["dist"] < 1e-5).sum()) == 16
+    u = orc.oseen_contract(g["r_src"], g["r_trg"], g["f"], eta)
+    assert rel_max(u, g["u_oseen"]) < 1e-13
+    # the regularised pairs dominate their targets: without the branch the result is off by orders of magnitude
+    plain = orc.stokeslet_direct(g["r_src"], g["f"], g["r_trg"]) / eta
+    assert rel_max(plain[:16], g["u_oseen"][:16]) > 10.0
+    assert rel_max(plain[22:], g["u_oseen"][22:]) < 1e-12      # far targets: identical to the plain Stokeslet sum
+    ur = orc.rotlet(g["r_src"], g["r_trg_rotlet"], g["torque"], eta)
+    assert rel_max(ur, g["u_rotlet"]) < 1e-13
+    # self form: diagonal skipped, close neighbours regularised
+    us = orc.oseen_contract(g["x_self"], g["x_self"], g["f_self"], eta)
+    assert rel_max(us, g["u_self"]) < 1e-13
