@@ -141,8 +141,34 @@ def regularised():
           f"{os.path.basename(out)} ({os.path.getsize(out)} B)")
 
 
+def shell_double_layer():
+    """Third fixture: the periphery's double layer as the reference's precompute builds it --
+    `stresslet_kernel_times_normal_numba` (:535-590), the matrix precompute.py:113 starts
+    `stresslet_plus_complementary` from -- contracted with a density.  Its off-diagonal blocks are the kernel
+    Periphery::flow evaluates (periphery.cpp:55-79: f_dl = 2 eta n (x) rho, stresslet, / eta), so
+    S @ density == Periphery::flow at the shell's own nodes with the r = 0 pairs skipped; this pins the normal /
+    density index convention and the -3/(4 pi) normalisation on a second, independent reference function."""
+    K = load_ref()
+    rng = np.random.default_rng(21)
+    n = 60
+    d = rng.normal(size=(n, 3))
+    d /= np.linalg.norm(d, axis=1)[:, None]
+    nodes = d * np.array([3.0, 2.0, 2.0])
+    normals = -d / np.array([3.0, 2.0, 2.0])
+    normals /= np.linalg.norm(normals, axis=1)[:, None]     # inward normals of the ellipsoid
+    density = rng.uniform(-1, 1, (n, 3))
+    S = K.stresslet_kernel_times_normal_numba(nodes.ravel(), normals.ravel(), eta=1.0)
+    u = (S @ density.ravel()).reshape(n, 3)
+    out = os.path.join(HERE, "ref_numba_shell_double_layer.npz")
+    np.savez_compressed(out, nodes=nodes, normals=normals, density=density, u=u,
+                        S_block_0_1=S[0:3, 3:6], S_diag_max=np.abs(np.stack([S[3 * i:3 * i + 3, 3 * i:3 * i + 3]
+                                                                            for i in range(n)])).max())
+    print(f"shell_double_layer: {n} nodes -> {os.path.basename(out)} ({os.path.getsize(out)} B)")
+
+
 if __name__ == "__main__":
     if not os.path.exists(REF):
         sys.exit("reference tree not present: golden vectors can only be regenerated in the build container")
     main()
     regularised()
+    shell_double_layer()

@@ -261,3 +261,17 @@ def test_regularised_helpers_match_reference_numba_golden(golden_cases):
     # self form: diagonal skipped, close neighbours regularised
     us = orc.oseen_contract(g["x_self"], g["x_self"], g["f_self"], eta)
     assert rel_max(us, g["u_self"]) < 1e-13
+
+
+def test_periphery_flow_matches_reference_precompute_matrix(golden_cases):
+    # stresslet_kernel_times_normal_numba (the matrix precompute.py:113 starts from) @ density == Periphery::flow
+    # (periphery.cpp:55-79) at the shell's own nodes, r = 0 pairs skipped; independent of eta (2 eta / eta)
+    g = golden_cases["shell_double_layer"]
+    assert float(g["S_diag_max"]) == 0.0                 # "Set to zero diagonal terms" -- the r = 0 rule
+    for eta in (1.0, 1.7):
+        u = orc.periphery_flow(g["nodes"], g["nodes"], g["normals"], g["density"], eta)
+        assert rel_max(u, g["u"]) < 1e-13
+    # one 3 x 3 block by hand: S_01 = -3/(4 pi) (r . n_1) r r^T / r^5, r = x_0 - x_1 (source normal)
+    r = g["nodes"][0] - g["nodes"][1]
+    blk = -3.0 / (4.0 * np.pi) * (r @ g["normals"][1]) / np.linalg.norm(r) ** 5 * np.outer(r, r)
+    assert np.allclose(blk, g["S_block_0_1"], rtol=1e-13, atol=0)
