@@ -152,9 +152,11 @@ SKB_API int skb_ctx_last_eval_was_symmetric(const skb_ctx *ctx, int *yes);
 SKB_API int skb_plan_query(int kind, int64_t n_trg, int64_t n_src, int num_sms, const int *occupancy4, int force_T,
                            int force_S, int *T, int *n_splits, int *tiles_per_split, int *grid_x);
 /* Work items of the symmetric kernel for `n_blocks` node blocks and the rows owned by `part` of `n_parts`:
- * items4[4*i..] = (I, J0, J1, slot) in launch order (at most max_items are written), row_begin[n_blocks + 1]. */
+ * items4[4*i..] = (I, g0, g1, slot) in launch order (at most max_items are written): block I meets the 32-node groups
+ * [g0, g1), all of them beyond block I (a block is skb_sym_groups_per_block() groups); row_begin[n_blocks + 1]. */
 SKB_API int skb_sym_plan_query(int n_blocks, int part, int n_parts, int num_sms, int max_items, int *items4,
                                int *n_items, int *row_begin);
+SKB_API int skb_sym_groups_per_block(void);
 
 /* Pure DFMA micro-benchmark on the context's first device: returns achieved FP64 FMA/s * 2 (flop/s).
  * SURVEY.md section 8d asks for the measured FP64 roofline denominator next to the datasheet value. */

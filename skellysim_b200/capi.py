@@ -93,6 +93,7 @@ def library() -> C.CDLL:
                            + [C.POINTER(C.c_int)] * 4, C.c_int),
         "skb_sym_plan_query": ([C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int),
                                 C.POINTER(C.c_int)], C.c_int),
+        "skb_sym_groups_per_block": ([], C.c_int),
         "skb_ctx_set_sym_partition": ([ctxp, C.c_int, C.c_int], C.c_int),
         "skb_ctx_last_eval_was_symmetric": ([ctxp, C.POINTER(C.c_int)], C.c_int),
         # include/skelly_b200_flow.h
@@ -619,8 +620,13 @@ def plan_query(kind, n_trg, n_src, num_sms=148, occupancy=(8, 6, 4, 2), force_T=
     return {"T": T.value, "n_splits": S.value, "tiles_per_split": per.value, "grid_x": gx.value}
 
 
+def sym_groups_per_block() -> int:
+    return int(library().skb_sym_groups_per_block())
+
+
 def sym_plan_query(n_blocks, part=0, n_parts=1, num_sms=148):
-    """Host-side work list of the symmetric kernel (no GPU needed): list of (I, J0, J1, slot), row_begin."""
+    """Host-side work list of the symmetric kernel (no GPU needed): list of (I, g0, g1, slot), row_begin; block I
+    meets the 32-node groups [g0, g1) (sym_groups_per_block() groups per block)."""
     n = C.c_int()
     _check(library().skb_sym_plan_query(int(n_blocks), int(part), int(n_parts), int(num_sms), 0, None, C.byref(n),
                                         None))

@@ -40,12 +40,15 @@ constexpr double kEps = 1e-5;
 struct TargetCache {
     std::vector<double> host;
     bool valid = false;
+    unsigned long long version = 0; // bumped by every upload: part of the CUDA-graph key (a replay bakes in whether
+                                    // the symmetric path -- targets start with the sources -- was taken)
     bool same(const double *r, long long n) const {
         return valid && (long long)host.size() == 3 * n && (n == 0 || std::memcmp(host.data(), r, (size_t)n * 24) == 0);
     }
     void store(const double *r, long long n) {
         host.assign(r, r + 3 * n);
         valid = true;
+        ++version;
     }
 };
 } // namespace
@@ -677,6 +680,10 @@ int skb_flow_velocity_at_targets(skb_flow *fl, const double *r_trg, int64_t n_tr
         unsigned long long key = mix_key(fl->geom_version, (unsigned long long)n_trg);
         key = mix_key(key, dbl_bits(eta));
         key = mix_key(key, buffer_key(fl, 0));
+        // same count but different targets: the captured sequence assumed the old targets' relation to the sources
+        key = mix_key(key, fl->tc_fib.version);
+        key = mix_key(key, fl->tc_shell.version);
+        key = mix_key(key, fl->tc_body.version);
         SKB_TRY(run_graphed(fl, fl->g_vat, key, [&]() { return body(h_ff, h_sd, h_bd, h_f, h_t, h_v); }));
         CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
         CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));

@@ -412,8 +412,8 @@ int skb_sym_plan_query(int n_blocks, int part, int n_parts, int num_sms, int max
     if (items4)
         for (int i = 0; i < (int)order.size() && i < max_items; ++i) {
             items4[4 * i + 0] = order[i].I;
-            items4[4 * i + 1] = order[i].J0;
-            items4[4 * i + 2] = order[i].J1;
+            items4[4 * i + 1] = order[i].g0;
+            items4[4 * i + 2] = order[i].g1;
             items4[4 * i + 3] = order[i].slot;
         }
     if (row_begin)
@@ -421,6 +421,8 @@ int skb_sym_plan_query(int n_blocks, int part, int n_parts, int num_sms, int max
             row_begin[b] = rb[b];
     return SKB_OK;
 }
+
+int skb_sym_groups_per_block(void) { return kSymGroupsPerBlock; }
 
 int skb_ctx_last_eval_was_symmetric(const skb_ctx *ctx, int *yes) {
     if (!ctx || !yes)
@@ -524,8 +526,8 @@ static int update_layout(skb_ctx *ctx) {
     const long long P = (long long)ctx->devs.size();
     const long long n_trg = ctx->n_trg;
     const long long n_sl = ctx->devs[0].src[SKB_STOKESLET].n, n_dl = ctx->devs[0].src[SKB_STRESSLET].n;
-    const long long block = (long long)kSymThreads * 4;
-    bool want = ctx->sym_mode != 0 && n_dl <= 0 && n_sl >= (ctx->sym_mode == 1 ? 2 : 8) * block && n_trg >= n_sl &&
+    const long long block = (long long)kSymThreads * kSymT;
+    bool want = ctx->sym_mode != 0 && n_dl <= 0 && n_sl >= (ctx->sym_mode == 1 ? 2 * block : 4096) && n_trg >= n_sl &&
                 (long long)ctx->h_src[SKB_STOKESLET].size() == 3 * n_sl &&
                 std::memcmp(ctx->h_trg.data(), ctx->h_src[SKB_STOKESLET].data(), (size_t)n_sl * 24) == 0;
     if (want) {
@@ -694,55 +696,91 @@ static int sym_owned_rows(int nb, int part, int parts) {
     return n;
 }
 
-// Work items of the symmetric kernel: (I, [J0,J1)) over the strict upper triangle of nb blocks, restricted to the block
-// rows owned by `part`; rows are cut into near-equal chunks sized for ~6 waves of resident CTAs.  `order` is the launch
-// order (large items first); item.slot is its row-major position, row_begin[b]..row_begin[b+1] the slots of row b.
+// Work items of the symmetric kernel: (I, groups [g0, g1)) over the strict upper triangle of nb blocks, restricted to
+// the block rows owned by `part`.  Units are 32-node groups (kSymGroupsPerBlock per block).  Guided sizes: most of the
+// work goes out in large items (about a quarter of a CTA slot's share each), the last ~30 % in items a quarter of that
+// size and the last ~8 % in single stages (4 groups = 17 us of one CTA slot), so that all CTA slots drain together: the
+// hardware hands the next item to whichever slot frees up first, in `order` (large items first).  item.slot is the
+// item's row-major position, row_begin[b]..row_begin[b+1] the slots of row b (their forward partials are summed in
+// that order by sym_reduce_kernel).
 void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymItem> &order,
                      std::vector<int> &row_begin) {
-    const int occ = 3;
-    const long long pairs = (long long)nb * (nb - 1) / 2 / std::max(parts, 1);
+    const int gpb = kSymGroupsPerBlock, sg = kSymStageGroups;
+    const int occ = kSymMinB;
+    auto env_int = [](const char *name, int dflt) {
+        const char *e = getenv(name);
+        return e && atoi(e) > 0 ? atoi(e) : dflt;
+    };
+    static const int waves = env_int("SKB_SYM_WAVES", 4);      // large items per CTA slot (if all work were large items)
+    static const int pct_mid = env_int("SKB_SYM_PCT_MID", 30);  // last x % of the work: quarter-size items
+    static const int pct_fine = env_int("SKB_SYM_PCT_FINE", 8); // last x % of the work: single stages
+    long long work = 0; // groups x blocks owned by this part
+    for (int I = 0; I < nb; ++I)
+        if (sym_row_owner(I, parts) == part)
+            work += (long long)gpb * (nb - 1 - I);
     const long long slots = (long long)num_sms * occ;
-    static const int waves = [] {
-        const char *e = getenv("SKB_SYM_WAVES"); // tuning knob: target number of CTA waves (finer items, smaller tail)
-        return e && atoi(e) > 0 ? atoi(e) : 6;
-    }();
-    const long long chunk = std::max<long long>(1, pairs / (slots * waves));
-    std::vector<SymItem> items;
-    row_begin.assign(nb + 1, 0);
+    long long big = work / std::max<long long>(1, slots * waves);
+    big = std::max<long long>(sg, std::min<long long>(big / sg * sg, 1024LL * sg));
+    const long long mid = std::max<long long>(sg, big / 4 / sg * sg);
+    struct Piece {
+        int I, g0, g1, prow;
+    };
+    std::vector<Piece> pieces;
     int prow = 0;
     for (int I = 0; I < nb; ++I) {
-        row_begin[I] = (int)items.size();
-        const int len = nb - 1 - I;
         if (sym_row_owner(I, parts) != part)
             continue;
         const int my_prow = prow++; // every owned row has a P row, in increasing I (sym_reduce_kernel counts the same way)
+        const int first = gpb * (I + 1), len = gpb * (nb - 1 - I);
         if (len <= 0)
             continue;
-        const int n_chunks = (int)((len + chunk - 1) / chunk);
-        for (int c = 0; c < n_chunks; ++c) {
-            SymItem it;
-            it.I = I;
-            it.J0 = I + 1 + (int)((long long)len * c / n_chunks);
-            it.J1 = I + 1 + (int)((long long)len * (c + 1) / n_chunks);
-            it.slot = (int)items.size();
-            it.prow = my_prow;
-            it.pad = 0;
-            items.push_back(it);
+        const int n_chunks = (int)((len + big - 1) / big);
+        for (int c = 0; c < n_chunks; ++c) { // near-equal chunks, cut at stage boundaries
+            const int a = (int)((long long)(len / sg) * c / n_chunks) * sg;
+            const int b = c + 1 == n_chunks ? len : (int)((long long)(len / sg) * (c + 1) / n_chunks) * sg;
+            if (b > a)
+                pieces.push_back(Piece{I, first + a, first + b, my_prow});
         }
     }
-    row_begin[nb] = (int)items.size();
+    // the tail of the launch order is cut finer
+    std::stable_sort(pieces.begin(), pieces.end(),
+                     [](const Piece &x, const Piece &y) { return (x.g1 - x.g0) > (y.g1 - y.g0); });
+    std::vector<Piece> fine;
+    long long done = 0;
+    // (at most ~6 items of a tier per CTA slot: more would only add forward-partial slabs)
+    const long long fine_work = std::min<long long>(work * pct_fine / 100, slots * 6 * sg);
+    const long long mid_work = std::min<long long>(work * pct_mid / 100, fine_work + slots * 6 * mid);
+    for (const Piece &pc : pieces) {
+        const long long len = pc.g1 - pc.g0;
+        const long long left = work - done;
+        const long long unit = left <= fine_work ? sg : left <= mid_work ? mid : len;
+        for (long long g = pc.g0; g < pc.g1; g += unit)
+            fine.push_back(Piece{pc.I, (int)g, (int)std::min<long long>(pc.g1, g + unit), pc.prow});
+        done += len;
+    }
+    // slots: row-major
+    std::sort(fine.begin(), fine.end(),
+              [](const Piece &x, const Piece &y) { return x.I != y.I ? x.I < y.I : x.g0 < y.g0; });
+    std::vector<SymItem> items(fine.size());
+    row_begin.assign(nb + 1, 0);
+    for (size_t i = 0; i < fine.size(); ++i) {
+        items[i] = SymItem{fine[i].I, fine[i].g0, fine[i].g1, (int)i, fine[i].prow, 0};
+        row_begin[fine[i].I + 1] = (int)i + 1;
+    }
+    for (int b = 0; b < nb; ++b) // rows without items inherit the running count
+        row_begin[b + 1] = std::max(row_begin[b + 1], row_begin[b]);
     order = items;
     std::stable_sort(order.begin(), order.end(),
-                     [](const SymItem &a, const SymItem &b) { return (a.J1 - a.J0) > (b.J1 - b.J0); });
+                     [](const SymItem &x, const SymItem &y) { return (x.g1 - x.g0) > (y.g1 - y.g0); });
 }
 
 // Decide whether the symmetric path applies and make sure its plan / buffers exist.
 static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) {
     *use = 0;
     SourceSet &s = d.src[SKB_STOKESLET];
-    const int T = 4;
+    const int T = kSymT;
     const long long block = (long long)kSymThreads * T;
-    if (s.n < 8 * block && ctx->sym_mode != 1)
+    if (s.n < 4096 && ctx->sym_mode != 1)
         return SKB_OK; // too small to matter
     if (s.n < 2 * block || d.n_trg < s.n)
         return SKB_OK;
@@ -775,6 +813,11 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
         if (s.sym_P.ensure((size_t)sym_owned_rows((int)nb, d.sym_part, d.sym_parts) * (size_t)s.n_pad * 24) !=
             SKB_OK) { // not enough free memory for the reverse partials: the plain kernel serves this geometry
             (void)cudaGetLastError();
+            if (ctx->sym_layout) // every device holds ALL leading targets there and the caller reduce-scatters the
+                                 // partial sums: a silent switch to the plain kernel would count them P times
+                return set_error(SKB_ERR_ALLOC, "symmetric multi-device layout: no memory for the reverse partials "
+                                                "(%zu bytes); free memory or skb_ctx_set_symmetric(ctx, 0)",
+                                 (size_t)sym_owned_rows((int)nb, d.sym_part, d.sym_parts) * (size_t)s.n_pad * 24);
             s.self_state = 0;
             return SKB_OK;
         }
@@ -813,7 +856,7 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
     cudaError_t e = cudaSuccess;
     CUDA_TRY(cudaEventRecord(d.ev_fork2, st)); // strengths are packed: the diagonal blocks may start from here
     if (s.sym_items > 0) {
-        e = launch_sym<4, 3>(a, s.sym_items, st);
+        e = launch_sym<kSymT, kSymMinB>(a, s.sym_items, st);
         if (e != cudaSuccess)
             return set_error(SKB_ERR_CUDA, "pair_sym_kernel launch failed: %s", cudaGetErrorString(e));
         count_launch(1);
@@ -949,6 +992,12 @@ static int eval_host(skb_ctx *ctx, int kind, StrengthMode mode, const double *f_
     if (mode == kNormalDensity && n_src > 0 && !ctx->devs[0].src[kind].has_normals)
         return set_error(SKB_ERR_STATE, "eval_double_layer: skb_set_source_normals has not been called");
     SKB_TRY(update_layout(ctx));
+    if (n_src == 0) { // an empty class contributes nothing, whatever layout the devices hold the targets in
+        if (!accumulate && ctx->n_trg > 0)
+            std::memset(u_trg, 0, (size_t)ctx->n_trg * 24);
+        ctx->stats = skb_eval_stats{};
+        return SKB_OK;
+    }
     const bool sym_layout = ctx->sym_layout && kind == SKB_STOKESLET; // (no stresslet sources exist in that layout)
     const long long n_self = sym_layout ? ctx->n_self : 0;
     const int fdim = (kind == SKB_STOKESLET || mode == kNormalDensity) ? 3 : 9;

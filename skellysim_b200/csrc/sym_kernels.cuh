@@ -4,27 +4,50 @@
 // System::apply_matvec (r_all starts with the fiber nodes, src/core/system.cpp:284-299) -- the Oseen tensor is
 // symmetric in the pair: G(x_i - x_j) = G(x_j - x_i).  d, r^2, 1/r and 1/r^2 (12 of the 22 FP64 instructions of a
 // pair) can then serve both directions: 32 instructions per pair-of-pairs instead of 44, and under the measured
-// register-file read model (profiles/r1_fp64_ubench.md) 82 instead of 107 FP64-pipe cycles.
+// register-file read model (profiles/r1_fp64_ubench.md) ~76 instead of 98 FP64-pipe cycles.
 //
-// Layout of the work: nodes are cut into blocks of kSymThreads*T; a work item is (target block I, source blocks
-// [J0, J1)), all J > I (strict upper triangle; the block diagonal and the non-square remainder go through
-// pair_sum_kernel).  Each thread keeps T nodes of I in registers: position, strength and the forward accumulators
-// (u_I += G f_J), for the whole item.  The J block is staged in shared memory by TMA; within a warp the 32 lanes walk
-// a group of 32 J-nodes as a ring: at step s lane l meets node (l + s) mod 32, and that node's reverse accumulator
+// Layout of the work: nodes are cut into blocks of kSymThreads*T (the "I side": each thread keeps T nodes in registers:
+// position, strength and the forward accumulators u_I += G f_J) and into GROUPS of 32 nodes (the "J side").  A work
+// item is (block I, groups [g0, g1)), all groups beyond block I (strict upper triangle; the block diagonal and the
+// non-square remainder go through pair_sum_kernel).  Items are as fine as one group (512*T/4 x 32 pairs), so the
+// planner can hand out large items first and small ones last (build_sym_items): the kernel's tail -- and the tail of
+// every rank's share under multi-GPU sharding -- is a few tens of microseconds, not one block pair (0.27 ms).
+// J groups are staged in shared memory by TMA, up to 4 groups per stage in a 4-stage ring; within a warp the 32 lanes
+// walk a group as a ring: at step s lane l meets node (l + s) mod 32, and that node's reverse accumulator
 // (u_J += G f_I) travels with it from lane to lane by one warp shuffle per step, so after 32 steps it is back home
-// holding the sum over the warp's 32*T targets -- no cross-lane reduction tree.  The four warps visit the 16 groups in a
-// staggered order and add their sums into one shared-memory slab in a fixed order (bitwise reproducible); the slab is
-// the (I -> J) reverse partial written once to P[I][J-nodes].  The final combination is a fixed-order sum.
+// holding the sum over the warp's 32*T targets -- no cross-lane reduction tree.  Each warp parks its sums in its own
+// shared-memory slab; once per stage the four slabs are added in a fixed order (bitwise reproducible) and written to
+// the reverse partial P[row(I)][J nodes].  The final combination (sym_reduce_kernel) is a fixed-order sum.
 #pragma once
 #include "pair_kernels.cuh"
 
 namespace skb {
 
+#ifndef SKB_SYM_T
+#define SKB_SYM_T 4 // nodes of the I block per thread (tuning knob; profiles/r2_sym_variants.md)
+#endif
+#ifndef SKB_SYM_MINB
+#define SKB_SYM_MINB 3 // resident CTAs per SM asked of ptxas (register cap 65536 / (128 * MINB))
+#endif
+#ifndef SKB_SYM_UNROLL
+#define SKB_SYM_UNROLL 1 // ring steps unrolled
+#endif
+#ifndef SKB_SYM_PREFETCH
+#define SKB_SYM_PREFETCH 0 // 1: the next step's record is loaded from shared memory before this step's chain
+#endif
 constexpr int kSymThreads = 128;
-constexpr int kSymStages = 2;
+constexpr int kSymT = SKB_SYM_T;
+constexpr int kSymMinB = SKB_SYM_MINB;
+constexpr int kSymUnroll = SKB_SYM_UNROLL;
+constexpr int kSymStages = 4;       // TMA ring depth
+constexpr int kSymPrefetch = 2;     // stages in flight ahead of the one being consumed
+constexpr int kSymGroup = 32;       // nodes per J group (one ring)
+constexpr int kSymStageGroups = 4;  // groups per stage
+constexpr int kSymStageNodes = kSymGroup * kSymStageGroups;
+constexpr int kSymGroupsPerBlock = kSymThreads * kSymT / kSymGroup;
 
 struct SymItem {
-    int I, J0, J1, slot; // target block, source blocks [J0, J1) (all > I), forward-partial slab index
+    int I, g0, g1, slot; // I block, J groups [g0, g1) (all beyond block I), forward-partial slab index
     int prow, pad;       // row of P this item writes: index of I among the block rows owned by this part
 };
 
@@ -40,9 +63,10 @@ struct SymArgs {
 
 template <int T> struct SymSmem {
     static constexpr int block = kSymThreads * T;
-    static constexpr int stage_bytes = block * 48; // positions + strengths of one J block
-    static constexpr int rev_bytes = block * 24;
-    static constexpr int bar_offset = kSymStages * stage_bytes + rev_bytes;
+    static constexpr int stage_bytes = kSymStageNodes * 48; // positions + strengths of one stage
+    static constexpr int slab_doubles = kSymStageNodes * 3; // one warp's reverse sums of one stage
+    static constexpr int slabs_bytes = 2 * (kSymThreads / 32) * slab_doubles * 8; // double-buffered
+    static constexpr int bar_offset = kSymStages * stage_bytes + slabs_bytes;
     static constexpr int total_bytes = bar_offset + 2 * kSymStages * 8;
 };
 
@@ -143,33 +167,38 @@ template <int T, int MINB>
 __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymArgs a) {
     using L = SymSmem<T>;
     constexpr int kBlock = L::block;
-    constexpr int kGroups = kBlock / 32;
+    constexpr int kWarps = kSymThreads / 32;
     extern __shared__ __align__(128) unsigned char smem[];
-    double *rev = reinterpret_cast<double *>(smem + kSymStages * L::stage_bytes);
+    double *slabs = reinterpret_cast<double *>(smem + kSymStages * L::stage_bytes);
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::bar_offset);
     uint64_t *empty_bar = full_bar + kSymStages;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const SymItem item = a.items[blockIdx.x];
-    const int nJ = item.J1 - item.J0;
+    const int n_groups = item.g1 - item.g0;
+    const int n_stages = (n_groups + kSymStageGroups - 1) / kSymStageGroups;
 
-    auto issue_block = [&](int k) { // k-th J block of the item -> ring slot k % kSymStages
+    auto issue_stage = [&](int k) { // k-th stage of the item -> ring slot k % kSymStages
         const int s = k % kSymStages;
         unsigned char *dst = smem + s * L::stage_bytes;
-        const size_t off = (size_t)(item.J0 + k) * kBlock * 24;
-        mbar_arrive_expect_tx(&full_bar[s], L::stage_bytes);
-        tma_bulk_g2s(dst, reinterpret_cast<const char *>(a.r) + off, kBlock * 24, &full_bar[s]);
-        tma_bulk_g2s(dst + kBlock * 24, reinterpret_cast<const char *>(a.f) + off, kBlock * 24, &full_bar[s]);
+        const int g = item.g0 + k * kSymStageGroups;
+        const int ng = (item.g1 - g) < kSymStageGroups ? (item.g1 - g) : kSymStageGroups;
+        const uint32_t bytes = (uint32_t)ng * kSymGroup * 24;
+        const size_t off = (size_t)g * kSymGroup * 24;
+        mbar_arrive_expect_tx(&full_bar[s], 2 * bytes);
+        tma_bulk_g2s(dst, reinterpret_cast<const char *>(a.r) + off, bytes, &full_bar[s]);
+        tma_bulk_g2s(dst + kSymStageNodes * 24, reinterpret_cast<const char *>(a.f) + off, bytes, &full_bar[s]);
     };
 
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < kSymStages; ++s) {
             mbar_init(&full_bar[s], 1);
-            mbar_init(&empty_bar[s], kSymThreads / 32);
+            mbar_init(&empty_bar[s], kWarps);
         }
         mbar_fence_init();
-        issue_block(0);
+        for (int k = 0; k < kSymPrefetch && k < n_stages; ++k)
+            issue_stage(k);
     }
     // this thread's T nodes of block I: position, strength, forward accumulators
     double tx[T], ty[T], tz[T], hx[T], hy[T], hz[T], ufx[T], ufy[T], ufz[T];
@@ -180,34 +209,68 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
         hx[t] = __ldg(a.f + 3 * i + 0), hy[t] = __ldg(a.f + 3 * i + 1), hz[t] = __ldg(a.f + 3 * i + 2);
         ufx[t] = ufy[t] = ufz[t] = 0.0;
     }
-    __syncthreads();
+    __syncthreads(); // barrier init visible
 
-    for (int k = 0; k < nJ; ++k) {
+    for (int k = 0; k < n_stages; ++k) {
         const int s = k % kSymStages;
-        if (tid == 0 && k + 1 < nJ) { // prefetch the next J block into the other slot
-            if (k + 1 >= kSymStages)
-                mbar_wait(&empty_bar[(k + 1) % kSymStages], (((k + 1) / kSymStages) - 1) & 1);
-            issue_block(k + 1);
+        if (tid == 0 && k + kSymPrefetch < n_stages) {
+            const int kn = k + kSymPrefetch;
+            if (kn >= kSymStages)
+                mbar_wait(&empty_bar[kn % kSymStages], ((kn / kSymStages) - 1) & 1);
+            issue_stage(kn);
         }
-        for (int i = tid; i < kBlock * 3; i += kSymThreads)
-            rev[i] = 0.0;
+        const int g_first = item.g0 + k * kSymStageGroups;
+        const int ng = (item.g1 - g_first) < kSymStageGroups ? (item.g1 - g_first) : kSymStageGroups;
         mbar_wait(&full_bar[s], (k / kSymStages) & 1);
-        __syncthreads();
         const double *ps = reinterpret_cast<const double *>(smem + s * L::stage_bytes);
-        const double *fs = ps + kBlock * 3;
+        const double *fs = ps + kSymStageNodes * 3;
+        double *slab_set = slabs + (k & 1) * kWarps * L::slab_doubles; // double-buffered: one barrier per stage
+        double *my_slab = slab_set + warp * L::slab_doubles;
 #pragma unroll 1
-        for (int it = 0; it < kGroups; ++it) {
-            // staggered so the 4 warps are always on 4 different groups; every warp visits every group once
-            const int g = (it + warp * (kGroups / 4)) % kGroups;
-            const int base = g * 32;
+        for (int gi = 0; gi < ng; ++gi) {
+            const int base = gi * kSymGroup;
             double urx = 0.0, ury = 0.0, urz = 0.0;
-#pragma unroll 1
+#if SKB_SYM_PREFETCH
+            double nrx, nry, nrz, ngx, ngy, ngz;
+            {
+                const int idx = base + lane;
+                nrx = ps[3 * idx + 0], nry = ps[3 * idx + 1], nrz = ps[3 * idx + 2];
+                ngx = fs[3 * idx + 0], ngy = fs[3 * idx + 1], ngz = fs[3 * idx + 2];
+            }
+#endif
+            _Pragma("unroll kSymUnroll")
             for (int st = 0; st < 32; ++st) {
+#if SKB_SYM_PREFETCH
+                const double rx = nrx, ry = nry, rz = nrz, gx = ngx, gy = ngy, gz = ngz;
+                {
+                    const int idx = base + ((lane + st + 1) & 31); // (the 33rd load re-reads the first record: harmless)
+                    nrx = ps[3 * idx + 0], nry = ps[3 * idx + 1], nrz = ps[3 * idx + 2];
+                    ngx = fs[3 * idx + 0], ngy = fs[3 * idx + 1], ngz = fs[3 * idx + 2];
+                }
+#else
                 const int idx = base + ((lane + st) & 31);
                 // per-lane record from shared memory: 24 B stride is bank-conflict free for 64-bit loads
                 const double rx = ps[3 * idx + 0], ry = ps[3 * idx + 1], rz = ps[3 * idx + 2];
                 const double gx = fs[3 * idx + 0], gy = fs[3 * idx + 1], gz = fs[3 * idx + 2];
-                stokeslet_pairpairs<T>(tx, ty, tz, hx, hy, hz, rx, ry, rz, gx, gy, gz, ufx, ufy, ufz, urx, ury, urz);
+#endif
+                if constexpr (T <= 4) {
+                    stokeslet_pairpairs<T>(tx, ty, tz, hx, hy, hz, rx, ry, rz, gx, gy, gz, ufx, ufy, ufz, urx, ury, urz);
+                } else { // chains in groups of 4: bounds the live temporaries
+#pragma unroll
+                    for (int g0 = 0; g0 < T; g0 += 4) {
+                        double ax[4], ay[4], az[4], bx[4], by[4], bz[4], cx[4], cy[4], cz[4];
+#pragma unroll
+                        for (int c = 0; c < 4; ++c) {
+                            ax[c] = tx[g0 + c], ay[c] = ty[g0 + c], az[c] = tz[g0 + c];
+                            bx[c] = hx[g0 + c], by[c] = hy[g0 + c], bz[c] = hz[g0 + c];
+                            cx[c] = ufx[g0 + c], cy[c] = ufy[g0 + c], cz[c] = ufz[g0 + c];
+                        }
+                        stokeslet_pairpairs<4>(ax, ay, az, bx, by, bz, rx, ry, rz, gx, gy, gz, cx, cy, cz, urx, ury, urz);
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            ufx[g0 + c] = cx[c], ufy[g0 + c] = cy[c], ufz[g0 + c] = cz[c];
+                    }
+                }
                 // the record moves to lane - 1 for the next step; its accumulator goes with it
                 const int from = (lane + 1) & 31;
                 urx = __shfl_sync(0xffffffffu, urx, from);
@@ -215,18 +278,24 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
                 urz = __shfl_sync(0xffffffffu, urz, from);
             }
             // after 32 steps lane l holds the finished sum of node base + l over this warp's 32*T targets
-            rev[3 * (base + lane) + 0] += urx;
-            rev[3 * (base + lane) + 1] += ury;
-            rev[3 * (base + lane) + 2] += urz;
-            __syncthreads(); // fixed order of the 4 warps' additions per group -> reproducible
+            my_slab[3 * (base + lane) + 0] = urx;
+            my_slab[3 * (base + lane) + 1] = ury;
+            my_slab[3 * (base + lane) + 2] = urz;
         }
-        // reverse partial of (I -> block J0+k): one coalesced write
-        double *out = a.P + ((size_t)item.prow * a.n_pad + (size_t)(item.J0 + k) * kBlock) * 3;
-        for (int i = tid; i < kBlock * 3; i += kSymThreads)
-            out[i] = rev[i];
-        __syncthreads();
+        __syncwarp();
         if (lane == 0)
-            mbar_arrive(&empty_bar[s]);
+            mbar_arrive(&empty_bar[s]); // this warp is done reading the stage
+        __syncthreads();                // all four slabs of this stage are complete
+        // reverse partial of (I -> these groups): the four warps' sums in a fixed order, one coalesced write.
+        // (the next stage's sums go to the other slab set; this set is rewritten only after the next barrier)
+        double *out = a.P + ((size_t)item.prow * a.n_pad + (size_t)g_first * kSymGroup) * 3;
+        for (int i = tid; i < ng * kSymGroup * 3; i += kSymThreads) {
+            double v = slab_set[i];
+#pragma unroll
+            for (int w = 1; w < kWarps; ++w)
+                v += slab_set[w * L::slab_doubles + i];
+            out[i] = v;
+        }
     }
     double *fo = a.F + (size_t)item.slot * kBlock * 3;
 #pragma unroll

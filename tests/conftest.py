@@ -25,7 +25,15 @@ def _has_gpu():
 
 def pytest_collection_modifyitems(config, items):
     # `-m gpu` on a box without a GPU must fail loudly, not skip: a silent skip would read as green.
-    pass
+    # A plain `pytest` (no -m) on a box without a GPU skips the gpu-marked tests instead of failing them.
+    if "gpu" in (config.getoption("-m") or ""):
+        return
+    if _has_gpu():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device (run `pytest -m gpu` on the GPU box; that invocation never skips)")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
 
 
 @pytest.fixture(scope="session")

@@ -36,32 +36,54 @@ def test_forced_tuning_is_honoured():
     assert p["T"] == 2 and p["n_splits"] == 5
 
 
-@pytest.mark.parametrize("nb", [2, 3, 63, 178, 188])
+@pytest.mark.parametrize("nb", [2, 3, 63, 178, 188, 1954])
 @pytest.mark.parametrize("parts", [1, 2, 8])
 def test_symmetric_work_list_covers_the_upper_triangle_exactly_once(nb, parts):
-    seen = set()
+    gpb = capi.sym_groups_per_block()
+    covered = {}   # block row -> sorted list of group ranges
     for part in range(parts):
         items, row_begin = capi.sym_plan_query(nb, part, parts)
         slots = sorted(it[3] for it in items)
         assert slots == list(range(len(items)))                    # forward-partial slabs: a permutation
         assert row_begin[0] == 0 and row_begin[-1] == len(items)
-        sizes = [j1 - j0 for (_, j0, j1, _) in items]
+        sizes = [g1 - g0 for (_, g0, g1, _) in items]
         assert sizes == sorted(sizes, reverse=True)                # launch order: large items first
         by_slot = {it[3]: it for it in items}
         for b in range(nb):
             for s in range(row_begin[b], row_begin[b + 1]):
                 assert by_slot[s][0] == b                          # row b's slabs are contiguous
-        for (i, j0, j1, _) in items:
-            assert 0 <= i < j0 < j1 <= nb
-            for j in range(j0, j1):
-                assert (i, j) not in seen
-                seen.add((i, j))
-    assert len(seen) == nb * (nb - 1) // 2
+        for (i, g0, g1, _) in items:
+            assert 0 <= i and gpb * (i + 1) <= g0 < g1 <= gpb * nb  # only groups beyond block i
+            assert g0 % 4 == 0                                     # items start on a stage boundary
+            covered.setdefault(i, []).append((g0, g1))
+    total = 0
+    for i in range(nb - 1):
+        rs = sorted(covered.get(i, []))
+        assert rs[0][0] == gpb * (i + 1) and rs[-1][1] == gpb * nb  # the whole row ...
+        for (a0, a1), (b0, b1) in zip(rs, rs[1:]):
+            assert a1 == b0                                        # ... exactly once
+        total += rs[-1][1] - rs[0][0]
+    assert total == gpb * nb * (nb - 1) // 2
+    assert (nb - 1) not in covered
+
+
+@pytest.mark.parametrize("nb,parts", [(63, 1), (188, 1), (188, 8), (531, 8)])
+def test_symmetric_work_list_has_a_fine_tail(nb, parts):
+    # large items first, the last few per cent of the work in single stages: every CTA slot drains within ~one stage
+    items, _ = capi.sym_plan_query(nb, 0, parts)
+    sizes = [g1 - g0 for (_, g0, g1, _) in items]
+    work = sum(sizes)
+    slots = 148 * 3
+    assert sizes[-1] <= 4
+    tail = [s for s in sizes if s <= 4]
+    assert sum(tail) >= min(0.04 * work, 4 * 4 * slots)             # enough fine items to level the slots ...
+    assert len(tail) >= min(slots, len(sizes)) or work < 8 * slots
+    assert max(sizes) <= max(4, 0.4 * work / slots + 4)            # ... and no item is a big share of a slot
 
 
 def test_symmetric_work_list_is_balanced_across_parts():
     loads = []
     for part in range(8):
         items, _ = capi.sym_plan_query(178, part, 8)
-        loads.append(sum(j1 - j0 for (_, j0, j1, _) in items))
-    assert max(loads) - min(loads) <= 0.03 * max(loads) + 8
+        loads.append(sum(g1 - g0 for (_, g0, g1, _) in items))
+    assert max(loads) - min(loads) <= 0.03 * max(loads) + 8 * capi.sym_groups_per_block()
