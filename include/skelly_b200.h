@@ -105,6 +105,15 @@ SKB_API int skb_eval_fused(skb_ctx *ctx, const double *f_sl, const double *f_dl,
 SKB_API int skb_set_source_normals(skb_ctx *ctx, const double *normals, int64_t n_src);
 SKB_API int skb_eval_double_layer(skb_ctx *ctx, const double *density, double eta, double *u_trg, int accumulate);
 
+/* Opt-in fused self-exclusion (the reference computes all pairs and then subtracts each fiber's own
+ * dense block, fiber_container_finite_difference.cpp:203-210, fiber_finite_difference.cpp:56): give every Stokeslet
+ * source an id (its fiber index).  The targets must START with the sources (checked); a pair (target i < n_src,
+ * source j) with ids[i] == ids[j] then contributes exactly 0 -- decided in the integer pipe next to the r == 0 rule,
+ * no FP64 work added.  Differs from compute-then-subtract only where the reference's regularised branch would act
+ * (two distinct nodes of one fiber closer than 1e-5, kernels.cpp:176-184) and by the absence of the cancellation
+ * rounding.  ids == NULL switches it off; skb_set_sources(SKB_STOKESLET) clears it. */
+SKB_API int skb_set_source_exclusion_ids(skb_ctx *ctx, const int32_t *ids, int64_t n_src);
+
 /* ---- device-pointer entry points (single-GPU contexts) ----------------------------------------
  * For hosts that already own device memory and a stream (one rank per GPU under NCCL: the caller
  * all-gathers strengths itself, then evaluates its target block).  Asynchronous on `stream`, a

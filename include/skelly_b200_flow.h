@@ -82,6 +82,14 @@ SKB_API int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double
                             const double *body_densities, const double *body_forces_torques, double eta,
                             double *v_all);
 
+/* Opt-in: the matvec's fiber self term.  fused == 0 (default): the reference's way -- all pairs,
+ * then `vel -= fib.stokeslet_ * wf` per fiber (fiber_container_finite_difference.cpp:203-210) on the device.
+ * fused != 0: the pair kernels skip every intra-fiber pair (per-node fiber id compared in the integer pipe), nothing is
+ * subtracted: no cancellation of the O(1/ds) near-neighbour terms, and N_f * n fewer pairs.  The two agree except where
+ * the reference's regularised branch acts (distinct nodes of one fiber closer than 1e-5, kernels.cpp:176-184).  Applies
+ * to skb_flow_matvec / skb_flow_apply_matvec with all fiber nodes in the target list. */
+SKB_API int skb_flow_set_self_exclusion(skb_flow *fl, int fused);
+
 /* Restrict the matvec to rows [begin, end) of the target list [fibers | periphery | bodies] (end < 0: all).
  * For one-rank-per-GPU hosts: every rank loads the full geometry, all-gathers the strengths, and evaluates its own
  * block of targets; v_all / d_v_window then has (end - begin) rows.  The self-term subtraction is applied to the

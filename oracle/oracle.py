@@ -114,6 +114,21 @@ def stresslet_direct_cpu(r_src, f_src, r_trg, eta, n_threads=0, simd=-1):
     return _direct_cpu("oracle_stresslet_direct_cpu", r_src, f_src, r_trg, 9, eta, n_threads, simd)
 
 
+def stokeslet_direct_excluding(r_src, f_src, r_trg, ids):
+    """Stokeslet sum where the targets START with the sources and pairs (target i < n_src, source j) with
+    ids[i] == ids[j] are left out: the fused form of FiberContainerFiniteDifference::flow's "all pairs, then subtract the
+    fiber's own block" (fiber_container_finite_difference.cpp:203-210) for fibers whose nodes are farther apart than the
+    regularisation threshold 1e-5 (kernels.cpp:176-184).  Built as (all pairs) - (same-id pairs), each by the scalar
+    restatement of kernels.cu:57-77."""
+    r_src, f_src, r_trg = _a(r_src, 3), _a(f_src, 3), _a(r_trg, 3)
+    ids = np.asarray(ids).reshape(-1)
+    u = stokeslet_direct(r_src, f_src, r_trg)
+    for g in np.unique(ids):
+        m = np.nonzero(ids == g)[0]
+        u[m] -= stokeslet_direct(r_src[m], f_src[m], r_src[m])
+    return u
+
+
 def simd_level() -> int:
     return lib().oracle_simd_level()
 

@@ -80,6 +80,7 @@ def library() -> C.CDLL:
         "skb_eval_fused": ([ctxp, _dp, _dp, _dp], C.c_int),
         "skb_set_source_normals": ([ctxp, _dp, C.c_int64], C.c_int),
         "skb_eval_double_layer": ([ctxp, _dp, C.c_double, _dp, C.c_int], C.c_int),
+        "skb_set_source_exclusion_ids": ([ctxp, C.POINTER(C.c_int32), C.c_int64], C.c_int),
         "skb_set_targets_device": ([ctxp, C.c_void_p, C.c_int64, C.c_void_p], C.c_int),
         "skb_set_sources_device": ([ctxp, C.c_int, C.c_void_p, C.c_int64, C.c_void_p], C.c_int),
         "skb_eval_device": ([ctxp, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p], C.c_int),
@@ -111,6 +112,7 @@ def library() -> C.CDLL:
         "skb_flow_set_background": ([ctxp, C.POINTER(C.c_int), _dp, _dp], C.c_int),
         "skb_flow_velocity_at_targets": ([ctxp, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_set_target_window": ([ctxp, C.c_int64, C.c_int64], C.c_int),
+        "skb_flow_set_self_exclusion": ([ctxp, C.c_int], C.c_int),
         "skb_flow_set_target_ranges": ([ctxp, C.c_int, C.c_int] + [C.c_int64] * 4, C.c_int),
         "skb_flow_apply_fiber_force_device": ([ctxp, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "skb_flow_fiber_matvec_device": ([ctxp] + [C.c_void_p] * 5, C.c_int),
@@ -238,6 +240,15 @@ class Context:
         r_src = _arr(r_src, 3)
         _check(library().skb_set_sources(self._h, int(kind), _p(r_src), r_src.shape[0]))
         self.n_src[int(kind)] = r_src.shape[0]
+
+    def set_source_exclusion_ids(self, ids):
+        """Opt-in fused self-exclusion: Stokeslet sources that are the leading targets; pairs with equal ids (fiber
+        indices) contribute exactly 0.  None switches it off."""
+        if ids is None:
+            _check(library().skb_set_source_exclusion_ids(self._h, None, 0))
+            return
+        ids = np.ascontiguousarray(ids, dtype=np.int32).reshape(-1)
+        _check(library().skb_set_source_exclusion_ids(self._h, ids.ctypes.data_as(C.POINTER(C.c_int32)), ids.shape[0]))
 
     def set_source_normals(self, normals):
         normals = _arr(normals, 3)
@@ -403,6 +414,11 @@ class Flow:
         _check(library().skb_flow_velocity_at_targets(self._h, _p(r_trg), r_trg.shape[0], _p(a), _p(b), _p(c), _p(ft),
                                                       float(eta), _p(vel)))
         return vel
+
+    def set_self_exclusion(self, fused: bool):
+        """Matvec self term: False = the reference's compute-then-subtract (default); True = the pair kernels skip
+        intra-fiber pairs."""
+        _check(library().skb_flow_set_self_exclusion(self._h, int(bool(fused))))
 
     def set_target_window(self, begin: int, end: int = -1):
         """Evaluate only rows [begin, end) of [fibers | periphery | bodies] in matvec() (one rank's block)."""

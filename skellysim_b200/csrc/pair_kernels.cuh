@@ -70,6 +70,8 @@ struct PairArgs {
                            // [b*diag_tiles, (b+1)*diag_tiles), one per blockIdx.y (the diagonal blocks the
                            // symmetric kernel leaves out)
     int diag_part, diag_parts; // block-diagonal mode: only blocks owned by this part are evaluated
+    const int *src_fid;    // [n_src_pad] fiber id per source  (EXCL kernels only: same-fiber pairs contribute 0)
+    const int *trg_fid;    // [n_trg]     fiber id per target
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -120,11 +122,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gme
 // for most of the DFMA latency: 78.6% pipe utilisation in profiles/r1_ncu_pair_v1.md.
 // Stokeslet: 22 FP64 instructions per pair (kernels.cu:62-76);  outputs rinv y[c] and v = f + d (f.d) y^2.
 // ---------------------------------------------------------------------------------------------
-template <int C>
+// EXCL: chains whose target and source carry the same fiber id (ti == si) contribute exactly 0 (sym_kernels.cuh).
+template <int C, bool EXCL = false>
 __device__ __forceinline__ void stokeslet_chains(const double (&tx)[C], const double (&ty)[C], const double (&tz)[C],
                                                  const double (&sx)[C], const double (&sy)[C], const double (&sz)[C],
                                                  const double (&fx)[C], const double (&fy)[C], const double (&fz)[C],
-                                                 double (&y)[C], double (&vx)[C], double (&vy)[C], double (&vz)[C]) {
+                                                 double (&y)[C], double (&vx)[C], double (&vy)[C], double (&vz)[C],
+                                                 const int (&ti)[C], const int (&si)[C]) {
     // Instruction ORDER matters beyond dependencies: an FP64 instruction that reads 3 distinct 64-bit registers
     // occupies the pipe for 3 cycles instead of 2 (register-file read limit, scripts/ubench/fp64_ubench.cu) unless
     // one operand comes from the operand-reuse cache, i.e. the previous instruction read the same register in the
@@ -152,7 +156,8 @@ __device__ __forceinline__ void stokeslet_chains(const double (&tx)[C], const do
     for (int c = 0; c < C; ++c) {
         double y0;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2[c]));
-        if (__double2hiint(r2[c]) < 0x00100000) // r2 == 0 (or subnormal): the pair contributes exactly 0
+        // r2 == 0 (or subnormal): the pair contributes exactly 0
+        if (__double2hiint(r2[c]) < 0x00100000 || (EXCL && ti[c] == si[c]))
             y0 = 0.0;
         y[c] = y0;
     }
@@ -294,24 +299,26 @@ __device__ __forceinline__ void stresslet_chains(const double (&tx)[C], const do
 // Two sources (a, b) against the thread's T targets, as groups of independent chains:
 //   T == 1: one group of 2 chains (a, b);  T == 2: one group of 4 (2 targets x 2 sources);
 //   T >= 4: per source, groups of 4 targets.
-template <int T>
+template <int T, bool EXCL = false>
 __device__ __forceinline__ void stokeslet_two_sources(const double (&tx)[T], const double (&ty)[T],
                                                       const double (&tz)[T], const double (&sa)[3],
                                                       const double (&fa)[3], const double (&sb)[3],
                                                       const double (&fb)[3], double (&ux)[T], double (&uy)[T],
-                                                      double (&uz)[T]) {
+                                                      double (&uz)[T], const int (&tfid)[T], int ida, int idb) {
     if constexpr (T <= 2) {
         constexpr int C = 2 * T;
         double cx[C], cy[C], cz[C], sx[C], sy[C], sz[C], fx[C], fy[C], fz[C], y[C], vx[C], vy[C], vz[C];
+        int ti[C], si[C];
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int t = c % T;
             const bool second = c >= T;
+            ti[c] = tfid[t], si[c] = second ? idb : ida;
             cx[c] = tx[t], cy[c] = ty[t], cz[c] = tz[t];
             sx[c] = second ? sb[0] : sa[0], sy[c] = second ? sb[1] : sa[1], sz[c] = second ? sb[2] : sa[2];
             fx[c] = second ? fb[0] : fa[0], fy[c] = second ? fb[1] : fa[1], fz[c] = second ? fb[2] : fa[2];
         }
-        stokeslet_chains<C>(cx, cy, cz, sx, sy, sz, fx, fy, fz, y, vx, vy, vz);
+        stokeslet_chains<C, EXCL>(cx, cy, cz, sx, sy, sz, fx, fy, fz, y, vx, vy, vz, ti, si);
 #pragma unroll
         for (int c = 0; c < C; ++c) {
             const int t = c % T;
@@ -326,13 +333,15 @@ __device__ __forceinline__ void stokeslet_two_sources(const double (&tx)[T], con
 #pragma unroll
             for (int g = 0; g < T / G; ++g) {
                 double cx[G], cy[G], cz[G], sx[G], sy[G], sz[G], fx[G], fy[G], fz[G], y[G], vx[G], vy[G], vz[G];
+                int ti[G], si[G];
 #pragma unroll
                 for (int c = 0; c < G; ++c) {
+                    ti[c] = tfid[G * g + c], si[c] = src ? idb : ida;
                     cx[c] = tx[G * g + c], cy[c] = ty[G * g + c], cz[c] = tz[G * g + c];
                     sx[c] = src ? sb[0] : sa[0], sy[c] = src ? sb[1] : sa[1], sz[c] = src ? sb[2] : sa[2];
                     fx[c] = src ? fb[0] : fa[0], fy[c] = src ? fb[1] : fa[1], fz[c] = src ? fb[2] : fa[2];
                 }
-                stokeslet_chains<G>(cx, cy, cz, sx, sy, sz, fx, fy, fz, y, vx, vy, vz);
+                stokeslet_chains<G, EXCL>(cx, cy, cz, sx, sy, sz, fx, fy, fz, y, vx, vy, vz, ti, si);
 #pragma unroll
                 for (int c = 0; c < G; ++c) {
                     ux[G * g + c] = fma(y[c], vx[c], ux[G * g + c]);
@@ -399,11 +408,12 @@ __device__ __forceinline__ void stresslet_two_sources(const double (&tx)[T], con
 }
 
 // shared-memory footprint of the main kernel
-template <int KIND, int T> struct SmemLayout {
+template <int KIND, int T, bool EXCL = false> struct SmemLayout {
     static constexpr int fdim = KindTraits<KIND>::fdim;
     static constexpr int pos_stage_bytes = kSrcTile * 3 * 8;
     static constexpr int f_stage_bytes = kSrcTile * fdim * 8;
-    static constexpr int stage_bytes = pos_stage_bytes + f_stage_bytes;
+    static constexpr int id_stage_bytes = EXCL ? kSrcTile * 4 : 0;
+    static constexpr int stage_bytes = pos_stage_bytes + f_stage_bytes + id_stage_bytes;
     static constexpr int trg_bytes = kCtaThreads * T * 3 * 8;
     static constexpr int bar_offset = kStages * stage_bytes + trg_bytes;
     static constexpr int total_bytes = bar_offset + 2 * kStages * 8;
@@ -415,9 +425,10 @@ template <int KIND, int T> struct SmemLayout {
 // k + kPrefetch into the ring slot that every warp released two tiles ago, so the wait on that slot's
 // "empty" barrier never blocks in practice and no registers are spent on a dedicated producer warp.
 // ---------------------------------------------------------------------------------------------
-template <int KIND, int T, int MINB>
+template <int KIND, int T, int MINB, bool EXCL = false>
 __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairArgs a) {
-    using L = SmemLayout<KIND, T>;
+    static_assert(!EXCL || KIND == kStokeslet, "fiber self-exclusion is a Stokeslet (fiber -> fiber) notion");
+    using L = SmemLayout<KIND, T, EXCL>;
     constexpr int kTileT = kCtaThreads * T;
     extern __shared__ __align__(128) unsigned char smem[];
     double *trg_s = reinterpret_cast<double *>(smem + kStages * L::stage_bytes);
@@ -446,6 +457,10 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
         mbar_arrive_expect_tx(&full_bar[s], L::stage_bytes);
         tma_bulk_g2s(dst, gp + (size_t)k * L::pos_stage_bytes, L::pos_stage_bytes, &full_bar[s]);
         tma_bulk_g2s(dst + L::pos_stage_bytes, gf + (size_t)k * L::f_stage_bytes, L::f_stage_bytes, &full_bar[s]);
+        if constexpr (EXCL)
+            tma_bulk_g2s(dst + L::pos_stage_bytes + L::f_stage_bytes,
+                         reinterpret_cast<const char *>(a.src_fid) + (size_t)(first_tile + k) * L::id_stage_bytes,
+                         L::id_stage_bytes, &full_bar[s]);
     };
 
     if (tid == 0) {
@@ -481,9 +496,11 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
     __syncthreads(); // barrier init + target block visible to everyone
 
     double tx[T], ty[T], tz[T], ux[T], uy[T], uz[T];
+    int tfid[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const int i = t * kCtaThreads + tid;
+        tfid[t] = (EXCL && t_base + i < a.n_trg) ? __ldg(a.trg_fid + t_base + i) : -1;
         tx[t] = trg_s[3 * i + 0];
         ty[t] = trg_s[3 * i + 1];
         tz[t] = trg_s[3 * i + 2];
@@ -514,7 +531,13 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
             if constexpr (KIND == kStokeslet) {
                 const double2 f0 = fs[3 * j + 0], f1 = fs[3 * j + 1], f2 = fs[3 * j + 2];
                 const double fa[3] = {f0.x, f0.y, f1.x}, fb[3] = {f1.y, f2.x, f2.y};
-                stokeslet_two_sources<T>(tx, ty, tz, sa, fa, sb, fb, ux, uy, uz);
+                int ida = 0, idb = 0;
+                if constexpr (EXCL) {
+                    const int2 id2 = reinterpret_cast<const int2 *>(smem + s * L::stage_bytes + L::pos_stage_bytes +
+                                                                    L::f_stage_bytes)[j];
+                    ida = id2.x, idb = id2.y;
+                }
+                stokeslet_two_sources<T, EXCL>(tx, ty, tz, sa, fa, sb, fb, ux, uy, uz, tfid, ida, idb);
             } else {
                 const double2 f0 = fs[6 * j + 0], f1 = fs[6 * j + 1], f2 = fs[6 * j + 2];
                 const double2 f3 = fs[6 * j + 3], f4 = fs[6 * j + 4], f5 = fs[6 * j + 5];

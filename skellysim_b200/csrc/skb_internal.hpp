@@ -40,11 +40,19 @@ LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_sr
 int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const double *d_f_packed, long long n_src,
                     long long n_src_pad, const double *d_r_trg, long long n_trg, double *d_partial,
                     const LaunchPlan &plan, cudaStream_t st, int diag_tiles = 0, int diag_part = 0,
-                    int diag_parts = 1);
+                    int diag_parts = 1, const int *d_src_fid = nullptr, const int *d_trg_fid = nullptr);
 int launch_reduce(const double *d_partial, double *d_u, long long n_trg, int n_splits, double scale, int accumulate,
                   cudaStream_t st);
 
-enum StrengthMode { kRaw = 0, kNormalDensity = 1 };
+// kRaw: strengths as the caller ships them (3 or 9 per source); kNormalDensity: density, stresslet formed on the device;
+// kPacked: already in the kernels' packed, padded layout ([n_pad*3] weighted Stokeslet strengths / [n_pad*6] sym6
+// stresslet combinations), e.g. the landing zone peers pushed into -- no pack kernel runs
+enum StrengthMode { kRaw = 0, kNormalDensity = 1, kPacked = 2 };
+
+struct EvalOpts {
+    double *d_u_sym = nullptr; // symmetric path: write the leading (self-interaction) rows here instead of d_u_out
+    int sym_accumulate = -1;   // -1: same as `accumulate`
+};
 
 } // namespace skb
 
@@ -59,6 +67,13 @@ struct SourceSet {
     skb::DevBuf weights; // optional per-source quadrature weight folded into the Stokeslet strengths
     skb::DevBuf f_raw;   // strengths as shipped by the caller (3 or 9 per source; all-gather landing zone)
     skb::DevBuf f_packed;
+    const double *f_cur = nullptr; // packed strengths of the evaluation in flight (f_packed, or the caller's kPacked buffer)
+    // opt-in fused self-exclusion: Stokeslet sources and the leading targets carry an id (the fiber
+    // index); pairs with equal ids contribute 0.  excl_ids: [n_pad] source ids; excl_trg: [n_trg] target ids (-1 beyond
+    // the leading n targets), built on demand for the plain kernel
+    bool excl = false;
+    skb::DevBuf excl_ids, excl_trg;
+    long long excl_trg_n = -1;
     // symmetric (Newton's third law) path of the Stokeslet self-interaction, sym_kernels.cuh
     int self_state = -1;       // -1 unknown, 0 targets do not start with these sources, 1 they do
     bool sym_plan_valid = false;
@@ -103,7 +118,7 @@ namespace skb {
 // result (=|+=) scale_mul * [1 | -3]/(8 pi) * sum.
 int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, const double *d_f_raw, double two_eta,
                    double *d_u_out, int accumulate, cudaStream_t st, bool record_events, int *launches,
-                   LaunchPlan *plan_out, double scale_mul);
+                   LaunchPlan *plan_out, double scale_mul, const EvalOpts &opts = EvalOpts());
 
 struct SymItem;
 void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymItem> &order,

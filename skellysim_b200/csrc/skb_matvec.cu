@@ -66,6 +66,7 @@ struct skb_flow {
     skb_ctx *fib[2] = {nullptr, nullptr}, *shell[2] = {nullptr, nullptr}, *body[2] = {nullptr, nullptr};
     TargetCache tc_fib, tc_shell, tc_body;
     bool mv_dirty = true;
+    bool self_excl = false; // matvec: skip intra-fiber pairs in the kernels instead of compute-then-subtract (N3, opt-in)
     long long win_begin = 0, win_end = -1; // target window of the matvec in [fibers|shell|bodies] rows; -1 = all
     bool use_ranges = false;               // skb_flow_set_target_ranges instead of a contiguous window
     long long rq_f0 = 0, rq_f1 = 0, rq_s0 = 0, rq_s1 = 0, rq_b0 = 0, rq_b1 = 0; // requested (fiber indices, rows)
@@ -139,13 +140,15 @@ static int fibers_dev(skb_flow *fl, skb_ctx *ctx, const double *d_forces, double
     SKB_TRY(eval_on_device(ctx, d, SKB_STOKESLET, kRaw, d_forces, 0.0, d_vel, accumulate, fl->cur, false,
                            &fl->launches, nullptr, 1.0 / eta));
     fl->pairs += fl->n_fib * d.n_trg;
-    if (subtract_self) { // fcfd.cpp:203-210; the first N_f targets are the fiber nodes themselves
+    if (subtract_self && ctx->devs[0].src[SKB_STOKESLET].excl) {
+        // opt-in fused form: the pair kernels already skipped every intra-fiber pair (skb_flow_set_self_exclusion)
+    } else if (subtract_self) { // fcfd.cpp:203-210; the first N_f targets are the fiber nodes themselves
         if (d.n_trg < node_end - node_begin)
             return set_error(SKB_ERR_INVALID, "fiber flow with subtract_self needs the fiber nodes as the first "
                                               "%lld targets (n_trg = %lld)", node_end - node_begin, d.n_trg);
         const size_t smem = (size_t)fl->max_fiber_nodes * 6 * sizeof(double);
         fiber_self_subtract_kernel<<<fl->n_fibers, 128, smem, fl->cur>>>(
-            (const double *)fl->r_fib.ptr, (const double *)d.src[SKB_STOKESLET].f_packed.ptr,
+            (const double *)fl->r_fib.ptr, d.src[SKB_STOKESLET].f_cur,
             (const long long *)fl->fiber_offset.ptr, 1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps, d_vel, node_begin,
             node_end);
         CUDA_TRY(cudaGetLastError());
@@ -736,6 +739,18 @@ static int prepare_matvec_targets(skb_flow *fl) {
     SKB_TRY(skb_set_targets(fl->fib[1], r_win.data(), fl->n_win));
     SKB_TRY(skb_set_targets(fl->body[1], r_win.data(), fl->n_win));
     SKB_TRY(skb_set_targets(fl->shell[1], r_fb.data(), (long long)r_fb.size() / 3));
+    if (fl->self_excl && fl->n_fib > 0) {
+        if (fl->fa != 0 || fl->fb != nf)
+            return set_error(SKB_ERR_INVALID, "skb_flow_set_self_exclusion needs all fiber nodes as the leading matvec "
+                                              "targets (no target window / ranges that cut the fiber rows)");
+        std::vector<int32_t> ids((size_t)nf);
+        for (int f = 0; f < fl->n_fibers; ++f)
+            for (long long i = fl->h_fiber_off[(size_t)f]; i < fl->h_fiber_off[(size_t)f + 1]; ++i)
+                ids[(size_t)i] = f;
+        SKB_TRY(skb_set_source_exclusion_ids(fl->fib[1], ids.data(), nf));
+    } else {
+        SKB_TRY(skb_set_source_exclusion_ids(fl->fib[1], nullptr, 0));
+    }
     fl->mv_dirty = false;
     return SKB_OK;
 }
@@ -771,6 +786,15 @@ static int matvec_core(skb_flow *fl, const double *d_ff, const double *d_sd, con
     }
     // v_all += bc.flow(r_all, x_bodies, body_link_conditions, eta)     system.cpp:316
     SKB_TRY(bodies_dev(fl, fl->body[1], d_bd, d_f, d_t, eta, d_v, 1));
+    return SKB_OK;
+}
+
+int skb_flow_set_self_exclusion(skb_flow *fl, int fused) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_self_exclusion: NULL flow");
+    fl->self_excl = fused != 0;
+    fl->mv_dirty = true;
+    fl->geom_version++;
     return SKB_OK;
 }
 

@@ -44,9 +44,10 @@ long long launch_count() { return g_launches.load(std::memory_order_relaxed); }
 // ------------------------------------------------------------------------------------------------
 // launch planning
 // ------------------------------------------------------------------------------------------------
-template <int KIND, int T, int MINB> static cudaError_t launch_variant(const PairArgs &a, dim3 grid, cudaStream_t st) {
-    using L = SmemLayout<KIND, T>;
-    auto kern = pair_sum_kernel<KIND, T, MINB>;
+template <int KIND, int T, int MINB, bool EXCL = false>
+static cudaError_t launch_variant(const PairArgs &a, dim3 grid, cudaStream_t st) {
+    using L = SmemLayout<KIND, T, EXCL>;
+    auto kern = pair_sum_kernel<KIND, T, MINB, EXCL>;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -155,8 +156,11 @@ LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_sr
 
 int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const double *d_f_packed, long long n_src,
                     long long n_src_pad, const double *d_r_trg, long long n_trg, double *d_partial,
-                    const LaunchPlan &plan, cudaStream_t st, int diag_tiles, int diag_part, int diag_parts) {
+                    const LaunchPlan &plan, cudaStream_t st, int diag_tiles, int diag_part, int diag_parts,
+                    const int *d_src_fid, const int *d_trg_fid) {
     PairArgs a;
+    a.src_fid = d_src_fid;
+    a.trg_fid = d_trg_fid;
     a.r_src = d_r_src;
     a.f_src = d_f_packed;
     a.r_trg = d_r_trg;
@@ -172,12 +176,18 @@ int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const
     dim3 grid(plan.grid_x, plan.n_splits, 1);
     cudaError_t e = cudaSuccess;
 #define LAUNCH_CALL(KIND, T, MINB) e = launch_variant<KIND, T, MINB>(a, grid, st)
-    if (kind == kStokeslet) {
+#define LAUNCH_CALL_EXCL(KIND, T, MINB) e = launch_variant<KIND, T, MINB, true>(a, grid, st)
+    if (kind == kStokeslet && d_src_fid) { // fused self-exclusion variant (same-id pairs contribute 0)
+        if (!d_trg_fid)
+            return set_error(SKB_ERR_INVALID, "launch_pair_sum: exclusion ids without target ids");
+        SKB_DISPATCH_T(kStokeslet, plan.T, LAUNCH_CALL_EXCL)
+    } else if (kind == kStokeslet) {
         SKB_DISPATCH_T(kStokeslet, plan.T, LAUNCH_CALL)
     } else {
         SKB_DISPATCH_T(kStresslet, plan.T, LAUNCH_CALL)
     }
 #undef LAUNCH_CALL
+#undef LAUNCH_CALL_EXCL
     if (e != cudaSuccess)
         return set_error(SKB_ERR_CUDA, "pair_sum_kernel launch failed: %s", cudaGetErrorString(e));
     count_launch(1);
@@ -342,6 +352,8 @@ int skb_ctx_destroy(skb_ctx *ctx) {
             s.sym_flag.release();
             s.f_raw.release();
             s.f_packed.release();
+            s.excl_ids.release();
+            s.excl_trg.release();
         }
         if (d.ev_t0) cudaEventDestroy(d.ev_t0);
         if (d.ev_t1) cudaEventDestroy(d.ev_t1);
@@ -494,6 +506,7 @@ static int set_targets_impl(skb_ctx *ctx, const double *r_trg, long long n_trg, 
     for (auto &d : ctx->devs) {
         d.src[0].self_state = -1;
         d.src[1].self_state = -1;
+        d.src[0].excl_trg_n = -1;
         if (d.n_trg == 0)
             continue;
         CUDA_TRY(cudaSetDevice(d.info.dev));
@@ -614,6 +627,8 @@ static int set_sources_impl(skb_ctx *ctx, int kind, const double *r_src, long lo
         s.n_pad = n_pad;
         s.has_normals = false;
         s.has_weights = false;
+        s.excl = false;    // ids belong to one set of sources
+        s.excl_trg_n = -1;
         s.self_state = -1; // (the symmetric plan depends on the block count only and survives position updates)
         if (n_src == 0)
             continue;
@@ -660,9 +675,10 @@ __global__ void self_check_kernel(const double *__restrict__ a, const double *__
         *differs = 1;
 }
 
-template <int T, int MINB> static cudaError_t launch_sym(const SymArgs &a, int n_items, cudaStream_t st) {
+template <int T, int MINB, bool EXCL>
+static cudaError_t launch_sym(const SymArgs &a, int n_items, cudaStream_t st) {
     using L = SymSmem<T>;
-    auto kern = pair_sym_kernel<T, MINB>;
+    auto kern = pair_sym_kernel<T, MINB, EXCL>;
     static bool attr_set[64] = {false};
     int dev = 0;
     cudaGetDevice(&dev);
@@ -774,6 +790,28 @@ void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymIt
                      [](const SymItem &x, const SymItem &y) { return (x.g1 - x.g0) > (y.g1 - y.g0); });
 }
 
+// Are the first n_src targets bit-identical to the Stokeslet sources?  (decided once per set of positions)
+static int ensure_self_state(DeviceState &d, SourceSet &s, cudaStream_t st) {
+    if (s.self_state >= 0)
+        return SKB_OK;
+    if (d.n_trg < s.n || s.n <= 0) {
+        s.self_state = 0;
+        return SKB_OK;
+    }
+    SKB_TRY(s.sym_flag.ensure(sizeof(int)));
+    CUDA_TRY(cudaMemsetAsync(s.sym_flag.ptr, 0, sizeof(int), st));
+    const long long n3 = 3 * s.n;
+    self_check_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>((const double *)d.r_trg.ptr, (const double *)s.r.ptr,
+                                                                    n3, (int *)s.sym_flag.ptr);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    int differs = 1;
+    CUDA_TRY(cudaMemcpyAsync(&differs, s.sym_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    s.self_state = differs ? 0 : 1;
+    return SKB_OK;
+}
+
 // Decide whether the symmetric path applies and make sure its plan / buffers exist.
 static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) {
     *use = 0;
@@ -787,20 +825,7 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
     const long long nb = s.n_pad / block; // n_pad is a multiple of 1024
     if ((long long)sym_owned_rows((int)nb, d.sym_part, d.sym_parts) * s.n_pad * 24 > sym_mem_budget())
         return SKB_OK;
-    if (s.self_state < 0) { // positions changed: are the first n_src targets bit-identical to the sources?
-        SKB_TRY(s.sym_flag.ensure(sizeof(int)));
-        CUDA_TRY(cudaMemsetAsync(s.sym_flag.ptr, 0, sizeof(int), st));
-        const long long n3 = 3 * s.n;
-        self_check_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>((const double *)d.r_trg.ptr,
-                                                                        (const double *)s.r.ptr, n3,
-                                                                        (int *)s.sym_flag.ptr);
-        CUDA_TRY(cudaGetLastError());
-        count_launch(1);
-        int differs = 1;
-        CUDA_TRY(cudaMemcpyAsync(&differs, s.sym_flag.ptr, sizeof(int), cudaMemcpyDeviceToHost, st));
-        CUDA_TRY(cudaStreamSynchronize(st));
-        s.self_state = differs ? 0 : 1;
-    }
+    SKB_TRY(ensure_self_state(d, s, st));
     if (s.self_state != 1)
         return SKB_OK;
     if (!s.sym_plan_valid || s.sym_T != T || s.sym_nb != (int)nb || s.sym_part != d.sym_part ||
@@ -843,11 +868,12 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
 static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulate, cudaStream_t st, double scale_mul,
                     int *launches) {
     SourceSet &s = d.src[SKB_STOKESLET];
+    const double *f_packed = s.f_cur;
     const int T = s.sym_T;
     const long long block = (long long)kSymThreads * T;
     SymArgs a;
     a.r = (const double *)s.r.ptr;
-    a.f = (const double *)s.f_packed.ptr;
+    a.f = f_packed;
     a.items = (const SymItem *)s.sym_item_buf.ptr;
     a.P = (double *)s.sym_P.ptr;
     a.F = (double *)s.sym_F.ptr;
@@ -856,7 +882,9 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
     cudaError_t e = cudaSuccess;
     CUDA_TRY(cudaEventRecord(d.ev_fork2, st)); // strengths are packed: the diagonal blocks may start from here
     if (s.sym_items > 0) {
-        e = launch_sym<kSymT, kSymMinB>(a, s.sym_items, st);
+        a.fid = s.excl ? (const int *)s.excl_ids.ptr : nullptr;
+        e = s.excl ? launch_sym<kSymT, kSymMinB, true>(a, s.sym_items, st)
+                   : launch_sym<kSymT, kSymMinB, false>(a, s.sym_items, st);
         if (e != cudaSuccess)
             return set_error(SKB_ERR_CUDA, "pair_sym_kernel launch failed: %s", cudaGetErrorString(e));
         count_launch(1);
@@ -869,9 +897,10 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
     dp.tiles_per_split = 1;
     dp.grid_x = (unsigned)((s.n + block - 1) / block);
     CUDA_TRY(cudaStreamWaitEvent(d.aux_stream, d.ev_fork2, 0)); // recorded before the symmetric launch
-    SKB_TRY(launch_pair_sum(d.info, SKB_STOKESLET, (const double *)s.r.ptr, (const double *)s.f_packed.ptr, s.n,
+    SKB_TRY(launch_pair_sum(d.info, SKB_STOKESLET, (const double *)s.r.ptr, f_packed, s.n,
                             s.n_pad, (const double *)s.r.ptr, s.n, (double *)s.sym_diag.ptr, dp, d.aux_stream, T,
-                            s.sym_part, s.sym_parts));
+                            s.sym_part, s.sym_parts, s.excl ? (const int *)s.excl_ids.ptr : nullptr,
+                            s.excl ? (const int *)s.excl_ids.ptr : nullptr));
     CUDA_TRY(cudaEventRecord(d.ev_join2, d.aux_stream));
     CUDA_TRY(cudaStreamWaitEvent(st, d.ev_join2, 0));
     const long long n3 = 3 * s.n;
@@ -893,9 +922,18 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
 } // namespace skb
 
 namespace skb {
+__global__ void excl_target_ids_kernel(const int *__restrict__ src_ids, long long n_src, long long trg_begin,
+                                       long long n_trg, int *__restrict__ out) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_trg) {
+        const long long g = trg_begin + i; // global target row: the leading n_src rows are the sources themselves
+        out[i] = g < n_src ? src_ids[g] : -1;
+    }
+}
+
 int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, const double *d_f_raw, double two_eta,
                    double *d_u_out, int accumulate, cudaStream_t st, bool record_events, int *launches,
-                   LaunchPlan *plan_out, double scale_mul) {
+                   LaunchPlan *plan_out, double scale_mul, const EvalOpts &opts) {
     SourceSet &s = d.src[kind];
     const int bs = 256;
     if (d.n_trg == 0)
@@ -906,20 +944,35 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
         return SKB_OK;
     }
     // 1. strengths -> packed, padded layout
-    if (kind == SKB_STOKESLET) {
-        pack_sl_kernel<<<(unsigned)((s.n_pad * 3 + bs - 1) / bs), bs, 0, st>>>(
-            d_f_raw, s.has_weights ? (const double *)s.weights.ptr : nullptr, (double *)s.f_packed.ptr, s.n, s.n_pad);
-    } else if (mode == kRaw) {
-        pack_dl9_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(d_f_raw, (double *)s.f_packed.ptr, s.n,
-                                                                             s.n_pad);
+    s.f_cur = (const double *)s.f_packed.ptr;
+    if (mode == kPacked) {
+        s.f_cur = d_f_raw;
     } else {
-        pack_dl_normal_density_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(
-            (const double *)s.normals.ptr, d_f_raw, two_eta, (double *)s.f_packed.ptr, s.n, s.n_pad);
+        if (kind == SKB_STOKESLET) {
+            pack_sl_kernel<<<(unsigned)((s.n_pad * 3 + bs - 1) / bs), bs, 0, st>>>(
+                d_f_raw, s.has_weights ? (const double *)s.weights.ptr : nullptr, (double *)s.f_packed.ptr, s.n, s.n_pad);
+        } else if (mode == kRaw) {
+            pack_dl9_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(d_f_raw, (double *)s.f_packed.ptr, s.n,
+                                                                                 s.n_pad);
+        } else {
+            pack_dl_normal_density_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(
+                (const double *)s.normals.ptr, d_f_raw, two_eta, (double *)s.f_packed.ptr, s.n, s.n_pad);
+        }
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        if (launches)
+            *launches += 1;
     }
-    CUDA_TRY(cudaGetLastError());
-    count_launch(1);
     if (record_events)
         CUDA_TRY(cudaEventRecord(d.ev_k0, st));
+    // fused self-exclusion (opt-in): ids only make sense when the sources are the leading targets
+    const bool excl = kind == SKB_STOKESLET && s.excl;
+    if (excl && ctx->devs.size() == 1) { // (multi-device contexts check their host copies of the positions, eval_host)
+        SKB_TRY(ensure_self_state(d, s, st));
+        if (s.self_state != 1)
+            return set_error(SKB_ERR_STATE, "exclusion ids are set, but the targets do not start with the Stokeslet "
+                                            "sources (skb_set_source_exclusion_ids)");
+    }
     // 2. pair sums
     // ---- symmetric path: sources are the leading targets (fiber -> fiber block of apply_matvec) ----
     long long n_sym = 0;
@@ -942,12 +995,26 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
     LaunchPlan plan{};
     // the long symmetric kernel is launched first so that the remainder's CTAs are dispatched into its tail
     if (n_sym > 0)
-        SKB_TRY(sym_eval(ctx, d, d_u_out, accumulate, st, scale_mul, launches));
+        SKB_TRY(sym_eval(ctx, d, opts.d_u_sym ? opts.d_u_sym : d_u_out,
+                         opts.sym_accumulate >= 0 ? opts.sym_accumulate : accumulate, st, scale_mul, launches));
     if (n_trg_std > 0) {
+        const int *d_src_ids = nullptr, *d_trg_ids = nullptr;
+        if (excl && n_sym == 0) { // the whole target list goes through the plain kernel: it needs per-target ids
+            if (s.excl_trg_n != d.n_trg) {
+                SKB_TRY(s.excl_trg.ensure((size_t)d.n_trg * sizeof(int)));
+                excl_target_ids_kernel<<<(unsigned)((d.n_trg + bs - 1) / bs), bs, 0, st_std>>>(
+                    (const int *)s.excl_ids.ptr, s.n, d.trg_begin, d.n_trg, (int *)s.excl_trg.ptr);
+                CUDA_TRY(cudaGetLastError());
+                count_launch(1);
+                s.excl_trg_n = d.n_trg;
+            }
+            d_src_ids = (const int *)s.excl_ids.ptr;
+            d_trg_ids = (const int *)s.excl_trg.ptr;
+        } // (with the symmetric path the remainder targets are not sources: nothing to exclude there)
         plan = plan_launch(d.info, kind, n_trg_std, (int)((s.n + kSrcTile - 1) / kSrcTile), ctx->force_T, ctx->force_S);
         SKB_TRY(d.partial.ensure((size_t)plan.n_splits * (size_t)n_trg_std * 24));
-        SKB_TRY(launch_pair_sum(d.info, kind, (const double *)s.r.ptr, (const double *)s.f_packed.ptr, s.n, s.n_pad,
-                                d_r_trg_std, n_trg_std, (double *)d.partial.ptr, plan, st_std));
+        SKB_TRY(launch_pair_sum(d.info, kind, (const double *)s.r.ptr, s.f_cur, s.n, s.n_pad, d_r_trg_std, n_trg_std,
+                                (double *)d.partial.ptr, plan, st_std, 0, 0, 1, d_src_ids, d_trg_ids));
         // 3. combine splits, scale: 1/(8 pi) (kernels.cu:59) or -3/(8 pi) (kernels.cu:26,51)
         SKB_TRY(launch_reduce((const double *)d.partial.ptr, d_u_std, n_trg_std, plan.n_splits, scale, accumulate,
                               st_std));
@@ -968,8 +1035,6 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
     }
     if (record_events)
         CUDA_TRY(cudaEventRecord(d.ev_k1, st));
-    if (launches)
-        *launches += 1; // the pack kernel
     if (plan_out)
         *plan_out = plan;
     return SKB_OK;
@@ -992,6 +1057,11 @@ static int eval_host(skb_ctx *ctx, int kind, StrengthMode mode, const double *f_
     if (mode == kNormalDensity && n_src > 0 && !ctx->devs[0].src[kind].has_normals)
         return set_error(SKB_ERR_STATE, "eval_double_layer: skb_set_source_normals has not been called");
     SKB_TRY(update_layout(ctx));
+    if (kind == SKB_STOKESLET && ctx->devs.size() > 1 && ctx->devs[0].src[kind].excl &&
+        !(ctx->n_trg >= n_src && (long long)ctx->h_src[kind].size() == 3 * n_src &&
+          std::memcmp(ctx->h_trg.data(), ctx->h_src[kind].data(), (size_t)n_src * 24) == 0))
+        return set_error(SKB_ERR_STATE, "exclusion ids are set, but the targets do not start with the Stokeslet sources "
+                                        "(skb_set_source_exclusion_ids)");
     if (n_src == 0) { // an empty class contributes nothing, whatever layout the devices hold the targets in
         if (!accumulate && ctx->n_trg > 0)
             std::memset(u_trg, 0, (size_t)ctx->n_trg * 24);
@@ -1169,6 +1239,31 @@ int skb_set_source_normals(skb_ctx *ctx, const double *normals, int64_t n_src) {
         SKB_TRY(s.normals.ensure((size_t)n * 24));
         CUDA_TRY(cudaMemcpyAsync(s.normals.ptr, normals, (size_t)n * 24, cudaMemcpyHostToDevice, d.stream));
         CUDA_TRY(cudaStreamSynchronize(d.stream));
+    }
+    return SKB_OK;
+}
+
+int skb_set_source_exclusion_ids(skb_ctx *ctx, const int32_t *ids, int64_t n_src) {
+    if (!ctx)
+        return set_error(SKB_ERR_INVALID, "skb_set_source_exclusion_ids: NULL ctx");
+    const long long n = ctx->devs[0].src[SKB_STOKESLET].n;
+    if (n < 0)
+        return set_error(SKB_ERR_STATE, "skb_set_source_exclusion_ids: call skb_set_sources(SKB_STOKESLET, ...) first");
+    if (ids && n_src != n)
+        return set_error(SKB_ERR_INVALID, "skb_set_source_exclusion_ids: n_src=%lld does not match the %lld Stokeslet "
+                                          "sources", (long long)n_src, n);
+    for (auto &d : ctx->devs) {
+        SourceSet &s = d.src[SKB_STOKESLET];
+        s.excl = false;
+        s.excl_trg_n = -1;
+        if (!ids || n == 0)
+            continue;
+        CUDA_TRY(cudaSetDevice(d.info.dev));
+        SKB_TRY(s.excl_ids.ensure((size_t)s.n_pad * sizeof(int)));
+        CUDA_TRY(cudaMemsetAsync(s.excl_ids.ptr, 0xff, (size_t)s.n_pad * sizeof(int), d.stream)); // pads: id -1
+        CUDA_TRY(cudaMemcpyAsync(s.excl_ids.ptr, ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, d.stream));
+        CUDA_TRY(cudaStreamSynchronize(d.stream));
+        s.excl = true;
     }
     return SKB_OK;
 }

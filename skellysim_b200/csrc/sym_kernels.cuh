@@ -24,23 +24,26 @@
 namespace skb {
 
 #ifndef SKB_SYM_T
-#define SKB_SYM_T 4 // nodes of the I block per thread (tuning knob; profiles/r2_sym_variants.md)
+#define SKB_SYM_T 8 // nodes of the I block per thread (tuning knob; profiles/r2_sym_variants.md)
 #endif
 #ifndef SKB_SYM_MINB
-#define SKB_SYM_MINB 3 // resident CTAs per SM asked of ptxas (register cap 65536 / (128 * MINB))
+#define SKB_SYM_MINB 2 // resident CTAs per SM asked of ptxas (register cap 65536 / (128 * MINB))
 #endif
 #ifndef SKB_SYM_UNROLL
 #define SKB_SYM_UNROLL 1 // ring steps unrolled
 #endif
 #ifndef SKB_SYM_PREFETCH
-#define SKB_SYM_PREFETCH 0 // 1: the next step's record is loaded from shared memory before this step's chain
+#define SKB_SYM_PREFETCH 1 // 1: the next step's record is loaded from shared memory before this step's chain
 #endif
 constexpr int kSymThreads = 128;
 constexpr int kSymT = SKB_SYM_T;
 constexpr int kSymMinB = SKB_SYM_MINB;
 constexpr int kSymUnroll = SKB_SYM_UNROLL;
-constexpr int kSymStages = 4;       // TMA ring depth
-constexpr int kSymPrefetch = 2;     // stages in flight ahead of the one being consumed
+#ifndef SKB_SYM_STAGES
+#define SKB_SYM_STAGES 4 // TMA ring depth (a stage is 6 KB)
+#endif
+constexpr int kSymStages = SKB_SYM_STAGES;
+constexpr int kSymPrefetch = kSymStages > 2 ? 2 : 1; // stages in flight ahead of the one being consumed
 constexpr int kSymGroup = 32;       // nodes per J group (one ring)
 constexpr int kSymStageGroups = 4;  // groups per stage
 constexpr int kSymStageNodes = kSymGroup * kSymStageGroups;
@@ -54,6 +57,7 @@ struct SymItem {
 struct SymArgs {
     const double *r;      // [n_pad*3] node positions, padded to a multiple of the block (pads replicate the last node)
     const double *f;      // [n_pad*3] packed Stokeslet strengths, zero padded
+    const int *fid;       // [n_pad] fiber index of every node (EXCL kernels only)
     const SymItem *items; // [gridDim.x]
     double *P;            // [owned rows][n_pad*3]  reverse partials: P[prow(I)][node of J] = sum over targets in I
     double *F;            // [n_items][block*3] forward partials of each item
@@ -63,7 +67,7 @@ struct SymArgs {
 
 template <int T> struct SymSmem {
     static constexpr int block = kSymThreads * T;
-    static constexpr int stage_bytes = kSymStageNodes * 48; // positions + strengths of one stage
+    static constexpr int stage_bytes = kSymStageNodes * 52; // positions + strengths (+ fiber ids) of one stage
     static constexpr int slab_doubles = kSymStageNodes * 3; // one warp's reverse sums of one stage
     static constexpr int slabs_bytes = 2 * (kSymThreads / 32) * slab_doubles * 8; // double-buffered
     static constexpr int bar_offset = kSymStages * stage_bytes + slabs_bytes;
@@ -73,13 +77,17 @@ template <int T> struct SymSmem {
 // T pair-of-pairs: targets (tx,ty,tz | strength hx,hy,hz) against ONE record (rx,ry,rz | strength gx,gy,gz).
 // forward:  uf_t += y (g + d (g.d) y^2)      reverse:  ur += y (h_t + d (h_t.d) y^2)       d = x_t - x_rec
 // (the reverse displacement is -d; the two sign changes cancel).  32 FP64 instructions per pair-of-pairs.
-template <int T>
+// EXCL (opt-in): pairs whose two nodes belong to the same fiber contribute exactly 0 -- the fused form
+// of FiberContainerFiniteDifference::flow's "all pairs, then subtract the fiber's own block"
+// (fiber_container_finite_difference.cpp:203-210).  The fiber ids are compared in the integer pipe next to the r == 0
+// rule and mask the same reciprocal-square-root seed: no FP64 instruction is added.
+template <int T, bool EXCL = false>
 __device__ __forceinline__ void stokeslet_pairpairs(const double (&tx)[T], const double (&ty)[T],
                                                     const double (&tz)[T], const double (&hx)[T],
                                                     const double (&hy)[T], const double (&hz)[T], double rx, double ry,
                                                     double rz, double gx, double gy, double gz, double (&ufx)[T],
                                                     double (&ufy)[T], double (&ufz)[T], double &urx, double &ury,
-                                                    double &urz) {
+                                                    double &urz, const int (&tid)[T], int rid) {
     double dx[T], dy[T], dz[T], r2[T], y[T], q[T], fr[T], hr[T];
 #pragma unroll
     for (int c = 0; c < T; ++c)
@@ -103,7 +111,7 @@ __device__ __forceinline__ void stokeslet_pairpairs(const double (&tx)[T], const
     for (int c = 0; c < T; ++c) {
         double y0;
         asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y0) : "d"(r2[c]));
-        if (__double2hiint(r2[c]) < 0x00100000)
+        if (__double2hiint(r2[c]) < 0x00100000 || (EXCL && tid[c] == rid))
             y0 = 0.0;
         y[c] = y0;
     }
@@ -163,7 +171,7 @@ __device__ __forceinline__ void stokeslet_pairpairs(const double (&tx)[T], const
     }
 }
 
-template <int T, int MINB>
+template <int T, int MINB, bool EXCL = false>
 __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymArgs a) {
     using L = SymSmem<T>;
     constexpr int kBlock = L::block;
@@ -185,9 +193,13 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
         const int ng = (item.g1 - g) < kSymStageGroups ? (item.g1 - g) : kSymStageGroups;
         const uint32_t bytes = (uint32_t)ng * kSymGroup * 24;
         const size_t off = (size_t)g * kSymGroup * 24;
-        mbar_arrive_expect_tx(&full_bar[s], 2 * bytes);
+        const uint32_t id_bytes = EXCL ? (uint32_t)ng * kSymGroup * 4 : 0u;
+        mbar_arrive_expect_tx(&full_bar[s], 2 * bytes + id_bytes);
         tma_bulk_g2s(dst, reinterpret_cast<const char *>(a.r) + off, bytes, &full_bar[s]);
         tma_bulk_g2s(dst + kSymStageNodes * 24, reinterpret_cast<const char *>(a.f) + off, bytes, &full_bar[s]);
+        if constexpr (EXCL)
+            tma_bulk_g2s(dst + kSymStageNodes * 48, reinterpret_cast<const char *>(a.fid) + (size_t)g * kSymGroup * 4,
+                         id_bytes, &full_bar[s]);
     };
 
     if (tid == 0) {
@@ -202,9 +214,11 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
     }
     // this thread's T nodes of block I: position, strength, forward accumulators
     double tx[T], ty[T], tz[T], hx[T], hy[T], hz[T], ufx[T], ufy[T], ufz[T];
+    int tfid[T];
 #pragma unroll
     for (int t = 0; t < T; ++t) {
         const size_t i = (size_t)item.I * kBlock + t * kSymThreads + tid;
+        tfid[t] = EXCL ? __ldg(a.fid + i) : 0;
         tx[t] = __ldg(a.r + 3 * i + 0), ty[t] = __ldg(a.r + 3 * i + 1), tz[t] = __ldg(a.r + 3 * i + 2);
         hx[t] = __ldg(a.f + 3 * i + 0), hy[t] = __ldg(a.f + 3 * i + 1), hz[t] = __ldg(a.f + 3 * i + 2);
         ufx[t] = ufy[t] = ufz[t] = 0.0;
@@ -224,6 +238,7 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
         mbar_wait(&full_bar[s], (k / kSymStages) & 1);
         const double *ps = reinterpret_cast<const double *>(smem + s * L::stage_bytes);
         const double *fs = ps + kSymStageNodes * 3;
+        const int *ids = reinterpret_cast<const int *>(smem + s * L::stage_bytes + kSymStageNodes * 48);
         double *slab_set = slabs + (k & 1) * kWarps * L::slab_doubles; // double-buffered: one barrier per stage
         double *my_slab = slab_set + warp * L::slab_doubles;
 #pragma unroll 1
@@ -232,40 +247,51 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
             double urx = 0.0, ury = 0.0, urz = 0.0;
 #if SKB_SYM_PREFETCH
             double nrx, nry, nrz, ngx, ngy, ngz;
+            int nid = 0;
             {
                 const int idx = base + lane;
                 nrx = ps[3 * idx + 0], nry = ps[3 * idx + 1], nrz = ps[3 * idx + 2];
                 ngx = fs[3 * idx + 0], ngy = fs[3 * idx + 1], ngz = fs[3 * idx + 2];
+                if constexpr (EXCL)
+                    nid = ids[idx];
             }
 #endif
             _Pragma("unroll kSymUnroll")
             for (int st = 0; st < 32; ++st) {
 #if SKB_SYM_PREFETCH
                 const double rx = nrx, ry = nry, rz = nrz, gx = ngx, gy = ngy, gz = ngz;
+                const int rid = nid;
                 {
                     const int idx = base + ((lane + st + 1) & 31); // (the 33rd load re-reads the first record: harmless)
                     nrx = ps[3 * idx + 0], nry = ps[3 * idx + 1], nrz = ps[3 * idx + 2];
                     ngx = fs[3 * idx + 0], ngy = fs[3 * idx + 1], ngz = fs[3 * idx + 2];
+                    if constexpr (EXCL)
+                        nid = ids[idx];
                 }
 #else
                 const int idx = base + ((lane + st) & 31);
                 // per-lane record from shared memory: 24 B stride is bank-conflict free for 64-bit loads
                 const double rx = ps[3 * idx + 0], ry = ps[3 * idx + 1], rz = ps[3 * idx + 2];
                 const double gx = fs[3 * idx + 0], gy = fs[3 * idx + 1], gz = fs[3 * idx + 2];
+                const int rid = EXCL ? ids[idx] : 0;
 #endif
                 if constexpr (T <= 4) {
-                    stokeslet_pairpairs<T>(tx, ty, tz, hx, hy, hz, rx, ry, rz, gx, gy, gz, ufx, ufy, ufz, urx, ury, urz);
+                    stokeslet_pairpairs<T, EXCL>(tx, ty, tz, hx, hy, hz, rx, ry, rz, gx, gy, gz, ufx, ufy, ufz, urx, ury,
+                                                 urz, tfid, rid);
                 } else { // chains in groups of 4: bounds the live temporaries
 #pragma unroll
                     for (int g0 = 0; g0 < T; g0 += 4) {
                         double ax[4], ay[4], az[4], bx[4], by[4], bz[4], cx[4], cy[4], cz[4];
+                        int ti[4];
 #pragma unroll
                         for (int c = 0; c < 4; ++c) {
+                            ti[c] = tfid[g0 + c];
                             ax[c] = tx[g0 + c], ay[c] = ty[g0 + c], az[c] = tz[g0 + c];
                             bx[c] = hx[g0 + c], by[c] = hy[g0 + c], bz[c] = hz[g0 + c];
                             cx[c] = ufx[g0 + c], cy[c] = ufy[g0 + c], cz[c] = ufz[g0 + c];
                         }
-                        stokeslet_pairpairs<4>(ax, ay, az, bx, by, bz, rx, ry, rz, gx, gy, gz, cx, cy, cz, urx, ury, urz);
+                        stokeslet_pairpairs<4, EXCL>(ax, ay, az, bx, by, bz, rx, ry, rz, gx, gy, gz, cx, cy, cz, urx, ury,
+                                                     urz, ti, rid);
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             ufx[g0 + c] = cx[c], ufy[g0 + c] = cy[c], ufz[g0 + c] = cz[c];
