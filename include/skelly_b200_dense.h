@@ -28,6 +28,10 @@ enum skb_dense_op { SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY = 0, SKB_DENSE_M_INV 
 
 /* n_gpus devices (0..n-1) of this process; rows are split in contiguous blocks like the reference's MPI_Scatterv */
 SKB_API int skb_dense_create(int n_gpus, skb_dense **out);
+/* the same on an explicit device list (one rank per GPU: a single-device handle on the rank's own GPU holding the
+ * rank's row block of the operators, periphery.cpp:387-417) */
+SKB_API int skb_dense_create_on(const int *device_ids, int n_gpus, skb_dense **out);
+SKB_API int skb_dense_device(const skb_dense *dn, int index, int *device);
 SKB_API int skb_dense_destroy(skb_dense *dn);
 
 /* A: row-major n_rows x n_cols (the numpy layout of the precompute file).  Copied to the device(s). */

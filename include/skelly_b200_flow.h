@@ -109,6 +109,31 @@ SKB_API int skb_flow_matvec_device(skb_flow *fl, const double *d_fib_forces, con
                                    const double *d_body_densities, const double *d_body_forces,
                                    const double *d_body_torques, double eta, double *d_v_window, void *stream);
 
+/* ---- multi-GPU groups: one skb_flow per GPU, exchange through peer memory (NVLink / NVSwitch) -----------------
+ * Every member holds the full geometry (skb_flow_set_fibers / _periphery / _bodies with identical arguments) and owns
+ * whole fibers, periphery rows and body rows (skb_flow_set_target_ranges).  Per matvec each member packs the strengths
+ * of ITS fibers / periphery rows once and stores them straight into all members' windows (pack + all-gather in one
+ * kernel), evaluates its block rows of the symmetric fiber-fiber interaction and its own remainder rows from local
+ * memory, and finally adds up the partial velocities of its own fiber rows from all windows (reduce-scatter fused
+ * with the accumulation).  No library collective is on the path; ordering is by epoch flags in the windows.
+ *   same process (what the reference's one-rank rule for direct evaluators admits, system.cpp:618-623): create one
+ *     flow per device, skb_flow_group_init on each, then skb_flow_group_connect every ordered pair -- or simply use
+ *     skb_mflow_* below, which does all of that;
+ *   one process per GPU: skb_flow_group_init, skb_flow_group_export -> exchange the 64-byte handles by any means
+ *     (MPI_Allgather, torch.distributed) -> skb_flow_group_import for every peer.
+ * skb_flow_group_init must follow the geometry calls (the window is laid out for their node counts; positions may
+ * change later, counts may not).  In a group, the *_device entry points take the OWN slices: fiber forces / x_fibers of
+ * the own fibers, periphery density of the own rows; body inputs are complete on every member.  All members must issue
+ * the same sequence of matvec calls (like any collective). */
+#define SKB_FLOW_IPC_HANDLE_BYTES 64
+SKB_API int skb_flow_group_init(skb_flow *fl, int rank, int size);
+SKB_API int skb_flow_group_export(skb_flow *fl, void *handle_64_bytes);
+SKB_API int skb_flow_group_import(skb_flow *fl, int peer_rank, const void *handle_64_bytes);
+SKB_API int skb_flow_group_connect(skb_flow *fl, int peer_rank, skb_flow *peer);
+/* after synchronising: *missing_peer = rank of a member whose flag never arrived within the time-out (a flag wait
+ * gives up after ~10 s instead of hanging the GPU), or -1 */
+SKB_API int skb_flow_group_error(skb_flow *fl, int *missing_peer);
+
 /* ---- per-fiber dense operators on the device ------------------------------------------
  * The O(N_f n^2) host work of one GMRES iteration -- FiberContainerFiniteDifference::apply_fiber_force
  * (fiber_container_finite_difference.cpp:272-287) and ::matvec (:216-232 -> FiberFiniteDifference::matvec,
@@ -171,6 +196,18 @@ SKB_API int skb_flow_apply_matvec_dense(skb_flow *fl, struct skb_dense *dn, cons
                                         const double *x_shell, const double *body_densities,
                                         const double *body_forces_torques, const double *fiber_link_conditions,
                                         double eta, double *res_fibers, double *res_shell, double *v_bodies);
+
+/* Device-pointer form of skb_flow_apply_matvec(_dense): everything already on this flow's device, asynchronous on
+ * `stream`.  dn == NULL: d_out_shell = v_shell; else res_shell (the handle holds the own periphery rows x all columns).
+ * Works for a whole system and for a group member (OWN slices: d_x_fibers / d_res_fibers 4 per own fiber node,
+ * d_x_shell / d_out_shell 3 per own periphery row, d_fiber_link_conditions 7 per own fiber or NULL, d_v_bodies 3 per own
+ * body row; body densities / forces / torques complete).  This is one GMRES iteration's operator apply with nothing
+ * crossing PCIe (a12: solver_hydro.cpp:42-48 calls exactly this per iteration). */
+SKB_API int skb_flow_apply_matvec_device(skb_flow *fl, struct skb_dense *dn, const double *d_x_fibers,
+                                         const double *d_x_shell, const double *d_body_densities,
+                                         const double *d_body_forces, const double *d_body_torques,
+                                         const double *d_fiber_link_conditions, double eta, double *d_res_fibers,
+                                         double *d_out_shell, double *d_v_bodies, void *stream);
 
 typedef struct skb_flow_stats {
     double device_ms;   /* CUDA-event time of the last call, first launch to last kernel (copies excluded) */

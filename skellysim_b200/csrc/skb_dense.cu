@@ -120,7 +120,7 @@ struct skb_dense {
 
 extern "C" {
 
-int skb_dense_create(int n_gpus, skb_dense **out) {
+static int dense_create_impl(const int *ids, int n_gpus, skb_dense **out) {
     if (!out)
         return set_error(SKB_ERR_INVALID, "skb_dense_create: out == NULL");
     *out = nullptr;
@@ -133,10 +133,12 @@ int skb_dense_create(int n_gpus, skb_dense **out) {
     dn->devs.resize(n_gpus);
     for (int g = 0; g < n_gpus; ++g) {
         DenseDev &d = dn->devs[g];
-        d.dev = g;
-        CUDA_TRY(cudaSetDevice(g));
+        d.dev = ids ? ids[g] : g;
+        if (d.dev < 0 || d.dev >= n_dev)
+            return set_error(SKB_ERR_INVALID, "skb_dense_create_on: device id %d out of range", d.dev);
+        CUDA_TRY(cudaSetDevice(d.dev));
         cudaDeviceProp p;
-        CUDA_TRY(cudaGetDeviceProperties(&p, g));
+        CUDA_TRY(cudaGetDeviceProperties(&p, d.dev));
         d.num_sms = p.multiProcessorCount;
         CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
         CUDA_TRY(cudaEventCreate(&d.e0));
@@ -145,6 +147,19 @@ int skb_dense_create(int n_gpus, skb_dense **out) {
         CUDA_TRY(cudaEventCreate(&d.t1));
     }
     *out = dn.release();
+    return SKB_OK;
+}
+
+int skb_dense_create(int n_gpus, skb_dense **out) { return dense_create_impl(nullptr, n_gpus, out); }
+int skb_dense_create_on(const int *device_ids, int n_gpus, skb_dense **out) {
+    if (!device_ids)
+        return set_error(SKB_ERR_INVALID, "skb_dense_create_on: device_ids == NULL");
+    return dense_create_impl(device_ids, n_gpus, out);
+}
+int skb_dense_device(const skb_dense *dn, int index, int *device) {
+    if (!dn || !device || index < 0 || index >= (int)dn->devs.size())
+        return set_error(SKB_ERR_INVALID, "skb_dense_device: bad arguments");
+    *device = dn->devs[(size_t)index].dev;
     return SKB_OK;
 }
 

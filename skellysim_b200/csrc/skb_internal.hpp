@@ -52,6 +52,8 @@ enum StrengthMode { kRaw = 0, kNormalDensity = 1, kPacked = 2 };
 struct EvalOpts {
     double *d_u_sym = nullptr; // symmetric path: write the leading (self-interaction) rows here instead of d_u_out
     int sym_accumulate = -1;   // -1: same as `accumulate`
+    double *d_u_rem = nullptr; // symmetric path: write the rows beyond the self-interaction block here instead of
+                               // d_u_out + 3 n_src (group mode: the leading rows are partial sums that live elsewhere)
 };
 
 } // namespace skb
@@ -121,6 +123,7 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
                    LaunchPlan *plan_out, double scale_mul, const EvalOpts &opts = EvalOpts());
 
 struct SymItem;
+long long sym_block_nodes(); // nodes per block of the symmetric kernel (its I side)
 void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymItem> &order,
                      std::vector<int> &row_begin);
 

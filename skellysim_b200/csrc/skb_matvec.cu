@@ -4,6 +4,7 @@
 // upload of the strengths and the download of the velocities stays on the device.
 #include "aux_kernels.cuh"
 #include "fiber_ops.cuh"
+#include "group_kernels.cuh"
 #include "skb_internal.hpp"
 #include "../../include/skelly_b200_flow.h"
 #include "../../include/skelly_b200_dense.h"
@@ -108,15 +109,37 @@ struct skb_flow {
     int n_items_A = 0, n_items_F = 0;
     size_t gemv_smem = 0, fvel_smem = 0;
     DevBuf op_A, op_F, op_xs, op_len, op_plus, op_class, op_classD, op_classP, items_A, items_F;
-    DevBuf x_fib, res_fib, vb, res_shell, op_Ainv;
+    DevBuf x_fib, res_fib, vb, res_shell, op_Ainv, tmp_b;
     long long op_A_elems = 0;               // elements of the concatenated A_ (and of A_^-1)
     unsigned long long ops_gen = 0, precond_gen = 0; // the preconditioner belongs to one set of operators
+    // multi-GPU group (group_kernels.cuh): one member per GPU, exchange through peer memory
+    struct Group {
+        int rank = 0, size = 1;
+        void *window = nullptr;       // this member's window (cudaMalloc: exportable through CUDA IPC)
+        size_t window_bytes = 0;
+        void *peer[kMaxGroup] = {};   // base address of every member's window as mapped here (peer[rank] == window)
+        bool peer_ipc[kMaxGroup] = {};
+        size_t off_flags = 0, off_fsl[2] = {0, 0}, off_fshell[2] = {0, 0}, off_xshell[2] = {0, 0}, off_upart = 0;
+        long long n_fib = 0, n_shell = 0, n_pad_fib = 0, n_pad_shell = 0; // geometry the window was laid out for
+        unsigned long long epoch = 0;
+        bool use_sym = false;         // fiber rows: symmetric block rows + pull-reduce (else own rows with the plain kernel)
+        bool connected() const {
+            for (int m = 0; m < size; ++m)
+                if (!peer[m])
+                    return false;
+            return true;
+        }
+        template <class T> T *at(int member, size_t off) const { return reinterpret_cast<T *>((char *)peer[member] + off); }
+    } grp;
+    DevBuf scratch_u; // group mode: landing zone of eval_on_device's default output (never read)
     // staging
     DevBuf in_fib, in_shell, in_body, in_force, in_torque, vel, tmp;
     skb_flow_stats stats{};
     int launches = 0;
     long long pairs = 0;
 };
+
+static void group_release(skb_flow *fl);
 
 static int ensure_ctx(skb_flow *fl, skb_ctx **slot) {
     if (*slot)
@@ -387,11 +410,13 @@ int skb_flow_destroy(skb_flow *fl) {
     DevBuf *bufs[] = {&fl->fiber_offset, &fl->fiber_length, &fl->r_fib, &fl->r_shell, &fl->r_body, &fl->centers,
                       &fl->pt_pos, &fl->pt_force, &fl->pt_torque, &fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel, &fl->tmp,
                       &fl->op_A, &fl->op_F, &fl->op_xs, &fl->op_len, &fl->op_plus, &fl->op_class, &fl->op_classD,
-                      &fl->op_classP, &fl->items_A, &fl->items_F, &fl->x_fib, &fl->res_fib, &fl->vb, &fl->res_shell, &fl->op_Ainv};
+                      &fl->op_classP, &fl->items_A, &fl->items_F, &fl->x_fib, &fl->res_fib, &fl->vb, &fl->res_shell, &fl->op_Ainv, &fl->tmp_b};
     for (DevBuf *b : bufs)
         b->release();
     fl->g_matvec.reset();
     fl->g_vat.reset();
+    group_release(fl);
+    fl->scratch_u.release();
     if (fl->h_stage)
         cudaFreeHost(fl->h_stage);
     if (fl->ev0) cudaEventDestroy(fl->ev0);
@@ -727,6 +752,19 @@ static int prepare_matvec_targets(skb_flow *fl) {
     }
     const long long n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba;
     fl->n_win = n_fw + n_sw + n_bw;
+    const bool grouped = fl->grp.size > 1;
+    if (grouped) {
+        if (!fl->use_ranges)
+            return set_error(SKB_ERR_STATE, "group member: call skb_flow_set_target_ranges (own fibers / periphery rows / "
+                                            "body rows) before the first matvec");
+        if (fl->grp.n_fib != nf || fl->grp.n_shell != ns)
+            return set_error(SKB_ERR_STATE, "group member: the geometry changed size since skb_flow_group_init "
+                                            "(%lld/%lld fiber, %lld/%lld periphery nodes); re-initialise the group",
+                             nf, fl->grp.n_fib, ns, fl->grp.n_shell);
+        // fiber rows through the symmetric block rows of this member (partial sums, pulled together afterwards) when
+        // the self-interaction is big enough for that kernel; otherwise the member's own rows with the plain kernel
+        fl->grp.use_sym = nf >= 2LL * sym_block_nodes();
+    }
     // target lists of apply_matvec: r_all = [fibers | shell | bodies] (system.cpp:284-291),
     // r_fibbody = [fibers | bodies] (system.cpp:301-303), both restricted to this rank's pieces
     std::vector<double> r_win, r_fb;
@@ -736,11 +774,25 @@ static int prepare_matvec_targets(skb_flow *fl) {
     r_win.insert(r_win.end(), fl->h_r_body.begin() + 3 * fl->ba, fl->h_r_body.begin() + 3 * fl->bb);
     r_fb.insert(r_fb.end(), fl->h_r_fib.begin() + 3 * fl->fa, fl->h_r_fib.begin() + 3 * fl->fb);
     r_fb.insert(r_fb.end(), fl->h_r_body.begin() + 3 * fl->ba, fl->h_r_body.begin() + 3 * fl->bb);
-    SKB_TRY(skb_set_targets(fl->fib[1], r_win.data(), fl->n_win));
+    if (grouped && fl->grp.use_sym) {
+        // fiber sources meet [ALL fiber nodes | own shell rows | own body rows]
+        std::vector<double> r_sym;
+        r_sym.reserve((size_t)(nf + n_sw + n_bw) * 3);
+        r_sym.insert(r_sym.end(), fl->h_r_fib.begin(), fl->h_r_fib.end());
+        r_sym.insert(r_sym.end(), fl->h_r_shell.begin() + 3 * fl->sa, fl->h_r_shell.begin() + 3 * fl->sb);
+        r_sym.insert(r_sym.end(), fl->h_r_body.begin() + 3 * fl->ba, fl->h_r_body.begin() + 3 * fl->bb);
+        SKB_TRY(skb_ctx_set_symmetric(fl->fib[1], 1));
+        SKB_TRY(skb_ctx_set_sym_partition(fl->fib[1], fl->grp.rank, fl->grp.size));
+        SKB_TRY(skb_set_targets(fl->fib[1], r_sym.data(), nf + n_sw + n_bw));
+    } else {
+        SKB_TRY(skb_ctx_set_sym_partition(fl->fib[1], 0, 1));
+        SKB_TRY(skb_set_targets(fl->fib[1], r_win.data(), fl->n_win));
+    }
     SKB_TRY(skb_set_targets(fl->body[1], r_win.data(), fl->n_win));
     SKB_TRY(skb_set_targets(fl->shell[1], r_fb.data(), (long long)r_fb.size() / 3));
+    const bool all_fibers_lead = (fl->fa == 0 && fl->fb == nf) || (grouped && fl->grp.use_sym);
     if (fl->self_excl && fl->n_fib > 0) {
-        if (fl->fa != 0 || fl->fb != nf)
+        if (!all_fibers_lead)
             return set_error(SKB_ERR_INVALID, "skb_flow_set_self_exclusion needs all fiber nodes as the leading matvec "
                                               "targets (no target window / ranges that cut the fiber rows)");
         std::vector<int32_t> ids((size_t)nf);
@@ -755,9 +807,165 @@ static int prepare_matvec_targets(skb_flow *fl) {
     return SKB_OK;
 }
 
+// ---- group exchange steps (group_kernels.cuh) on fl->cur ---------------------------------------------------------
+static int group_flag(skb_flow *fl, int phase, bool do_signal, bool do_wait) {
+    skb_flow::Group &G = fl->grp;
+    GroupFlagArgs a;
+    for (int m = 0; m < G.size; ++m)
+        a.flags[m] = G.at<unsigned long long>(m, G.off_flags);
+    a.rank = G.rank;
+    a.size = G.size;
+    a.phase = phase;
+    a.epoch = G.epoch;
+    a.do_signal = do_signal;
+    a.do_wait = do_wait;
+    a.timeout_cycles = 20ULL * 1000 * 1000 * 1000; // ~10 s at 2 GHz
+    group_flag_kernel<<<1, 32, 0, fl->cur>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    fl->launches += 1;
+    return SKB_OK;
+}
+
+// device-side matvec flow of a group member on fl->cur: d_ff / d_sd are the strengths of the OWN fibers / periphery
+// rows, body inputs are complete on every member; d_v = [own fiber rows | own shell rows | own body rows] of v_all
+static int matvec_core_group(skb_flow *fl, const double *d_ff, const double *d_sd, const double *d_bd, const double *d_f,
+                             const double *d_t, double eta, double *d_v) {
+    skb_flow::Group &G = fl->grp;
+    if (!G.connected())
+        return set_error(SKB_ERR_STATE, "group member %d: not all peers are connected (skb_flow_group_import / _connect)",
+                         G.rank);
+    const long long ns = fl->n_shell, nf = fl->n_fib;
+    const long long n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba;
+    G.epoch += 1;
+    const int par = (int)(G.epoch & 1);
+    DeviceState &df = fl->fib[1]->devs[0];
+    // 1. PUSH: pack own strengths once, store them into every member's window (pack + all-gather in one kernel)
+    {
+        GroupPushArgs a;
+        a.fw = d_ff;
+        a.weight = df.src[SKB_STOKESLET].has_weights ? (const double *)df.src[SKB_STOKESLET].weights.ptr : nullptr;
+        a.fa = fl->fa;
+        a.n_f = n_fw;
+        a.density = d_sd;
+        a.normal = ns ? (const double *)fl->shell[1]->devs[0].src[SKB_STRESSLET].normals.ptr : nullptr;
+        a.sa = fl->sa;
+        a.n_s = n_sw;
+        a.two_eta = 2.0 * eta;
+        a.size = G.size;
+        for (int m = 0; m < G.size; ++m) {
+            a.f_sl[m] = G.at<double>(m, G.off_fsl[par]);
+            a.f_shell[m] = G.at<double>(m, G.off_fshell[par]);
+            a.x_shell[m] = G.at<double>(m, G.off_xshell[par]);
+        }
+        const long long work = 3 * n_fw + n_sw;
+        if (work > 0) {
+            const unsigned nblk = (unsigned)std::min<long long>((work + 255) / 256, 4LL * df.info.num_sms);
+            group_push_kernel<<<nblk, 256, 0, fl->cur>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            count_launch(1);
+            fl->launches += 1;
+        }
+    }
+    // 2. every member's strengths have landed here
+    SKB_TRY(group_flag(fl, 0, true, true));
+    const double *f_sl = G.at<double>(G.rank, G.off_fsl[par]);
+    const double *f_shell = G.at<double>(G.rank, G.off_fshell[par]);
+    double *u_part = G.at<double>(G.rank, G.off_upart);
+    // 3. v = fc.flow(r_all, fw, eta)  (system.cpp:299): own block rows of the symmetric fiber-fiber interaction
+    //    (partial sums for ALL fiber nodes -> u_part) + own shell / body rows (complete -> d_v)
+    if (fl->n_fibers > 0 && df.n_trg > 0) {
+        if (G.use_sym) {
+            SKB_TRY(fl->scratch_u.ensure((size_t)df.n_trg * 24));
+            EvalOpts o;
+            o.d_u_sym = u_part;
+            o.sym_accumulate = 0;
+            o.d_u_rem = d_v + 3 * n_fw;
+            SKB_TRY(eval_on_device(fl->fib[1], df, SKB_STOKESLET, kPacked, f_sl, 0.0, (double *)fl->scratch_u.ptr, 0,
+                                   fl->cur, false, &fl->launches, nullptr, 1.0 / eta, o));
+            if (!fl->fib[1]->last_was_sym)
+                return set_error(SKB_ERR_STATE, "group member %d: the symmetric kernel declined (memory for the reverse "
+                                                "partials?); lower SKB_SYM_MAX_BYTES pressure or use fewer nodes per GPU",
+                                 G.rank);
+            fl->pairs += nf * nf / G.size + nf * (n_sw + n_bw);
+            SKB_TRY(group_flag(fl, 1, true, false)); // my partial sums are complete
+        } else {
+            SKB_TRY(eval_on_device(fl->fib[1], df, SKB_STOKESLET, kPacked, f_sl, 0.0, d_v, 0, fl->cur, false,
+                                   &fl->launches, nullptr, 1.0 / eta));
+            fl->pairs += nf * df.n_trg;
+        }
+    } else if (fl->n_win > 0) {
+        CUDA_TRY(cudaMemsetAsync(d_v, 0, (size_t)fl->n_win * 24, fl->cur));
+    }
+    const bool fib_rows_pending = G.use_sym && fl->n_fibers > 0; // d_v's fiber rows are not written yet
+    // 4. v_fibers, v_bodies += shell.flow(r_fibbody, x_shell, eta)   (system.cpp:304,313-315)
+    bool fib_rows_set = !fib_rows_pending;
+    if (ns > 0 && n_fw + n_bw > 0) {
+        DeviceState &dsh = fl->shell[1]->devs[0];
+        SKB_TRY(fl->tmp.ensure((size_t)(n_fw + n_bw) * 24 + 8));
+        double *d_tmp = (double *)fl->tmp.ptr;
+        SKB_TRY(eval_on_device(fl->shell[1], dsh, SKB_STRESSLET, kPacked, f_shell, 2.0 * eta, d_tmp, 0, fl->cur, false,
+                               &fl->launches, nullptr, 1.0 / eta));
+        fl->pairs += ns * dsh.n_trg;
+        const int bs = 256;
+        if (n_fw > 0) {
+            if (fib_rows_pending) {
+                CUDA_TRY(cudaMemcpyAsync(d_v, d_tmp, (size_t)n_fw * 24, cudaMemcpyDeviceToDevice, fl->cur));
+                fib_rows_set = true;
+            } else {
+                add_inplace_kernel<<<(unsigned)((3 * n_fw + bs - 1) / bs), bs, 0, fl->cur>>>(d_v, d_tmp, 3 * n_fw);
+                count_launch(1);
+                fl->launches += 1;
+            }
+        }
+        if (n_bw > 0) {
+            add_inplace_kernel<<<(unsigned)((3 * n_bw + bs - 1) / bs), bs, 0, fl->cur>>>(
+                d_v + 3 * (n_fw + n_sw), d_tmp + 3 * n_fw, 3 * n_bw);
+            count_launch(1);
+            fl->launches += 1;
+        }
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (!fib_rows_set && n_fw > 0)
+        CUDA_TRY(cudaMemsetAsync(d_v, 0, (size_t)n_fw * 24, fl->cur));
+    // 5. v_all += bc.flow(r_all, x_bodies, body_link_conditions, eta)     (system.cpp:316)
+    SKB_TRY(bodies_dev(fl, fl->body[1], d_bd, d_f, d_t, eta, d_v, 1));
+    // 6. PULL: own fiber rows += sum over the members' partial sums (reduce-scatter fused with the accumulation)
+    if (fib_rows_pending) {
+        SKB_TRY(group_flag(fl, 1, false, true));
+        if (n_fw > 0) {
+            GroupPullArgs a;
+            for (int m = 0; m < G.size; ++m)
+                a.u_part[m] = G.at<double>(m, G.off_upart);
+            a.size = G.size;
+            a.fa = fl->fa;
+            a.n_f = n_fw;
+            a.v = d_v;
+            a.accumulate = 1;
+            group_pull_kernel<<<(unsigned)((3 * n_fw + 255) / 256), 256, 0, fl->cur>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            count_launch(1);
+            fl->launches += 1;
+        }
+    }
+    // 7. self term of the own fibers (fcfd.cpp:203-210), unless the kernels already skipped intra-fiber pairs
+    if (n_fw > 0 && !df.src[SKB_STOKESLET].excl) {
+        const size_t smem = (size_t)fl->max_fiber_nodes * 6 * sizeof(double);
+        fiber_self_subtract_kernel<<<fl->n_fibers, 128, smem, fl->cur>>>(
+            (const double *)fl->r_fib.ptr, f_sl, (const long long *)fl->fiber_offset.ptr, 1.0 / (8.0 * M_PI * eta),
+            kReg * kReg, kEps, d_v, fl->fa, fl->fb);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        fl->launches += 1;
+    }
+    return SKB_OK;
+}
+
 // device-side matvec flow on fl->cur: all strengths resident, d_v = window rows of v_all
 static int matvec_core(skb_flow *fl, const double *d_ff, const double *d_sd, const double *d_bd, const double *d_f,
                        const double *d_t, double eta, double *d_v) {
+    if (fl->grp.size > 1)
+        return matvec_core_group(fl, d_ff, d_sd, d_bd, d_f, d_t, eta, d_v);
     const long long ns = fl->n_shell;
     const long long n_win = fl->n_win, n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba;
     if (n_win == 0)
@@ -786,6 +994,125 @@ static int matvec_core(skb_flow *fl, const double *d_ff, const double *d_sd, con
     }
     // v_all += bc.flow(r_all, x_bodies, body_link_conditions, eta)     system.cpp:316
     SKB_TRY(bodies_dev(fl, fl->body[1], d_bd, d_f, d_t, eta, d_v, 1));
+    return SKB_OK;
+}
+
+// ---- group membership (multi-GPU through peer memory, group_kernels.cuh) ------------------------------------------
+} // extern "C"
+
+static void group_release(skb_flow *fl) {
+    skb_flow::Group &G = fl->grp;
+    cudaSetDevice(fl->dev);
+    for (int m = 0; m < G.size; ++m)
+        if (m != G.rank && G.peer[m] && G.peer_ipc[m])
+            cudaIpcCloseMemHandle(G.peer[m]);
+    if (G.window)
+        cudaFree(G.window);
+    G = skb_flow::Group();
+}
+
+extern "C" {
+
+int skb_flow_group_init(skb_flow *fl, int rank, int size) {
+    if (!fl || size < 1 || size > kMaxGroup || rank < 0 || rank >= size)
+        return set_error(SKB_ERR_INVALID, "skb_flow_group_init: need 0 <= rank < size <= %d", kMaxGroup);
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    CUDA_TRY(cudaStreamSynchronize(fl->stream));
+    group_release(fl);
+    fl->mv_dirty = true;
+    fl->ops_ready = false;
+    fl->geom_version++;
+    if (size == 1)
+        return SKB_OK;
+    skb_flow::Group &G = fl->grp;
+    G.rank = rank;
+    G.size = size;
+    G.n_fib = fl->n_fib;
+    G.n_shell = fl->n_shell;
+    // the same padded sizes the evaluator contexts use (set_sources_impl): the window replaces their f_packed
+    G.n_pad_fib = fl->n_fib > 0 ? fl->fib[1]->devs[0].src[SKB_STOKESLET].n_pad : 0;
+    G.n_pad_shell = fl->n_shell > 0 ? fl->shell[1]->devs[0].src[SKB_STRESSLET].n_pad : 0;
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        const size_t at = off;
+        off += (bytes + 255) & ~(size_t)255;
+        return at;
+    };
+    G.off_flags = take((size_t)(kGroupPhases * kMaxGroup + 8) * 8);
+    for (int b = 0; b < 2; ++b) {
+        G.off_fsl[b] = take((size_t)G.n_pad_fib * 24 + 16);
+        G.off_fshell[b] = take((size_t)G.n_pad_shell * 48 + 16);
+        G.off_xshell[b] = take((size_t)G.n_shell * 24 + 16);
+    }
+    G.off_upart = take((size_t)G.n_fib * 24 + 16);
+    G.window_bytes = off;
+    CUDA_TRY(cudaMalloc(&G.window, G.window_bytes));
+    CUDA_TRY(cudaMemset(G.window, 0, G.window_bytes)); // flags at epoch 0, strength pads zero for good
+    G.peer[rank] = G.window;
+    return SKB_OK;
+}
+
+int skb_flow_group_export(skb_flow *fl, void *handle) {
+    if (!fl || !handle || !fl->grp.window)
+        return set_error(SKB_ERR_INVALID, "skb_flow_group_export: no group window (skb_flow_group_init with size > 1 first)");
+    static_assert(sizeof(cudaIpcMemHandle_t) == SKB_FLOW_IPC_HANDLE_BYTES, "handle size");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    cudaIpcMemHandle_t h;
+    CUDA_TRY(cudaIpcGetMemHandle(&h, fl->grp.window));
+    std::memcpy(handle, &h, sizeof(h));
+    return SKB_OK;
+}
+
+int skb_flow_group_import(skb_flow *fl, int peer_rank, const void *handle) {
+    if (!fl || !handle || !fl->grp.window || peer_rank < 0 || peer_rank >= fl->grp.size || peer_rank == fl->grp.rank)
+        return set_error(SKB_ERR_INVALID, "skb_flow_group_import: bad arguments");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, sizeof(h));
+    void *p = nullptr;
+    CUDA_TRY(cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess));
+    fl->grp.peer[peer_rank] = p;
+    fl->grp.peer_ipc[peer_rank] = true;
+    return SKB_OK;
+}
+
+int skb_flow_group_connect(skb_flow *fl, int peer_rank, skb_flow *peer) {
+    if (!fl || !peer || !fl->grp.window || !peer->grp.window || peer_rank < 0 || peer_rank >= fl->grp.size ||
+        peer_rank == fl->grp.rank || peer->grp.rank != peer_rank || peer->grp.size != fl->grp.size)
+        return set_error(SKB_ERR_INVALID, "skb_flow_group_connect: bad arguments");
+    if (peer->grp.window_bytes != fl->grp.window_bytes || peer->grp.n_fib != fl->grp.n_fib ||
+        peer->grp.n_shell != fl->grp.n_shell)
+        return set_error(SKB_ERR_INVALID, "skb_flow_group_connect: the two members were laid out for different geometries");
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    if (peer->dev != fl->dev) {
+        int can = 0;
+        CUDA_TRY(cudaDeviceCanAccessPeer(&can, fl->dev, peer->dev));
+        if (!can)
+            return set_error(SKB_ERR_CUDA, "device %d cannot address device %d (no NVLink / P2P path)", fl->dev, peer->dev);
+        cudaError_t e = cudaDeviceEnablePeerAccess(peer->dev, 0);
+        if (e == cudaErrorPeerAccessAlreadyEnabled)
+            (void)cudaGetLastError();
+        else if (e != cudaSuccess)
+            return set_error(SKB_ERR_CUDA, "cudaDeviceEnablePeerAccess(%d -> %d): %s", fl->dev, peer->dev,
+                             cudaGetErrorString(e));
+    }
+    fl->grp.peer[peer_rank] = peer->grp.window;
+    fl->grp.peer_ipc[peer_rank] = false;
+    return SKB_OK;
+}
+
+int skb_flow_group_error(skb_flow *fl, int *missing_peer) {
+    if (!fl || !missing_peer)
+        return set_error(SKB_ERR_INVALID, "skb_flow_group_error: NULL");
+    *missing_peer = -1;
+    if (!fl->grp.window)
+        return SKB_OK;
+    unsigned long long w = 0;
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    CUDA_TRY(cudaMemcpy(&w, (char *)fl->grp.window + fl->grp.off_flags + (size_t)kGroupPhases * kMaxGroup * 8, 8,
+                        cudaMemcpyDeviceToHost));
+    if (w)
+        *missing_peer = (int)(w - 1);
     return SKB_OK;
 }
 
@@ -1258,6 +1585,60 @@ int skb_flow_fiber_matvec_device(skb_flow *fl, const double *d_x_fibers, const d
 
 } // extern "C"
 
+// System::apply_matvec (system.cpp:298-319) on fl->cur, everything device resident.  Inputs are the OWN slices of a
+// group member (all of them without a group): d_x 4 per own fiber node, d_xs 3 per own periphery row, body inputs
+// complete, d_link 7 per own fiber or NULL.  Outputs: d_res_fib 4 per own node, d_out_shell 3 per own periphery row
+// (res_shell when dn != NULL, else v_shell), d_v_bodies 3 per own body row; any of them may be NULL when empty.
+static int apply_matvec_core(skb_flow *fl, skb_dense *dn, const double *d_x, const double *d_xs, const double *d_bd,
+                             const double *d_f, const double *d_t, const double *d_link, double eta, double *d_res_fib,
+                             double *d_out_shell, double *d_v_bodies) {
+    const long long n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba;
+    SKB_TRY(fl->in_fib.ensure((size_t)n_fw * 24 + 8));
+    SKB_TRY(fl->vel.ensure((size_t)fl->n_win * 24 + 8));
+    // MatrixXd fw = fc.apply_fiber_force(x_fibers)                       system.cpp:298
+    SKB_TRY(fiber_force_dev(fl, d_x, (double *)fl->in_fib.ptr));
+    // v_all of system.cpp:299-316 (own rows)
+    SKB_TRY(matvec_core(fl, (const double *)fl->in_fib.ptr, d_xs, d_bd, d_f, d_t, eta, (double *)fl->vel.ptr));
+    // res_fibers = fc.matvec(x_fibers, v_fibers, fiber_link_conditions)   system.cpp:318
+    SKB_TRY(fiber_matvec_dev(fl, d_x, (const double *)fl->vel.ptr, d_link, d_res_fib));
+    const double *d_v_shell = (const double *)fl->vel.ptr + 3 * n_fw;
+    if (n_sw > 0 && d_out_shell) {
+        if (dn) {
+            // res_shell = shell.matvec(x_shell, v_shell) = stresslet_plus_complementary_ * x_shell + v_shell
+            // (system.cpp:319, periphery.cpp:38-47): the handle holds this member's rows, x_shell is complete -- the
+            // caller's vector without a group, the gathered copy in the window with one
+            const double *d_x_full = d_xs;
+            if (fl->grp.size > 1)
+                d_x_full = fl->grp.at<double>(fl->grp.rank, fl->grp.off_xshell[fl->grp.epoch & 1]);
+            SKB_TRY(skb_dense_apply_device(dn, SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY, d_x_full, d_v_shell, d_out_shell,
+                                           fl->cur));
+            fl->launches += 1;
+        } else {
+            CUDA_TRY(cudaMemcpyAsync(d_out_shell, d_v_shell, (size_t)n_sw * 24, cudaMemcpyDeviceToDevice, fl->cur));
+        }
+    }
+    if (n_bw > 0 && d_v_bodies)
+        CUDA_TRY(cudaMemcpyAsync(d_v_bodies, (const double *)fl->vel.ptr + 3 * (n_fw + n_sw), (size_t)n_bw * 24,
+                                 cudaMemcpyDeviceToDevice, fl->cur));
+    return SKB_OK;
+}
+
+static int check_dense_handle(skb_flow *fl, skb_dense *dn, const char *who) {
+    int dn_dev = -1;
+    SKB_TRY(skb_dense_device(dn, 0, &dn_dev));
+    if (fl->dev != dn_dev)
+        return set_error(SKB_ERR_INVALID, "%s: the flow is on device %d, the dense handle on device %d", who, fl->dev,
+                         dn_dev);
+    SKB_TRY(prepare_matvec_targets(fl));
+    int64_t rows = 0, cols = 0;
+    SKB_TRY(skb_dense_shape(dn, SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY, &rows, &cols));
+    const long long want_rows = 3 * (fl->sb - fl->sa);
+    if (rows != want_rows || cols != 3 * fl->n_shell)
+        return set_error(SKB_ERR_INVALID, "%s: stresslet_plus_complementary is %lld x %lld, need the %lld own rows x %lld",
+                         who, (long long)rows, (long long)cols, want_rows, 3 * fl->n_shell);
+    return SKB_OK;
+}
+
 // shared body of skb_flow_apply_matvec / skb_flow_apply_matvec_dense; dn != NULL: out_shell = res_shell
 static int apply_matvec_impl(skb_flow *fl, skb_dense *dn, const double *x_fibers, const double *shell_density,
                              const double *body_densities, const double *body_forces_torques,
@@ -1275,9 +1656,10 @@ static int apply_matvec_impl(skb_flow *fl, skb_dense *dn, const double *x_fibers
     if (n_all == 0)
         return SKB_OK;
     SKB_TRY(prepare_matvec_targets(fl));
-    if (fl->n_win != n_all)
+    if (fl->n_win != n_all || fl->grp.size > 1)
         return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec needs the full target window (have %lld of %lld "
-                                          "rows); with one rank per GPU use the *_device calls", fl->n_win, n_all);
+                                          "rows); group members use skb_flow_apply_matvec_device / skb_mflow_*",
+                         fl->n_win, n_all);
     std::vector<double> f, t;
     if (fl->n_bodies > 0)
         split_forces_torques(body_forces_torques, fl->n_bodies, f, t);
@@ -1292,37 +1674,21 @@ static int apply_matvec_impl(skb_flow *fl, skb_dense *dn, const double *x_fibers
     SKB_TRY(upload(fl, fl->in_body, body_densities, (size_t)nb * 3));
     SKB_TRY(upload(fl, fl->in_force, f.data(), f.size()));
     SKB_TRY(upload(fl, fl->in_torque, t.data(), t.size()));
-    SKB_TRY(fl->in_fib.ensure((size_t)nf * 24 + 8));
-    SKB_TRY(fl->vel.ensure((size_t)n_all * 24));
+    SKB_TRY(fl->res_shell.ensure((size_t)ns * 24 + 8));
+    SKB_TRY(fl->tmp_b.ensure((size_t)nb * 24 + 8));
     CUDA_TRY(cudaEventRecord(fl->ev0, fl->stream));
-    // MatrixXd fw = fc.apply_fiber_force(x_fibers)                       system.cpp:298
-    SKB_TRY(fiber_force_dev(fl, (const double *)fl->x_fib.ptr, (double *)fl->in_fib.ptr));
-    // v_all of system.cpp:299-316
-    SKB_TRY(matvec_core(fl, (const double *)fl->in_fib.ptr, (const double *)fl->in_shell.ptr,
-                        (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
-                        (const double *)fl->in_torque.ptr, eta, (double *)fl->vel.ptr));
-    // res_fibers = fc.matvec(x_fibers, v_fibers, fiber_link_conditions)   system.cpp:318
-    SKB_TRY(fiber_matvec_dev(fl, (const double *)fl->x_fib.ptr, (const double *)fl->vel.ptr,
-                             fiber_link_conditions ? (const double *)fl->vb.ptr : nullptr,
-                             (double *)fl->res_fib.ptr));
-    const double *d_shell_out = (const double *)fl->vel.ptr + 3 * nf;
-    if (dn && ns) {
-        // res_shell = shell.matvec(x_shell, v_shell) = stresslet_plus_complementary_ * x_shell + v_shell
-        // (system.cpp:319, periphery.cpp:38-47); x_shell is the density already on the device
-        SKB_TRY(fl->res_shell.ensure((size_t)ns * 24));
-        SKB_TRY(skb_dense_apply_device(dn, SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY, (const double *)fl->in_shell.ptr,
-                                       d_shell_out, (double *)fl->res_shell.ptr, fl->stream));
-        fl->launches += 1;
-        d_shell_out = (const double *)fl->res_shell.ptr;
-    }
+    SKB_TRY(apply_matvec_core(fl, dn, (const double *)fl->x_fib.ptr, (const double *)fl->in_shell.ptr,
+                              (const double *)fl->in_body.ptr, (const double *)fl->in_force.ptr,
+                              (const double *)fl->in_torque.ptr,
+                              (nf && fiber_link_conditions) ? (const double *)fl->vb.ptr : nullptr, eta,
+                              (double *)fl->res_fib.ptr, (double *)fl->res_shell.ptr, (double *)fl->tmp_b.ptr));
     CUDA_TRY(cudaEventRecord(fl->ev1, fl->stream));
     if (nf)
         CUDA_TRY(cudaMemcpyAsync(res_fibers, fl->res_fib.ptr, (size_t)nf * 32, cudaMemcpyDeviceToHost, fl->stream));
     if (ns)
-        CUDA_TRY(cudaMemcpyAsync(v_shell, d_shell_out, (size_t)ns * 24, cudaMemcpyDeviceToHost, fl->stream));
+        CUDA_TRY(cudaMemcpyAsync(v_shell, fl->res_shell.ptr, (size_t)ns * 24, cudaMemcpyDeviceToHost, fl->stream));
     if (nb)
-        CUDA_TRY(cudaMemcpyAsync(v_bodies, (const double *)fl->vel.ptr + 3 * (nf + ns), (size_t)nb * 24,
-                                 cudaMemcpyDeviceToHost, fl->stream));
+        CUDA_TRY(cudaMemcpyAsync(v_bodies, fl->tmp_b.ptr, (size_t)nb * 24, cudaMemcpyDeviceToHost, fl->stream));
     CUDA_TRY(cudaEventRecord(fl->evt1, fl->stream));
     return finish_stats(fl);
 }
@@ -1343,17 +1709,37 @@ int skb_flow_apply_matvec_dense(skb_flow *fl, skb_dense *dn, const double *x_fib
                                 double *res_shell, double *v_bodies) {
     if (!fl || !dn)
         return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec_dense: NULL handle");
-    if (fl->dev != 0) // a single-device skb_dense handle lives on device 0 (skb_dense_create)
-        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec_dense: the flow is on device %d, the dense handle on "
-                                          "device 0", fl->dev);
-    int64_t rows = 0, cols = 0;
-    SKB_TRY(skb_dense_shape(dn, SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY, &rows, &cols));
-    if (rows != 3 * fl->n_shell || cols != 3 * fl->n_shell)
-        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec_dense: stresslet_plus_complementary is %lld x %lld, the "
-                                          "periphery has %lld nodes (need %lld x %lld)", (long long)rows,
-                         (long long)cols, fl->n_shell, 3 * fl->n_shell, 3 * fl->n_shell);
+    SKB_TRY(check_dense_handle(fl, dn, "skb_flow_apply_matvec_dense"));
     return apply_matvec_impl(fl, dn, x_fibers, x_shell, body_densities, body_forces_torques, fiber_link_conditions,
                              eta, res_fibers, res_shell, v_bodies);
+}
+
+int skb_flow_apply_matvec_device(skb_flow *fl, skb_dense *dn, const double *d_x_fibers, const double *d_x_shell,
+                                 const double *d_body_densities, const double *d_body_forces,
+                                 const double *d_body_torques, const double *d_fiber_link_conditions, double eta,
+                                 double *d_res_fibers, double *d_out_shell, double *d_v_bodies, void *stream) {
+    if (!fl || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec_device: bad arguments");
+    SKB_TRY(need_ops(fl, "skb_flow_apply_matvec_device"));
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    begin_stats(fl);
+    SKB_TRY(prepare_matvec_targets(fl));
+    if (dn)
+        SKB_TRY(check_dense_handle(fl, dn, "skb_flow_apply_matvec_device"));
+    const long long n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba;
+    if ((n_fw > 0 && (!d_x_fibers || !d_res_fibers)) || (n_sw > 0 && (!d_x_shell || !d_out_shell)) ||
+        (fl->n_body > 0 && !d_body_densities) || (n_bw > 0 && !d_v_bodies) ||
+        (fl->n_bodies > 0 && (!d_body_forces || !d_body_torques)))
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec_device: NULL argument for a non-empty class");
+    if (fl->grp.size == 1 && fl->n_win == 0)
+        return SKB_OK;
+    fl->cur = (cudaStream_t)stream;
+    SKB_TRY(apply_matvec_core(fl, dn, d_x_fibers, d_x_shell, d_body_densities, d_body_forces, d_body_torques,
+                              d_fiber_link_conditions, eta, d_res_fibers, d_out_shell, d_v_bodies));
+    fl->stats.device_ms = fl->stats.total_ms = 0;
+    fl->stats.n_pairs = fl->pairs;
+    fl->stats.launches = fl->launches;
+    return SKB_OK;
 }
 
 int skb_flow_last_stats(const skb_flow *fl, skb_flow_stats *out) {

@@ -705,6 +705,7 @@ static long long sym_mem_budget() {
         return cached = 8LL << 30;
     return cached = std::max<long long>(8LL << 30, (long long)(0.30 * (double)total_b));
 }
+long long sym_block_nodes() { return (long long)kSymThreads * kSymT; }
 static int sym_owned_rows(int nb, int part, int parts) {
     int n = 0;
     for (int I = 0; I < nb; ++I)
@@ -984,7 +985,7 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
     }
     const long long n_trg_std = d.n_trg - n_sym; // targets beyond the square block go through the plain kernel
     const double *d_r_trg_std = (const double *)d.r_trg.ptr + 3 * n_sym;
-    double *d_u_std = d_u_out + 3 * n_sym;
+    double *d_u_std = (n_sym > 0 && opts.d_u_rem) ? opts.d_u_rem : d_u_out + 3 * n_sym;
     const double scale = scale_mul * (kind == SKB_STOKESLET ? 1.0 : -3.0) / (8.0 * M_PI);
     cudaStream_t st_std = st;
     if (n_sym > 0 && n_trg_std > 0) { // fork: the remainder fills the SMs the symmetric kernel's tail leaves idle
