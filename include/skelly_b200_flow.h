@@ -217,6 +217,47 @@ typedef struct skb_flow_stats {
 } skb_flow_stats;
 SKB_API int skb_flow_last_stats(const skb_flow *fl, skb_flow_stats *out);
 
+/* ---- skb_mflow: ONE process driving n GPUs ---------------------------------------------------------------------
+ * The multi-device form the reference's rule "direct evaluators need a single MPI rank" (system.cpp:618-623) admits.
+ * Same calls and array conventions as skb_flow, complete host arrays in and out; internally one group member per
+ * device (see the group section above), each driven by its own host thread.  Whole fibers (balanced by node count),
+ * periphery rows and body rows are block-partitioned over the devices; the periphery's dense operators are stored by
+ * row blocks (periphery.cpp:387-417).  devices == NULL: 0..n-1.  (A device may be listed more than once: that
+ * exercises the exchange protocol on a single GPU and is meant for tests.) */
+typedef struct skb_mflow skb_mflow;
+SKB_API int skb_mflow_create(const int *devices, int n, skb_mflow **out);
+SKB_API int skb_mflow_destroy(skb_mflow *mf);
+SKB_API int skb_mflow_n_devices(const skb_mflow *mf, int *n);
+SKB_API int skb_mflow_set_fibers(skb_mflow *mf, const double *r_fib, const int *n_nodes, const double *length,
+                                 int n_fibers);
+SKB_API int skb_mflow_set_periphery(skb_mflow *mf, const double *node_pos, const double *node_normal, int64_t n_nodes);
+SKB_API int skb_mflow_set_bodies(skb_mflow *mf, const double *node_pos, const double *node_normal, int64_t n_nodes,
+                                 const double *centers, int n_bodies);
+SKB_API int skb_mflow_set_self_exclusion(skb_mflow *mf, int fused);
+/* which fibers / periphery rows / body rows device `member` owns (any pointer may be NULL) */
+SKB_API int skb_mflow_partition(skb_mflow *mf, int member, int *fiber_begin, int *fiber_end, int64_t *shell_begin,
+                                int64_t *shell_end, int64_t *body_begin, int64_t *body_end);
+SKB_API int skb_mflow_set_fiber_class(skb_mflow *mf, int n_nodes, const double *D_1_0, const double *P_downsample_bc);
+/* complete arrays of ALL fibers, as skb_flow_set_fiber_operators without a window; every device keeps its own slice */
+SKB_API int skb_mflow_set_fiber_operators(skb_mflow *mf, const double *A, const double *force_operator,
+                                          const double *xs, const double *length_prev, const int *plus_bc_velocity);
+SKB_API int skb_mflow_set_fiber_preconditioner(skb_mflow *mf, const double *A_inv);
+/* op = skb_dense_op (skelly_b200_dense.h); A row-major (3 N_s) x (3 N_s) */
+SKB_API int skb_mflow_set_dense(skb_mflow *mf, int op, const double *A_rowmajor, int64_t n_rows, int64_t n_cols);
+SKB_API int skb_mflow_matvec(skb_mflow *mf, const double *fib_forces, const double *shell_density,
+                             const double *body_densities, const double *body_forces_torques, double eta,
+                             double *v_all);
+/* out_shell = res_shell when skb_mflow_set_dense(SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY, ...) was called, else v_shell */
+SKB_API int skb_mflow_apply_matvec(skb_mflow *mf, const double *x_fibers, const double *x_shell,
+                                   const double *body_densities, const double *body_forces_torques,
+                                   const double *fiber_link_conditions, double eta, double *res_fibers,
+                                   double *out_shell, double *v_bodies);
+/* System::velocity_at_targets (system.cpp:330-384): targets block-partitioned over the devices */
+SKB_API int skb_mflow_velocity_at_targets(skb_mflow *mf, const double *r_trg, int64_t n_trg, const double *fib_forces,
+                                          const double *shell_density, const double *body_densities,
+                                          const double *body_forces_torques, double eta, double *vel);
+SKB_API int skb_mflow_last_stats(const skb_mflow *mf, skb_flow_stats *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -6,9 +6,9 @@ ctypes binding used by the tests and bench.py.  There is no CPU fallback: import
 GPU (so the C-ABI export test can run), every compute call needs a B200.
 """
 from .capi import (DENSE_M_INV, DENSE_STRESSLET_PLUS_COMPLEMENTARY, KERNEL_STOKESLET, KERNEL_STRESSLET, Context, Dense,
-                   Flow, SkbError, build_library, library, library_path,
+                   Flow, MultiFlow, SkbError, build_library, library, library_path,
                    stokeslet_direct, stresslet_direct)
 
 __all__ = ["DENSE_M_INV", "DENSE_STRESSLET_PLUS_COMPLEMENTARY", "KERNEL_STOKESLET", "KERNEL_STRESSLET", "Context",
-           "Dense", "Flow", "SkbError", "build_library", "library",
+           "Dense", "Flow", "MultiFlow", "SkbError", "build_library", "library",
            "library_path", "stokeslet_direct", "stresslet_direct"]

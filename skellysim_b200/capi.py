@@ -113,6 +113,29 @@ def library() -> C.CDLL:
         "skb_flow_velocity_at_targets": ([ctxp, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_set_target_window": ([ctxp, C.c_int64, C.c_int64], C.c_int),
         "skb_flow_set_self_exclusion": ([ctxp, C.c_int], C.c_int),
+        "skb_flow_group_init": ([ctxp, C.c_int, C.c_int], C.c_int),
+        "skb_flow_group_export": ([ctxp, C.c_void_p], C.c_int),
+        "skb_flow_group_import": ([ctxp, C.c_int, C.c_void_p], C.c_int),
+        "skb_flow_group_connect": ([ctxp, C.c_int, ctxp], C.c_int),
+        "skb_flow_group_error": ([ctxp, C.POINTER(C.c_int)], C.c_int),
+        "skb_flow_apply_matvec_device": ([ctxp, ctxp] + [C.c_void_p] * 6 + [C.c_double] + [C.c_void_p] * 4, C.c_int),
+        "skb_mflow_create": ([C.POINTER(C.c_int), C.c_int, C.POINTER(ctxp)], C.c_int),
+        "skb_mflow_destroy": ([ctxp], C.c_int),
+        "skb_mflow_n_devices": ([ctxp, C.POINTER(C.c_int)], C.c_int),
+        "skb_mflow_set_fibers": ([ctxp, _dp, C.POINTER(C.c_int), _dp, C.c_int], C.c_int),
+        "skb_mflow_set_periphery": ([ctxp, _dp, _dp, C.c_int64], C.c_int),
+        "skb_mflow_set_bodies": ([ctxp, _dp, _dp, C.c_int64, _dp, C.c_int], C.c_int),
+        "skb_mflow_set_self_exclusion": ([ctxp, C.c_int], C.c_int),
+        "skb_mflow_partition": ([ctxp, C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)] + [C.POINTER(C.c_int64)] * 4,
+                                C.c_int),
+        "skb_mflow_set_fiber_class": ([ctxp, C.c_int, _dp, _dp], C.c_int),
+        "skb_mflow_set_fiber_operators": ([ctxp, _dp, _dp, _dp, _dp, C.POINTER(C.c_int)], C.c_int),
+        "skb_mflow_set_fiber_preconditioner": ([ctxp, _dp], C.c_int),
+        "skb_mflow_set_dense": ([ctxp, C.c_int, _dp, C.c_int64, C.c_int64], C.c_int),
+        "skb_mflow_matvec": ([ctxp, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
+        "skb_mflow_apply_matvec": ([ctxp, _dp, _dp, _dp, _dp, _dp, C.c_double, _dp, _dp, _dp], C.c_int),
+        "skb_mflow_velocity_at_targets": ([ctxp, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
+        "skb_mflow_last_stats": ([ctxp, C.POINTER(FlowStats)], C.c_int),
         "skb_flow_set_target_ranges": ([ctxp, C.c_int, C.c_int] + [C.c_int64] * 4, C.c_int),
         "skb_flow_apply_fiber_force_device": ([ctxp, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "skb_flow_fiber_matvec_device": ([ctxp] + [C.c_void_p] * 5, C.c_int),
@@ -129,6 +152,8 @@ def library() -> C.CDLL:
         "skb_dense_shape": ([ctxp, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)], C.c_int),
         # include/skelly_b200_dense.h
         "skb_dense_create": ([C.c_int, C.POINTER(ctxp)], C.c_int),
+        "skb_dense_create_on": ([C.POINTER(C.c_int), C.c_int, C.POINTER(ctxp)], C.c_int),
+        "skb_dense_device": ([ctxp, C.c_int, C.POINTER(C.c_int)], C.c_int),
         "skb_dense_destroy": ([ctxp], C.c_int),
         "skb_dense_set_matrix": ([ctxp, C.c_int, _dp, C.c_int64, C.c_int64], C.c_int),
         "skb_dense_apply": ([ctxp, C.c_int, _dp, _dp, _dp], C.c_int),
@@ -567,9 +592,163 @@ class Flow:
                                                    _p(v_b)))
         return res, v_s, v_b
 
+    def apply_matvec_device(self, dense, d_x_fibers: int, d_x_shell: int, d_body_densities: int, d_body_forces: int,
+                            d_body_torques: int, d_fiber_link_conditions: int, eta: float, d_res_fibers: int,
+                            d_out_shell: int, d_v_bodies: int, stream: int = 0):
+        """System::apply_matvec with every operand already on the device (addresses as ints, 0 = NULL); OWN slices
+        for a group member.  Asynchronous on `stream`."""
+        vp = lambda a: C.c_void_p(a) if a else None
+        _check(library().skb_flow_apply_matvec_device(self._h, dense._h if dense is not None else None, vp(d_x_fibers),
+                                                      vp(d_x_shell), vp(d_body_densities), vp(d_body_forces),
+                                                      vp(d_body_torques), vp(d_fiber_link_conditions), float(eta),
+                                                      vp(d_res_fibers), vp(d_out_shell), vp(d_v_bodies), vp(stream)))
+
+    # ---- multi-GPU groups (peer memory) ----
+    def group_init(self, rank: int, size: int):
+        _check(library().skb_flow_group_init(self._h, int(rank), int(size)))
+
+    def group_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        _check(library().skb_flow_group_export(self._h, C.cast(buf, C.c_void_p)))
+        return buf.raw
+
+    def group_import(self, peer_rank: int, handle: bytes):
+        assert len(handle) == 64
+        buf = C.create_string_buffer(handle, 64)
+        _check(library().skb_flow_group_import(self._h, int(peer_rank), C.cast(buf, C.c_void_p)))
+
+    def group_connect(self, peer_rank: int, peer: "Flow"):
+        _check(library().skb_flow_group_connect(self._h, int(peer_rank), peer._h))
+
+    def group_error(self) -> int:
+        m = C.c_int(-1)
+        _check(library().skb_flow_group_error(self._h, C.byref(m)))
+        return m.value
+
     def stats(self) -> dict:
         s = FlowStats()
         _check(library().skb_flow_last_stats(self._h, C.byref(s)))
+        return {k: getattr(s, k) for k, _ in FlowStats._fields_}
+
+
+class MultiFlow:
+    """skb_mflow: ONE process driving n GPUs (include/skelly_b200_flow.h) -- same conventions as Flow, complete host
+    arrays in and out; fibers / periphery rows / body rows are partitioned over the devices, which exchange strengths
+    and partial velocities through peer memory."""
+
+    def __init__(self, devices):
+        devs = list(range(devices)) if isinstance(devices, int) else [int(d) for d in devices]
+        arr = (C.c_int * len(devs))(*devs)
+        self._h = C.c_void_p()
+        _check(library().skb_mflow_create(arr, len(devs), C.byref(self._h)))
+        self.devices = devs
+        self.n_fib = self.n_shell = self.n_body = self.n_bodies = self.n_fibers = 0
+
+    def close(self):
+        if getattr(self, "_h", None) and self._h.value:
+            library().skb_mflow_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_fibers(self, r_fib, n_nodes, lengths):
+        r_fib = _arr(r_fib, 3)
+        n_nodes = np.ascontiguousarray(n_nodes, dtype=np.int32)
+        lengths = np.ascontiguousarray(lengths, dtype=np.float64)
+        assert n_nodes.shape == lengths.shape and int(n_nodes.sum()) == r_fib.shape[0]
+        _check(library().skb_mflow_set_fibers(self._h, _p(r_fib), n_nodes.ctypes.data_as(C.POINTER(C.c_int)),
+                                              _p(lengths), int(n_nodes.shape[0])))
+        self.n_fib, self.n_fibers = r_fib.shape[0], int(n_nodes.shape[0])
+
+    def set_periphery(self, node_pos, node_normal):
+        node_pos, node_normal = _arr(node_pos, 3), _arr(node_normal, 3)
+        _check(library().skb_mflow_set_periphery(self._h, _p(node_pos), _p(node_normal), node_pos.shape[0]))
+        self.n_shell = node_pos.shape[0]
+
+    def set_bodies(self, node_pos, node_normal, centers):
+        node_pos, node_normal, centers = _arr(node_pos, 3), _arr(node_normal, 3), _arr(centers, 3)
+        _check(library().skb_mflow_set_bodies(self._h, _p(node_pos), _p(node_normal), node_pos.shape[0], _p(centers),
+                                              centers.shape[0]))
+        self.n_body, self.n_bodies = node_pos.shape[0], centers.shape[0]
+
+    def set_self_exclusion(self, fused: bool):
+        _check(library().skb_mflow_set_self_exclusion(self._h, int(bool(fused))))
+
+    def partition(self, member: int):
+        f0, f1 = C.c_int(), C.c_int()
+        r = [C.c_int64() for _ in range(4)]
+        _check(library().skb_mflow_partition(self._h, int(member), C.byref(f0), C.byref(f1), *[C.byref(x) for x in r]))
+        return (f0.value, f1.value) + tuple(x.value for x in r)
+
+    def set_fiber_class(self, n_nodes: int, D_1_0, P_downsample_bc):
+        n = int(n_nodes)
+        D = np.asfortranarray(D_1_0, dtype=np.float64)
+        P = np.asfortranarray(P_downsample_bc, dtype=np.float64)
+        if D.shape != (n, n) or P.shape != (4 * n - 14, 4 * n):
+            raise ValueError(f"class matrices for n={n}: got {D.shape}, {P.shape}")
+        _check(library().skb_mflow_set_fiber_class(self._h, n, _p(D), _p(P)))
+
+    def set_fiber_operators(self, A_list, force_list, xs, length_prev, plus_bc_velocity):
+        A, F = Flow._colmajor_concat(A_list), Flow._colmajor_concat(force_list)
+        xs = _arr(xs, 3)
+        lp = np.ascontiguousarray(length_prev, dtype=np.float64)
+        pl = np.ascontiguousarray(plus_bc_velocity, dtype=np.int32)
+        assert xs.shape[0] == self.n_fib and lp.shape == pl.shape == (self.n_fibers,)
+        _check(library().skb_mflow_set_fiber_operators(self._h, _p(A), _p(F), _p(xs), _p(lp),
+                                                       pl.ctypes.data_as(C.POINTER(C.c_int))))
+
+    def set_fiber_preconditioner(self, A_inv_list):
+        Ai = Flow._colmajor_concat(A_inv_list)
+        _check(library().skb_mflow_set_fiber_preconditioner(self._h, _p(Ai)))
+
+    def set_dense(self, op: int, A):
+        A = np.ascontiguousarray(A, dtype=np.float64)
+        _check(library().skb_mflow_set_dense(self._h, int(op), _p(A), A.shape[0], A.shape[1]))
+        self._has_dense = True
+
+    def matvec(self, fib_forces, shell_density, body_densities, body_forces_torques, eta):
+        a, b, c = _arr(fib_forces, 3), _arr(shell_density, 3), _arr(body_densities, 3)
+        ft = _arr(body_forces_torques, 6)
+        v = np.empty((self.n_fib + self.n_shell + self.n_body, 3))
+        _check(library().skb_mflow_matvec(self._h, _p(a), _p(b), _p(c), _p(ft), float(eta), _p(v)))
+        return v
+
+    def apply_matvec(self, x_fibers, x_shell, body_densities, body_forces_torques, eta, fiber_link_conditions=None):
+        """Returns (res_fibers (4 N_f,), out_shell (N_s,3), v_bodies (N_b,3)); out_shell is res_shell once
+        set_dense(DENSE_STRESSLET_PLUS_COMPLEMENTARY, ...) was called, else v_shell."""
+        x = np.ascontiguousarray(x_fibers, dtype=np.float64).reshape(-1)
+        assert x.shape[0] == 4 * self.n_fib
+        b, c = _arr(x_shell, 3), _arr(body_densities, 3)
+        ft = _arr(body_forces_torques, 6)
+        vb = None if fiber_link_conditions is None else _arr(fiber_link_conditions, 7)
+        res = np.empty(4 * self.n_fib)
+        o_s, v_b = np.empty((self.n_shell, 3)), np.empty((self.n_body, 3))
+        _check(library().skb_mflow_apply_matvec(self._h, _p(x), _p(b), _p(c), _p(ft), None if vb is None else _p(vb),
+                                                float(eta), _p(res), _p(o_s), _p(v_b)))
+        return res, o_s, v_b
+
+    def velocity_at_targets(self, r_trg, fib_forces, shell_density, body_densities, body_forces_torques, eta):
+        r_trg = _arr(r_trg, 3)
+        a, b, c = _arr(fib_forces, 3), _arr(shell_density, 3), _arr(body_densities, 3)
+        ft = _arr(body_forces_torques, 6)
+        vel = np.empty((r_trg.shape[0], 3))
+        _check(library().skb_mflow_velocity_at_targets(self._h, _p(r_trg), r_trg.shape[0], _p(a), _p(b), _p(c), _p(ft),
+                                                       float(eta), _p(vel)))
+        return vel
+
+    def stats(self) -> dict:
+        s = FlowStats()
+        _check(library().skb_mflow_last_stats(self._h, C.byref(s)))
         return {k: getattr(s, k) for k, _ in FlowStats._fields_}
 
 
@@ -581,9 +760,13 @@ class Dense:
     """The periphery's dense operators on the GPU (include/skelly_b200_dense.h): Periphery::matvec and
     Periphery::apply_preconditioner (periphery.cpp:21-47) as row-partitioned GEMVs."""
 
-    def __init__(self, n_gpus: int = 1):
+    def __init__(self, n_gpus: int = 1, device_ids=None):
         self._h = C.c_void_p()
-        _check(library().skb_dense_create(int(n_gpus), C.byref(self._h)))
+        if device_ids is not None:
+            arr = (C.c_int * len(device_ids))(*[int(d) for d in device_ids])
+            _check(library().skb_dense_create_on(arr, len(device_ids), C.byref(self._h)))
+        else:
+            _check(library().skb_dense_create(int(n_gpus), C.byref(self._h)))
         self.shape = {}
 
     def close(self):

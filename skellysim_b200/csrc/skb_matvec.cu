@@ -1750,3 +1750,521 @@ int skb_flow_last_stats(const skb_flow *fl, skb_flow_stats *out) {
 }
 
 } // extern "C"
+
+// =====================================================================================================================
+// skb_mflow -- ONE process, n GPUs (include/skelly_b200_flow.h): the multi-device shape the reference's "direct
+// evaluators need a single rank" rule admits (src/core/system.cpp:618-623).  One group member (skb_flow) per device,
+// connected through peer memory; whole fibers, periphery rows and body rows are block-partitioned over the members.
+// Every member is driven by its own host thread, so the n launch sequences are issued concurrently.
+// =====================================================================================================================
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
+
+namespace {
+class Workers {
+  public:
+    explicit Workers(int n) : n_(n), task_(n), state_(n, 0), rc_(n, 0), msg_(n) {
+        for (int g = 0; g < n; ++g)
+            th_.emplace_back([this, g] { loop(g); });
+    }
+    ~Workers() {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_)
+            t.join();
+    }
+    // run fn(g) on every worker; returns the first non-zero status (its message becomes this thread's last error)
+    int run(const std::function<int(int)> &fn) {
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            for (int g = 0; g < n_; ++g) {
+                task_[g] = fn;
+                state_[g] = 1;
+            }
+        }
+        cv_.notify_all();
+        std::unique_lock<std::mutex> lk(mu_);
+        done_.wait(lk, [this] {
+            for (int g = 0; g < n_; ++g)
+                if (state_[g] != 0)
+                    return false;
+            return true;
+        });
+        for (int g = 0; g < n_; ++g)
+            if (rc_[g] != SKB_OK)
+                return set_error(rc_[g], "device member %d: %s", g, msg_[g].c_str());
+        return SKB_OK;
+    }
+
+  private:
+    void loop(int g) {
+        for (;;) {
+            std::function<int(int)> fn;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                cv_.wait(lk, [this, g] { return stop_ || state_[g] == 1; });
+                if (stop_)
+                    return;
+                fn = task_[g];
+            }
+            const int rc = fn(g);
+            {
+                std::lock_guard<std::mutex> lk(mu_);
+                rc_[g] = rc;
+                msg_[g] = rc == SKB_OK ? "" : last_error();
+                state_[g] = 0;
+            }
+            done_.notify_all();
+        }
+    }
+    int n_;
+    std::vector<std::function<int(int)>> task_;
+    std::vector<int> state_, rc_;
+    std::vector<std::string> msg_;
+    std::vector<std::thread> th_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    bool stop_ = false;
+};
+} // namespace
+
+struct skb_mflow {
+    int n = 0;
+    std::vector<int> devs;
+    std::vector<skb_flow *> m;
+    std::vector<skb_dense *> dn;
+    std::unique_ptr<Workers> workers;
+    // geometry (host copies of what the partition needs)
+    long long n_fib = 0, n_shell = 0, n_body = 0;
+    int n_fibers = 0, n_bodies = 0;
+    std::vector<int> fiber_n;
+    std::vector<long long> fiber_off;
+    // partition: member g owns fibers [f0[g], f1[g]), periphery rows [s0, s1), body rows [b0, b1)
+    std::vector<int> f0, f1;
+    std::vector<long long> s0, s1, b0, b1;
+    bool part_dirty = true;
+    bool has_dense = false;
+    bool ops_ready = false;
+    struct IO { // per-member device buffers of the host-pointer calls
+        DevBuf x, xs, bd, f, t, link, res, outs, vb, ff, v;
+        cudaEvent_t e0 = nullptr, e1 = nullptr;
+    };
+    std::vector<IO> io;
+    skb_flow_stats stats{};
+};
+
+static void mflow_partition(skb_mflow *mf) {
+    const int n = mf->n;
+    mf->f0.assign(n, 0), mf->f1.assign(n, 0);
+    mf->s0.assign(n, 0), mf->s1.assign(n, 0), mf->b0.assign(n, 0), mf->b1.assign(n, 0);
+    // whole fibers, cut where the running node count passes g/n of the total (fcfd.cpp:102-120 splits by fiber count;
+    // by node count balances ragged suspensions as well)
+    int f = 0;
+    for (int g = 0; g < n; ++g) {
+        mf->f0[g] = f;
+        const long long want = mf->n_fib * (g + 1) / n;
+        while (f < mf->n_fibers && (g == n - 1 || mf->fiber_off[(size_t)f + 1] <= want))
+            ++f;
+        if (g == n - 1)
+            f = mf->n_fibers;
+        mf->f1[g] = f;
+    }
+    for (int g = 0; g < n; ++g) {
+        const long long cs = (mf->n_shell + n - 1) / n, cb = (mf->n_body + n - 1) / n;
+        mf->s0[g] = std::min(mf->n_shell, g * cs);
+        mf->s1[g] = std::min(mf->n_shell, (g + 1) * cs);
+        mf->b0[g] = std::min(mf->n_body, g * cb);
+        mf->b1[g] = std::min(mf->n_body, (g + 1) * cb);
+    }
+}
+
+// ranges + group wiring, after any change of the geometry's sizes
+static int mflow_prepare(skb_mflow *mf) {
+    if (!mf->part_dirty)
+        return SKB_OK;
+    mflow_partition(mf);
+    for (int g = 0; g < mf->n; ++g) {
+        SKB_TRY(skb_flow_set_target_ranges(mf->m[g], mf->f0[g], mf->f1[g], mf->s0[g], mf->s1[g], mf->b0[g], mf->b1[g]));
+        SKB_TRY(skb_flow_group_init(mf->m[g], g, mf->n));
+    }
+    for (int g = 0; g < mf->n; ++g)
+        for (int h = 0; h < mf->n; ++h)
+            if (g != h)
+                SKB_TRY(skb_flow_group_connect(mf->m[g], h, mf->m[h]));
+    mf->part_dirty = false;
+    mf->ops_ready = false;
+    return SKB_OK;
+}
+
+extern "C" {
+
+int skb_mflow_create(const int *devices, int n, skb_mflow **out) {
+    if (!out || n < 1 || n > kMaxGroup)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_create: need 1 <= n <= %d devices", kMaxGroup);
+    *out = nullptr;
+    std::unique_ptr<skb_mflow> mf(new skb_mflow);
+    mf->n = n;
+    mf->m.assign(n, nullptr);
+    mf->dn.assign(n, nullptr);
+    mf->io.resize(n);
+    for (int g = 0; g < n; ++g) {
+        mf->devs.push_back(devices ? devices[g] : g);
+        int rc = skb_flow_create(mf->devs[g], &mf->m[g]);
+        if (rc == SKB_OK) {
+            cudaSetDevice(mf->devs[g]);
+            if (cudaEventCreate(&mf->io[g].e0) != cudaSuccess || cudaEventCreate(&mf->io[g].e1) != cudaSuccess)
+                rc = set_error(SKB_ERR_CUDA, "cudaEventCreate failed");
+        }
+        if (rc != SKB_OK) {
+            for (int h = 0; h <= g; ++h)
+                skb_flow_destroy(mf->m[h]);
+            return rc;
+        }
+    }
+    mf->workers.reset(new Workers(n));
+    *out = mf.release();
+    return SKB_OK;
+}
+
+int skb_mflow_destroy(skb_mflow *mf) {
+    if (!mf)
+        return SKB_OK;
+    mf->workers.reset();
+    for (int g = 0; g < mf->n; ++g) {
+        cudaSetDevice(mf->devs[g]);
+        cudaDeviceSynchronize();
+    }
+    for (int g = 0; g < mf->n; ++g) {
+        cudaSetDevice(mf->devs[g]);
+        skb_mflow::IO &io = mf->io[g];
+        DevBuf *bufs[] = {&io.x, &io.xs, &io.bd, &io.f, &io.t, &io.link, &io.res, &io.outs, &io.vb, &io.ff, &io.v};
+        for (DevBuf *b : bufs)
+            b->release();
+        if (io.e0) cudaEventDestroy(io.e0);
+        if (io.e1) cudaEventDestroy(io.e1);
+        skb_dense_destroy(mf->dn[g]);
+        skb_flow_destroy(mf->m[g]);
+    }
+    delete mf;
+    return SKB_OK;
+}
+
+int skb_mflow_n_devices(const skb_mflow *mf, int *n) {
+    if (!mf || !n)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_n_devices: NULL");
+    *n = mf->n;
+    return SKB_OK;
+}
+
+int skb_mflow_set_fibers(skb_mflow *mf, const double *r_fib, const int *n_nodes, const double *length, int n_fibers) {
+    if (!mf || n_fibers < 0)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_fibers: bad arguments");
+    std::vector<long long> off((size_t)n_fibers + 1, 0);
+    for (int f = 0; f < n_fibers; ++f)
+        off[(size_t)f + 1] = off[(size_t)f] + (n_nodes ? n_nodes[f] : 0);
+    const bool resized = off != mf->fiber_off;
+    SKB_TRY(mf->workers->run([&](int g) -> int { return skb_flow_set_fibers(mf->m[g], r_fib, n_nodes, length, n_fibers); }));
+    mf->n_fibers = n_fibers;
+    mf->n_fib = off[(size_t)n_fibers];
+    mf->fiber_off = off;
+    mf->fiber_n.assign(n_nodes, n_nodes + n_fibers);
+    mf->ops_ready = false;
+    if (resized)
+        mf->part_dirty = true;
+    return SKB_OK;
+}
+
+int skb_mflow_set_periphery(skb_mflow *mf, const double *node_pos, const double *node_normal, int64_t n_nodes) {
+    if (!mf || n_nodes < 0)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_periphery: bad arguments");
+    SKB_TRY(mf->workers->run([&](int g) -> int { return skb_flow_set_periphery(mf->m[g], node_pos, node_normal, n_nodes); }));
+    if (mf->n_shell != n_nodes)
+        mf->part_dirty = true;
+    mf->n_shell = n_nodes;
+    return SKB_OK;
+}
+
+int skb_mflow_set_bodies(skb_mflow *mf, const double *node_pos, const double *node_normal, int64_t n_nodes,
+                         const double *centers, int n_bodies) {
+    if (!mf || n_nodes < 0 || n_bodies < 0)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_bodies: bad arguments");
+    SKB_TRY(mf->workers->run(
+        [&](int g) { return skb_flow_set_bodies(mf->m[g], node_pos, node_normal, n_nodes, centers, n_bodies); }));
+    if (mf->n_body != n_nodes)
+        mf->part_dirty = true;
+    mf->n_body = n_nodes;
+    mf->n_bodies = n_bodies;
+    return SKB_OK;
+}
+
+int skb_mflow_set_self_exclusion(skb_mflow *mf, int fused) {
+    if (!mf)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_self_exclusion: NULL");
+    for (int g = 0; g < mf->n; ++g)
+        SKB_TRY(skb_flow_set_self_exclusion(mf->m[g], fused));
+    return SKB_OK;
+}
+
+int skb_mflow_partition(skb_mflow *mf, int member, int *fiber_begin, int *fiber_end, int64_t *shell_begin,
+                        int64_t *shell_end, int64_t *body_begin, int64_t *body_end) {
+    if (!mf || member < 0 || member >= mf->n)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_partition: bad member");
+    SKB_TRY(mflow_prepare(mf));
+    if (fiber_begin) *fiber_begin = mf->f0[member];
+    if (fiber_end) *fiber_end = mf->f1[member];
+    if (shell_begin) *shell_begin = mf->s0[member];
+    if (shell_end) *shell_end = mf->s1[member];
+    if (body_begin) *body_begin = mf->b0[member];
+    if (body_end) *body_end = mf->b1[member];
+    return SKB_OK;
+}
+
+int skb_mflow_set_fiber_class(skb_mflow *mf, int n_nodes, const double *D_1_0, const double *P_downsample_bc) {
+    if (!mf)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_fiber_class: NULL");
+    for (int g = 0; g < mf->n; ++g)
+        SKB_TRY(skb_flow_set_fiber_class(mf->m[g], n_nodes, D_1_0, P_downsample_bc));
+    mf->ops_ready = false;
+    return SKB_OK;
+}
+
+// element offset of fiber f's block in a concatenation of per-fiber (k n) x (4 n) matrices
+static long long op_offset(const skb_mflow *mf, int f, int k) {
+    long long o = 0;
+    for (int i = 0; i < f; ++i)
+        o += (long long)k * 4 * mf->fiber_n[(size_t)i] * mf->fiber_n[(size_t)i];
+    return o;
+}
+
+int skb_mflow_set_fiber_operators(skb_mflow *mf, const double *A, const double *force_operator, const double *xs,
+                                  const double *length_prev, const int *plus_bc_velocity) {
+    if (!mf)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_fiber_operators: NULL");
+    SKB_TRY(mflow_prepare(mf));
+    if (mf->n_fibers > 0 && (!A || !force_operator || !xs || !length_prev || !plus_bc_velocity))
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_fiber_operators: NULL argument");
+    SKB_TRY(mf->workers->run([&](int g) -> int {
+        const int f0 = mf->f0[g];
+        if (mf->f1[g] == f0)
+            return skb_flow_set_fiber_operators(mf->m[g], nullptr, nullptr, nullptr, nullptr, nullptr);
+        return skb_flow_set_fiber_operators(mf->m[g], A + op_offset(mf, f0, 4), force_operator + op_offset(mf, f0, 3),
+                                            xs + 3 * mf->fiber_off[(size_t)f0], length_prev + f0, plus_bc_velocity + f0);
+    }));
+    mf->ops_ready = true;
+    return SKB_OK;
+}
+
+int skb_mflow_set_fiber_preconditioner(skb_mflow *mf, const double *A_inv) {
+    if (!mf || !mf->ops_ready)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_fiber_preconditioner: call skb_mflow_set_fiber_operators first");
+    return mf->workers->run([&](int g) -> int {
+        const int f0 = mf->f0[g];
+        return skb_flow_set_fiber_preconditioner(mf->m[g], mf->f1[g] == f0 ? nullptr : A_inv + op_offset(mf, f0, 4));
+    });
+}
+
+// the periphery's dense operator, rows block-partitioned like the periphery rows (periphery.cpp:387-417)
+int skb_mflow_set_dense(skb_mflow *mf, int op, const double *A_rowmajor, int64_t n_rows, int64_t n_cols) {
+    if (!mf || !A_rowmajor || n_rows != 3 * mf->n_shell || n_cols != 3 * mf->n_shell)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_dense: need the (3 N_s) x (3 N_s) operator of the %lld periphery "
+                                          "nodes set before", mf ? mf->n_shell : 0LL);
+    SKB_TRY(mflow_prepare(mf));
+    SKB_TRY(mf->workers->run([&](int g) -> int {
+        if (!mf->dn[g])
+            SKB_TRY(skb_dense_create_on(&mf->devs[g], 1, &mf->dn[g]));
+        return skb_dense_set_matrix(mf->dn[g], op, A_rowmajor + (size_t)(3 * mf->s0[g]) * (size_t)n_cols,
+                                    3 * (mf->s1[g] - mf->s0[g]), n_cols);
+    }));
+    if (op == SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY)
+        mf->has_dense = true;
+    return SKB_OK;
+}
+
+static int mflow_collect_stats(skb_mflow *mf) {
+    double dev_ms = 0;
+    long long pairs = 0;
+    int launches = 0;
+    for (int g = 0; g < mf->n; ++g) {
+        float ms = 0;
+        cudaSetDevice(mf->devs[g]);
+        if (cudaEventElapsedTime(&ms, mf->io[g].e0, mf->io[g].e1) == cudaSuccess)
+            dev_ms = std::max(dev_ms, (double)ms);
+        else
+            (void)cudaGetLastError();
+        skb_flow_stats st{};
+        skb_flow_last_stats(mf->m[g], &st);
+        pairs += st.n_pairs;
+        launches += st.launches;
+        int missing = -1;
+        SKB_TRY(skb_flow_group_error(mf->m[g], &missing));
+        if (missing >= 0)
+            return set_error(SKB_ERR_STATE, "device member %d timed out waiting for member %d (a peer failed or never "
+                                            "issued the matching call)", g, missing);
+    }
+    mf->stats.device_ms = dev_ms;
+    mf->stats.total_ms = dev_ms;
+    mf->stats.n_pairs = pairs;
+    mf->stats.launches = launches;
+    return SKB_OK;
+}
+
+// v_all over [fibers | periphery | bodies] like skb_flow_matvec; complete host arrays in and out
+int skb_mflow_matvec(skb_mflow *mf, const double *fib_forces, const double *shell_density, const double *body_densities,
+                     const double *body_forces_torques, double eta, double *v_all) {
+    if (!mf || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_mflow_matvec: bad arguments");
+    const long long nf = mf->n_fib, ns = mf->n_shell, nb = mf->n_body;
+    if ((nf > 0 && !fib_forces) || (ns > 0 && !shell_density) || (nb > 0 && !body_densities) ||
+        (mf->n_bodies > 0 && !body_forces_torques) || (nf + ns + nb > 0 && !v_all))
+        return set_error(SKB_ERR_INVALID, "skb_mflow_matvec: NULL input for a non-empty class");
+    SKB_TRY(mflow_prepare(mf));
+    std::vector<double> f, t;
+    if (mf->n_bodies > 0)
+        split_forces_torques(body_forces_torques, mf->n_bodies, f, t);
+    SKB_TRY(mf->workers->run([&](int g) -> int {
+        skb_flow *fl = mf->m[g];
+        skb_mflow::IO &io = mf->io[g];
+        CUDA_TRY(cudaSetDevice(mf->devs[g]));
+        const long long a = mf->fiber_off.empty() ? 0 : mf->fiber_off[(size_t)mf->f0[g]],
+                        b = mf->fiber_off.empty() ? 0 : mf->fiber_off[(size_t)mf->f1[g]];
+        const long long n_fw = b - a, n_sw = mf->s1[g] - mf->s0[g], n_bw = mf->b1[g] - mf->b0[g];
+        cudaStream_t st = fl->stream;
+        auto put = [&](DevBuf &buf, const double *h, size_t n_dbl) -> int {
+            SKB_TRY(buf.ensure(n_dbl * 8 + 8));
+            if (n_dbl)
+                CUDA_TRY(cudaMemcpyAsync(buf.ptr, h, n_dbl * 8, cudaMemcpyHostToDevice, st));
+            return SKB_OK;
+        };
+        SKB_TRY(put(io.ff, fib_forces ? fib_forces + 3 * a : nullptr, (size_t)n_fw * 3));
+        SKB_TRY(put(io.xs, shell_density ? shell_density + 3 * mf->s0[g] : nullptr, (size_t)n_sw * 3));
+        SKB_TRY(put(io.bd, body_densities, (size_t)nb * 3));
+        SKB_TRY(put(io.f, f.data(), f.size()));
+        SKB_TRY(put(io.t, t.data(), t.size()));
+        SKB_TRY(io.v.ensure((size_t)(n_fw + n_sw + n_bw) * 24 + 8));
+        CUDA_TRY(cudaEventRecord(io.e0, st));
+        SKB_TRY(skb_flow_matvec_device(fl, (const double *)io.ff.ptr, (const double *)io.xs.ptr,
+                                       (const double *)io.bd.ptr, (const double *)io.f.ptr, (const double *)io.t.ptr, eta,
+                                       (double *)io.v.ptr, st));
+        CUDA_TRY(cudaEventRecord(io.e1, st));
+        double *d_v = (double *)io.v.ptr;
+        if (n_fw)
+            CUDA_TRY(cudaMemcpyAsync(v_all + 3 * a, d_v, (size_t)n_fw * 24, cudaMemcpyDeviceToHost, st));
+        if (n_sw)
+            CUDA_TRY(cudaMemcpyAsync(v_all + 3 * (nf + mf->s0[g]), d_v + 3 * n_fw, (size_t)n_sw * 24,
+                                     cudaMemcpyDeviceToHost, st));
+        if (n_bw)
+            CUDA_TRY(cudaMemcpyAsync(v_all + 3 * (nf + ns + mf->b0[g]), d_v + 3 * (n_fw + n_sw), (size_t)n_bw * 24,
+                                     cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return SKB_OK;
+    }));
+    return mflow_collect_stats(mf);
+}
+
+// System::apply_matvec (system.cpp:269-324) over n devices: complete host arrays in and out.  out_shell = res_shell
+// when skb_mflow_set_dense(SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY) was called, else v_shell.
+int skb_mflow_apply_matvec(skb_mflow *mf, const double *x_fibers, const double *x_shell, const double *body_densities,
+                           const double *body_forces_torques, const double *fiber_link_conditions, double eta,
+                           double *res_fibers, double *out_shell, double *v_bodies) {
+    if (!mf || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_mflow_apply_matvec: bad arguments");
+    if (!mf->ops_ready)
+        return set_error(SKB_ERR_STATE, "skb_mflow_apply_matvec: call skb_mflow_set_fiber_operators first");
+    const long long nf = mf->n_fib, ns = mf->n_shell, nb = mf->n_body;
+    if ((nf > 0 && (!x_fibers || !res_fibers)) || (ns > 0 && (!x_shell || !out_shell)) ||
+        (nb > 0 && (!body_densities || !v_bodies)) || (mf->n_bodies > 0 && !body_forces_torques))
+        return set_error(SKB_ERR_INVALID, "skb_mflow_apply_matvec: NULL argument for a non-empty class");
+    SKB_TRY(mflow_prepare(mf));
+    std::vector<double> f, t;
+    if (mf->n_bodies > 0)
+        split_forces_torques(body_forces_torques, mf->n_bodies, f, t);
+    SKB_TRY(mf->workers->run([&](int g) -> int {
+        skb_flow *fl = mf->m[g];
+        skb_mflow::IO &io = mf->io[g];
+        CUDA_TRY(cudaSetDevice(mf->devs[g]));
+        const int f0 = mf->f0[g], f1 = mf->f1[g];
+        const long long a = mf->fiber_off.empty() ? 0 : mf->fiber_off[(size_t)f0],
+                        b = mf->fiber_off.empty() ? 0 : mf->fiber_off[(size_t)f1];
+        const long long n_fw = b - a, n_sw = mf->s1[g] - mf->s0[g], n_bw = mf->b1[g] - mf->b0[g];
+        cudaStream_t st = fl->stream;
+        auto put = [&](DevBuf &buf, const double *h, size_t n_dbl) -> int {
+            SKB_TRY(buf.ensure(n_dbl * 8 + 8));
+            if (n_dbl && h)
+                CUDA_TRY(cudaMemcpyAsync(buf.ptr, h, n_dbl * 8, cudaMemcpyHostToDevice, st));
+            return SKB_OK;
+        };
+        SKB_TRY(put(io.x, x_fibers ? x_fibers + 4 * a : nullptr, (size_t)n_fw * 4));
+        SKB_TRY(put(io.xs, x_shell ? x_shell + 3 * mf->s0[g] : nullptr, (size_t)n_sw * 3));
+        SKB_TRY(put(io.bd, body_densities, (size_t)nb * 3));
+        SKB_TRY(put(io.f, f.data(), f.size()));
+        SKB_TRY(put(io.t, t.data(), t.size()));
+        SKB_TRY(put(io.link, fiber_link_conditions ? fiber_link_conditions + 7 * (long long)f0 : nullptr,
+                    (size_t)(f1 - f0) * 7));
+        SKB_TRY(io.res.ensure((size_t)n_fw * 32 + 8));
+        SKB_TRY(io.outs.ensure((size_t)n_sw * 24 + 8));
+        SKB_TRY(io.vb.ensure((size_t)n_bw * 24 + 8));
+        CUDA_TRY(cudaEventRecord(io.e0, st));
+        SKB_TRY(skb_flow_apply_matvec_device(
+            fl, mf->has_dense ? mf->dn[g] : nullptr, (const double *)io.x.ptr, (const double *)io.xs.ptr,
+            (const double *)io.bd.ptr, (const double *)io.f.ptr, (const double *)io.t.ptr,
+            (fiber_link_conditions && f1 > f0) ? (const double *)io.link.ptr : nullptr, eta, (double *)io.res.ptr,
+            (double *)io.outs.ptr, (double *)io.vb.ptr, st));
+        CUDA_TRY(cudaEventRecord(io.e1, st));
+        if (n_fw)
+            CUDA_TRY(cudaMemcpyAsync(res_fibers + 4 * a, io.res.ptr, (size_t)n_fw * 32, cudaMemcpyDeviceToHost, st));
+        if (n_sw)
+            CUDA_TRY(cudaMemcpyAsync(out_shell + 3 * mf->s0[g], io.outs.ptr, (size_t)n_sw * 24, cudaMemcpyDeviceToHost,
+                                     st));
+        if (n_bw)
+            CUDA_TRY(cudaMemcpyAsync(v_bodies + 3 * mf->b0[g], io.vb.ptr, (size_t)n_bw * 24, cudaMemcpyDeviceToHost, st));
+        CUDA_TRY(cudaStreamSynchronize(st));
+        return SKB_OK;
+    }));
+    return mflow_collect_stats(mf);
+}
+
+// System::velocity_at_targets (system.cpp:330-384) over n devices: the targets are block-partitioned, every device
+// holds all sources
+int skb_mflow_velocity_at_targets(skb_mflow *mf, const double *r_trg, int64_t n_trg, const double *fib_forces,
+                                  const double *shell_density, const double *body_densities,
+                                  const double *body_forces_torques, double eta, double *vel) {
+    if (!mf || n_trg < 0 || (n_trg > 0 && (!r_trg || !vel)) || !(eta > 0))
+        return set_error(SKB_ERR_INVALID, "skb_mflow_velocity_at_targets: bad arguments");
+    const long long chunk = (n_trg + mf->n - 1) / mf->n;
+    SKB_TRY(mf->workers->run([&](int g) -> int {
+        const long long b = std::min<long long>(n_trg, g * chunk), e = std::min<long long>(n_trg, (g + 1) * chunk);
+        if (e <= b)
+            return (int)SKB_OK;
+        return skb_flow_velocity_at_targets(mf->m[g], r_trg + 3 * b, e - b, fib_forces, shell_density, body_densities,
+                                            body_forces_torques, eta, vel + 3 * b);
+    }));
+    double dev_ms = 0;
+    long long pairs = 0;
+    int launches = 0;
+    for (int g = 0; g < mf->n; ++g) {
+        skb_flow_stats st{};
+        skb_flow_last_stats(mf->m[g], &st);
+        dev_ms = std::max(dev_ms, st.device_ms);
+        pairs += st.n_pairs;
+        launches += st.launches;
+    }
+    mf->stats.device_ms = mf->stats.total_ms = dev_ms;
+    mf->stats.n_pairs = pairs;
+    mf->stats.launches = launches;
+    return SKB_OK;
+}
+
+int skb_mflow_last_stats(const skb_mflow *mf, skb_flow_stats *out) {
+    if (!mf || !out)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_last_stats: NULL");
+    *out = mf->stats;
+    return SKB_OK;
+}
+
+} // extern "C"

@@ -4,6 +4,10 @@ import sys
 import numpy as np
 import pytest
 
+# two group members on ONE GPU (tests/test_gpu_mflow.py) spin-wait on each other's flags from different streams: give
+# every stream its own hardware queue, so that no launch is serialised behind a waiting kernel (read at CUDA init)
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
