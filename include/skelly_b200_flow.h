@@ -237,6 +237,10 @@ SKB_API int skb_mflow_set_self_exclusion(skb_mflow *mf, int fused);
 /* which fibers / periphery rows / body rows device `member` owns (any pointer may be NULL) */
 SKB_API int skb_mflow_partition(skb_mflow *mf, int member, int *fiber_begin, int *fiber_end, int64_t *shell_begin,
                                 int64_t *shell_end, int64_t *body_begin, int64_t *body_end);
+/* the same partition without a GPU or a handle (rank-per-GPU hosts): out6 = the six arguments of
+ * skb_flow_set_target_ranges for `member` of `n_members` */
+SKB_API int skb_partition_query(const int *n_nodes, int n_fibers, int64_t n_shell, int64_t n_body, int n_members,
+                                int member, int64_t *out6);
 SKB_API int skb_mflow_set_fiber_class(skb_mflow *mf, int n_nodes, const double *D_1_0, const double *P_downsample_bc);
 /* complete arrays of ALL fibers, as skb_flow_set_fiber_operators without a window; every device keeps its own slice */
 SKB_API int skb_mflow_set_fiber_operators(skb_mflow *mf, const double *A, const double *force_operator,

@@ -119,6 +119,8 @@ def library() -> C.CDLL:
         "skb_flow_group_connect": ([ctxp, C.c_int, ctxp], C.c_int),
         "skb_flow_group_error": ([ctxp, C.POINTER(C.c_int)], C.c_int),
         "skb_flow_apply_matvec_device": ([ctxp, ctxp] + [C.c_void_p] * 6 + [C.c_double] + [C.c_void_p] * 4, C.c_int),
+        "skb_partition_query": ([C.POINTER(C.c_int), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
+                                 C.POINTER(C.c_int64)], C.c_int),
         "skb_mflow_create": ([C.POINTER(C.c_int), C.c_int, C.POINTER(ctxp)], C.c_int),
         "skb_mflow_destroy": ([ctxp], C.c_int),
         "skb_mflow_n_devices": ([ctxp, C.POINTER(C.c_int)], C.c_int),
@@ -817,6 +819,16 @@ def plan_query(kind, n_trg, n_src, num_sms=148, occupancy=(8, 6, 4, 2), force_T=
     _check(library().skb_plan_query(int(kind), int(n_trg), int(n_src), int(num_sms), occ, int(force_T), int(force_S),
                                     C.byref(T), C.byref(S), C.byref(per), C.byref(gx)))
     return {"T": T.value, "n_splits": S.value, "tiles_per_split": per.value, "grid_x": gx.value}
+
+
+def partition_query(fiber_n_nodes, n_shell, n_body, n_members, member):
+    """Rows of [fibers | periphery | bodies] member `member` of `n_members` owns (the partition of skb_mflow; no GPU
+    needed): (fiber_begin, fiber_end, shell_begin, shell_end, body_begin, body_end)."""
+    nn = np.ascontiguousarray(fiber_n_nodes, dtype=np.int32)
+    out = (C.c_int64 * 6)()
+    _check(library().skb_partition_query(nn.ctypes.data_as(C.POINTER(C.c_int)), int(nn.shape[0]), int(n_shell),
+                                         int(n_body), int(n_members), int(member), out))
+    return tuple(int(v) for v in out)
 
 
 def sym_groups_per_block() -> int:

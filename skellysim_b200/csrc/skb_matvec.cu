@@ -1859,29 +1859,40 @@ struct skb_mflow {
     skb_flow_stats stats{};
 };
 
-static void mflow_partition(skb_mflow *mf) {
-    const int n = mf->n;
-    mf->f0.assign(n, 0), mf->f1.assign(n, 0);
-    mf->s0.assign(n, 0), mf->s1.assign(n, 0), mf->b0.assign(n, 0), mf->b1.assign(n, 0);
-    // whole fibers, cut where the running node count passes g/n of the total (fcfd.cpp:102-120 splits by fiber count;
-    // by node count balances ragged suspensions as well)
+// member g of n owns whole fibers [f0, f1) -- cut where the running node count passes g/n of the total
+// (fcfd.cpp:102-120 splits by fiber count; by node count balances ragged suspensions as well) -- and equal blocks of
+// the periphery and body rows
+static void partition_rows(const std::vector<long long> &fiber_off, long long n_shell, long long n_body, int n,
+                           std::vector<int> &f0, std::vector<int> &f1, std::vector<long long> &s0,
+                           std::vector<long long> &s1, std::vector<long long> &b0, std::vector<long long> &b1) {
+    const int n_fibers = (int)fiber_off.size() - 1;
+    const long long n_fib = n_fibers > 0 ? fiber_off[(size_t)n_fibers] : 0;
+    f0.assign(n, 0), f1.assign(n, 0);
+    s0.assign(n, 0), s1.assign(n, 0), b0.assign(n, 0), b1.assign(n, 0);
     int f = 0;
     for (int g = 0; g < n; ++g) {
-        mf->f0[g] = f;
-        const long long want = mf->n_fib * (g + 1) / n;
-        while (f < mf->n_fibers && (g == n - 1 || mf->fiber_off[(size_t)f + 1] <= want))
+        f0[g] = f;
+        const long long want = n_fib * (g + 1) / n;
+        while (f < n_fibers && fiber_off[(size_t)f + 1] <= want)
             ++f;
         if (g == n - 1)
-            f = mf->n_fibers;
-        mf->f1[g] = f;
+            f = std::max(n_fibers, 0);
+        f1[g] = f;
     }
+    const long long cs = (n_shell + n - 1) / n, cb = (n_body + n - 1) / n;
     for (int g = 0; g < n; ++g) {
-        const long long cs = (mf->n_shell + n - 1) / n, cb = (mf->n_body + n - 1) / n;
-        mf->s0[g] = std::min(mf->n_shell, g * cs);
-        mf->s1[g] = std::min(mf->n_shell, (g + 1) * cs);
-        mf->b0[g] = std::min(mf->n_body, g * cb);
-        mf->b1[g] = std::min(mf->n_body, (g + 1) * cb);
+        s0[g] = std::min(n_shell, g * cs);
+        s1[g] = std::min(n_shell, (g + 1) * cs);
+        b0[g] = std::min(n_body, g * cb);
+        b1[g] = std::min(n_body, (g + 1) * cb);
     }
+}
+
+static void mflow_partition(skb_mflow *mf) {
+    std::vector<long long> off = mf->fiber_off;
+    if (off.empty())
+        off.push_back(0);
+    partition_rows(off, mf->n_shell, mf->n_body, mf->n, mf->f0, mf->f1, mf->s0, mf->s1, mf->b0, mf->b1);
 }
 
 // ranges + group wiring, after any change of the geometry's sizes
@@ -2022,6 +2033,23 @@ int skb_mflow_partition(skb_mflow *mf, int member, int *fiber_begin, int *fiber_
     if (shell_end) *shell_end = mf->s1[member];
     if (body_begin) *body_begin = mf->b0[member];
     if (body_end) *body_end = mf->b1[member];
+    return SKB_OK;
+}
+
+// host-only (no GPU needed): the partition skb_mflow uses, for rank-per-GPU hosts that want the same one
+int skb_partition_query(const int *n_nodes, int n_fibers, int64_t n_shell, int64_t n_body, int n_members, int member,
+                        int64_t *out6) {
+    if (n_fibers < 0 || (n_fibers > 0 && !n_nodes) || n_shell < 0 || n_body < 0 || n_members < 1 || member < 0 ||
+        member >= n_members || !out6)
+        return set_error(SKB_ERR_INVALID, "skb_partition_query: bad arguments");
+    std::vector<long long> off((size_t)n_fibers + 1, 0);
+    for (int f = 0; f < n_fibers; ++f)
+        off[(size_t)f + 1] = off[(size_t)f] + n_nodes[f];
+    std::vector<int> f0, f1;
+    std::vector<long long> s0, s1, b0, b1;
+    partition_rows(off, n_shell, n_body, n_members, f0, f1, s0, s1, b0, b1);
+    out6[0] = f0[member], out6[1] = f1[member], out6[2] = s0[member], out6[3] = s1[member], out6[4] = b0[member],
+    out6[5] = b1[member];
     return SKB_OK;
 }
 

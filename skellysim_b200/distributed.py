@@ -88,6 +88,23 @@ def reference_rank_ranges(n_fibers: int, n_shell_nodes: int, n_body_nodes: int, 
     return f0, f1, s0, s1, b0, b1
 
 
+def connect_group(flow, rank: int, world: int, group=None):
+    """One rank per GPU: make `flow` (geometry and target ranges already set) a member of a peer-memory group.  Every
+    rank exports the CUDA-IPC handle of its window, the 64-byte handles travel through torch.distributed once, every
+    rank maps all peers' windows.  After this, flow.matvec_device / apply_matvec_device exchange strengths and partial
+    velocities through NVLink loads / stores inside the library's own kernels -- no collective call per matvec."""
+    import torch.distributed as dist
+    flow.group_init(rank, world)
+    if world == 1:
+        return
+    handles = [None] * world
+    dist.all_gather_object(handles, flow.group_export(), group=group)
+    for r in range(world):
+        if r != rank:
+            flow.group_import(r, handles[r])
+    dist.barrier(group=group)
+
+
 def allgatherv_rows(local, counts, group=None):
     """All-gather of per-rank row blocks of unequal length (fw of the own fibers -> fw of all fibers): pads every
     block to max(counts) rows, one all_gather_into_tensor, returns the concatenation without the padding.
