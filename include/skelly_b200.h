@@ -155,6 +155,10 @@ SKB_API int skb_ctx_set_sym_partition(skb_ctx *ctx, int part, int n_parts);
 /* 1 if the last Stokeslet evaluation of this context went through the symmetric kernel, else 0 */
 SKB_API int skb_ctx_last_eval_was_symmetric(const skb_ctx *ctx, int *yes);
 
+/* duration (CUDA events on the launch stream, valid once that stream has passed them) and ordered-pair count of the
+ * last launch of the symmetric kernel on the context's first device; 0 / 0 when it has not run */
+SKB_API int skb_ctx_last_sym_kernel(const skb_ctx *ctx, double *ms, int64_t *pairs);
+
 /* ---- host-side planners, callable without a GPU (unit-tested on CPU) ------------------------------------------
  * Launch plan of the plain pair kernel for a problem of n_src sources x n_trg targets on a device with `num_sms`
  * SMs and the given resident-CTA counts for T = 1, 2, 4, 8 targets per thread. */

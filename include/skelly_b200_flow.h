@@ -216,6 +216,9 @@ typedef struct skb_flow_stats {
     int32_t launches;
 } skb_flow_stats;
 SKB_API int skb_flow_last_stats(const skb_flow *fl, skb_flow_stats *out);
+/* the matvec's dominant kernel (symmetric fiber-fiber block): duration of its last launch and the ordered pairs it
+ * covered (skb_ctx_last_sym_kernel of the matvec's fiber evaluator) -- the roofline line of bench.py */
+SKB_API int skb_flow_last_sym_kernel(const skb_flow *fl, double *ms, int64_t *pairs);
 
 /* ---- skb_mflow: ONE process driving n GPUs ---------------------------------------------------------------------
  * The multi-device form the reference's rule "direct evaluators need a single MPI rank" (system.cpp:618-623) admits.

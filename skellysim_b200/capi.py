@@ -96,6 +96,8 @@ def library() -> C.CDLL:
                                 C.POINTER(C.c_int)], C.c_int),
         "skb_sym_groups_per_block": ([], C.c_int),
         "skb_ctx_set_sym_partition": ([ctxp, C.c_int, C.c_int], C.c_int),
+        "skb_ctx_last_sym_kernel": ([ctxp, C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
+        "skb_flow_last_sym_kernel": ([ctxp, C.POINTER(C.c_double), C.POINTER(C.c_int64)], C.c_int),
         "skb_ctx_last_eval_was_symmetric": ([ctxp, C.POINTER(C.c_int)], C.c_int),
         # include/skelly_b200_flow.h
         "skb_flow_create": ([C.c_int, C.POINTER(ctxp)], C.c_int),
@@ -342,6 +344,11 @@ class Context:
         n_src rows of the result are partial sums to be all-reduced over the parts."""
         _check(library().skb_ctx_set_sym_partition(self._h, int(part), int(n_parts)))
 
+    def last_sym_kernel(self):
+        ms, pairs = C.c_double(0), C.c_int64(0)
+        _check(library().skb_ctx_last_sym_kernel(self._h, C.byref(ms), C.byref(pairs)))
+        return ms.value, pairs.value
+
     def last_eval_was_symmetric(self) -> bool:
         y = C.c_int(0)
         _check(library().skb_ctx_last_eval_was_symmetric(self._h, C.byref(y)))
@@ -573,7 +580,7 @@ class Flow:
                                                       C.c_void_p(d_res), C.c_void_p(stream)))
 
     def apply_matvec(self, x_fibers, shell_density, body_densities, body_forces_torques, eta,
-                     fiber_link_conditions=None, dense=None):
+                     fiber_link_conditions=None, dense=None, out=None):
         """System::apply_matvec (system.cpp:298-318) with the fiber operators on the device.
         Returns (res_fibers (4 N_f,), v_shell (N_s,3), v_bodies (N_b,3)); with dense= a single-device Dense holding
         stresslet_plus_complementary the second item is res_shell = shell.matvec(x_shell, v_shell) instead."""
@@ -582,8 +589,13 @@ class Flow:
         b, c = _arr(shell_density, 3), _arr(body_densities, 3)
         ft = _arr(body_forces_torques, 6)
         vb = None if fiber_link_conditions is None else _arr(fiber_link_conditions, 7)
-        res = np.empty(4 * self.n_fib)
-        v_s, v_b = np.empty((self.n_shell, 3)), np.empty((self.n_body, 3))
+        if out is not None:  # caller's (e.g. pinned) buffers: (res (4 N_f,), v_shell (N_s,3), v_bodies (N_b,3))
+            res, v_s, v_b = out
+            assert res.shape == (4 * self.n_fib,) and v_s.shape == (self.n_shell, 3) and v_b.shape == (self.n_body, 3)
+            assert all(a.flags.c_contiguous and a.dtype == np.float64 for a in out)
+        else:
+            res = np.empty(4 * self.n_fib)
+            v_s, v_b = np.empty((self.n_shell, 3)), np.empty((self.n_body, 3))
         if dense is not None:
             _check(library().skb_flow_apply_matvec_dense(self._h, dense._h, _p(x), _p(b), _p(c), _p(ft),
                                                          None if vb is None else _p(vb), float(eta), _p(res), _p(v_s),
@@ -606,6 +618,12 @@ class Flow:
                                                       vp(d_res_fibers), vp(d_out_shell), vp(d_v_bodies), vp(stream)))
 
     # ---- multi-GPU groups (peer memory) ----
+    def last_sym_kernel(self):
+        """(ms, ordered pairs) of the last launch of the symmetric fiber-fiber kernel inside matvec()."""
+        ms, pairs = C.c_double(0), C.c_int64(0)
+        _check(library().skb_flow_last_sym_kernel(self._h, C.byref(ms), C.byref(pairs)))
+        return ms.value, pairs.value
+
     def group_init(self, rank: int, size: int):
         _check(library().skb_flow_group_init(self._h, int(rank), int(size)))
 
@@ -805,6 +823,11 @@ class Dense:
             assert v.shape[0] == rows
         _check(library().skb_dense_apply(self._h, int(op), _p(x), _p(v) if v is not None else None, _p(y)))
         return y
+
+    def apply_device(self, op: int, d_x: int, d_v_add: int, d_y: int, stream: int = 0):
+        """Single-device handle, operands already on its device (addresses as ints, 0 = NULL v_add); asynchronous."""
+        _check(library().skb_dense_apply_device(self._h, int(op), C.c_void_p(d_x), C.c_void_p(d_v_add) if d_v_add else None,
+                                                C.c_void_p(d_y), C.c_void_p(stream) if stream else None))
 
     def stats(self) -> dict:
         s = DenseStats()

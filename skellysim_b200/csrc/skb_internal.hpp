@@ -81,6 +81,7 @@ struct SourceSet {
     bool sym_plan_valid = false;
     int sym_T = 0, sym_nb = 0, sym_items = 0, sym_part = 0, sym_parts = 1;
     skb::DevBuf sym_item_buf, sym_row_begin, sym_P, sym_F, sym_diag, sym_flag;
+    long long sym_pairs = 0; // ordered (target, source) pairs one launch of the symmetric kernel covers (both directions)
 };
 
 struct DeviceState {
@@ -89,6 +90,8 @@ struct DeviceState {
     cudaStream_t aux_stream = nullptr;              // remainder targets run beside the symmetric kernel
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_fork2 = nullptr, ev_join2 = nullptr;
     cudaEvent_t ev_t0 = nullptr, ev_t1 = nullptr, ev_k0 = nullptr, ev_k1 = nullptr;
+    cudaEvent_t ev_s0 = nullptr, ev_s1 = nullptr; // around the symmetric kernel's launch (its live duration inside a step)
+    bool sym_timed = false;
     long long trg_begin = 0, n_trg = 0; // this device's block of the global target list
     // symmetric multi-device layout: targets = [all n_self leading targets | remainder rows [rem_begin, +rem_count)]
     long long rem_begin = 0, rem_count = 0;

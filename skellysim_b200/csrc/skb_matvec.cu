@@ -1742,6 +1742,12 @@ int skb_flow_apply_matvec_device(skb_flow *fl, skb_dense *dn, const double *d_x_
     return SKB_OK;
 }
 
+int skb_flow_last_sym_kernel(const skb_flow *fl, double *ms, int64_t *pairs) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_last_sym_kernel: NULL");
+    return skb_ctx_last_sym_kernel(fl->fib[1], ms, pairs);
+}
+
 int skb_flow_last_stats(const skb_flow *fl, skb_flow_stats *out) {
     if (!fl || !out)
         return set_error(SKB_ERR_INVALID, "skb_flow_last_stats: NULL");

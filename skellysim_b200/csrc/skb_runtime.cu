@@ -295,6 +295,8 @@ static int ctx_create_impl(const int *ids, int n, skb_ctx **out) {
         CUDA_TRY(cudaEventCreate(&d.ev_t1));
         CUDA_TRY(cudaEventCreate(&d.ev_k0));
         CUDA_TRY(cudaEventCreate(&d.ev_k1));
+        CUDA_TRY(cudaEventCreate(&d.ev_s0));
+        CUDA_TRY(cudaEventCreate(&d.ev_s1));
     }
     if (n > 1)
         SKB_TRY(nccl_group_create(ctx->devs.size(), [&](int g) { return ctx->devs[g].info.dev; }, &ctx->nccl));
@@ -359,6 +361,8 @@ int skb_ctx_destroy(skb_ctx *ctx) {
         if (d.ev_t1) cudaEventDestroy(d.ev_t1);
         if (d.ev_k0) cudaEventDestroy(d.ev_k0);
         if (d.ev_k1) cudaEventDestroy(d.ev_k1);
+        if (d.ev_s0) cudaEventDestroy(d.ev_s0);
+        if (d.ev_s1) cudaEventDestroy(d.ev_s1);
         if (d.ev_fork) cudaEventDestroy(d.ev_fork);
         if (d.ev_join) cudaEventDestroy(d.ev_join);
         if (d.ev_fork2) cudaEventDestroy(d.ev_fork2);
@@ -440,6 +444,25 @@ int skb_ctx_last_eval_was_symmetric(const skb_ctx *ctx, int *yes) {
     if (!ctx || !yes)
         return set_error(SKB_ERR_INVALID, "skb_ctx_last_eval_was_symmetric: NULL");
     *yes = ctx->last_was_sym ? 1 : 0;
+    return SKB_OK;
+}
+
+int skb_ctx_last_sym_kernel(const skb_ctx *ctx, double *ms, int64_t *pairs) {
+    if (!ctx || !ms || !pairs)
+        return set_error(SKB_ERR_INVALID, "skb_ctx_last_sym_kernel: NULL");
+    *ms = 0;
+    *pairs = 0;
+    const DeviceState &d = ctx->devs[0];
+    if (!d.sym_timed)
+        return SKB_OK;
+    float t = 0;
+    cudaSetDevice(d.info.dev);
+    if (cudaEventElapsedTime(&t, d.ev_s0, d.ev_s1) == cudaSuccess) {
+        *ms = t;
+        *pairs = d.src[SKB_STOKESLET].sym_pairs;
+    } else {
+        (void)cudaGetLastError(); // not finished yet
+    }
     return SKB_OK;
 }
 
@@ -854,6 +877,16 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
         CUDA_TRY(cudaMemcpyAsync(s.sym_row_begin.ptr, row_begin.data(), row_begin.size() * sizeof(int),
                                  cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaStreamSynchronize(st)); // host vectors go out of scope
+        // pairs of one launch: every ordered pair of real nodes in (owned row I, any block J > I), both directions
+        long long pairs = 0;
+        for (long long I = 0; I < nb; ++I) {
+            if (sym_row_owner((int)I, d.sym_parts) != d.sym_part)
+                continue;
+            const long long nI = std::max<long long>(0, std::min<long long>(s.n, (I + 1) * block) - I * block);
+            const long long after = std::max<long long>(0, s.n - (I + 1) * block);
+            pairs += 2 * nI * after;
+        }
+        s.sym_pairs = pairs;
         s.sym_T = T;
         s.sym_nb = (int)nb;
         s.sym_items = (int)order.size();
@@ -884,8 +917,12 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
     CUDA_TRY(cudaEventRecord(d.ev_fork2, st)); // strengths are packed: the diagonal blocks may start from here
     if (s.sym_items > 0) {
         a.fid = s.excl ? (const int *)s.excl_ids.ptr : nullptr;
+        CUDA_TRY(cudaEventRecord(d.ev_s0, st));
         e = s.excl ? launch_sym<kSymT, kSymMinB, true>(a, s.sym_items, st)
                    : launch_sym<kSymT, kSymMinB, false>(a, s.sym_items, st);
+        if (e == cudaSuccess)
+            CUDA_TRY(cudaEventRecord(d.ev_s1, st));
+        d.sym_timed = true;
         if (e != cudaSuccess)
             return set_error(SKB_ERR_CUDA, "pair_sym_kernel launch failed: %s", cudaGetErrorString(e));
         count_launch(1);
