@@ -142,31 +142,33 @@ class Ops:
 
     @staticmethod
     def _range(kind: int, rows: int, n: int, f0: int, f1: int, seed: int):
-        out = np.empty((f1 - f0, rows, 4 * n))
+        """Storage array (fibers, 4n columns, rows): every fiber's matrix COLUMN-major, as Eigen's .data() -- what the C
+        ABI takes.  The matrix itself is the transposed view."""
+        out = np.empty((f1 - f0, 4 * n, rows))
         for blk in range(f0 // Ops.BLOCK, (max(f1, 1) - 1) // Ops.BLOCK + 1):
             lo, hi = blk * Ops.BLOCK, (blk + 1) * Ops.BLOCK
             a, b = max(lo, f0), min(hi, f1)
             if b <= a:
                 continue
             rng = np.random.default_rng([seed, kind, blk])
-            m = rng.standard_normal((Ops.BLOCK, rows, 4 * n))
+            m = rng.standard_normal((Ops.BLOCK, 4 * n, rows))
             out[a - f0:b - f0] = m[a - lo:b - lo]
         out /= np.sqrt(4 * n)
         return out
 
     @staticmethod
     def A_range(g, f0, f1, seed=6):
-        return Ops._range(0, 4 * g["n"], g["n"], f0, f1, seed)
+        return Ops._range(0, 4 * g["n"], g["n"], f0, f1, seed).transpose(0, 2, 1)
 
     @staticmethod
     def F_range(g, f0, f1, seed=6):
-        return Ops._range(1, 3 * g["n"], g["n"], f0, f1, seed)
+        return Ops._range(1, 3 * g["n"], g["n"], f0, f1, seed).transpose(0, 2, 1)
 
     def __init__(self, g, f0: int, f1: int, seed: int = 6, with_A=True):
         n = g["n"]
         self.n, self.f0, self.f1 = n, f0, f1
-        self.A = Ops.A_range(g, f0, f1, seed) if with_A else None
-        self.F = Ops.F_range(g, f0, f1, seed)
+        self.A = Ops.A_range(g, f0, f1, seed) if with_A else None   # (k, 4n, 4n) views of column-major storage
+        self.F = Ops.F_range(g, f0, f1, seed)                       # (k, 3n, 4n)
         self.xs = np.repeat(g["nh"][f0:f1], n, axis=0)              # straight fibers: the tangent is nhat everywhere
         self.lprev = np.ones(f1 - f0)
         self.plus = (np.random.default_rng([seed, 2]).integers(0, 2, g["n_fibers"]).astype(np.int32))[f0:f1]
@@ -475,7 +477,9 @@ class RankSystem:
         self.ops = Ops(g, f0, f1)
         fl.set_fiber_class(n, self.ops.D, self.ops.P)
         t0 = time.perf_counter()
-        fl.set_fiber_operators(self.ops.A, self.ops.F, self.ops.xs, self.ops.lprev, self.ops.plus)
+        # (.base of the transposed views = the column-major storage the C ABI takes: no host-side reshuffle is timed)
+        fl.set_fiber_operators(self.ops.A.base, self.ops.F.base, self.ops.xs, self.ops.lprev, self.ops.plus,
+                               colmajor=True)
         self.set_operators_ms = 1e3 * (time.perf_counter() - t0)
         _log("fiber operators uploaded")
         self.dn = None
@@ -736,7 +740,7 @@ def inprocess_leg(skb, n_devices: int):
         mf.set_periphery(g["shell"], g["shell_n"])
         mf.set_bodies(g["body"], g["body_n"], g["centers"])
         mf.set_fiber_class(g["n"], ops.D, ops.P)
-        mf.set_fiber_operators(ops.A, ops.F, ops.xs, ops.lprev, ops.plus)
+        mf.set_fiber_operators(ops.A.base, ops.F.base, ops.xs, ops.lprev, ops.plus, colmajor=True)
         mf.set_dense(skb.DENSE_STRESSLET_PLUS_COMPLEMENTARY, M)
         res, outs, vb = mf.apply_matvec(inp["x"], inp["xs"], inp["bd"], inp["ft"], ETA, inp["link"])
         ts = []

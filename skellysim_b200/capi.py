@@ -521,14 +521,19 @@ class Flow:
             return np.zeros(0)
         return np.concatenate([np.asarray(m, dtype=np.float64).ravel(order="F") for m in mats])
 
-    def set_fiber_operators(self, A_list, force_list, xs, length_prev, plus_bc_velocity):
+    def set_fiber_operators(self, A_list, force_list, xs, length_prev, plus_bc_velocity, colmajor=False):
         """A_ (4n,4n) and force_operator_ (3n,4n) per fiber (lists, or (n_fibers, rows, cols) stacks), tangents xs
-        (N_f,3), length_prev_, plus-end velocity BC -- of the OWN fibers when target ranges are set."""
-        A, F = self._colmajor_concat(A_list), self._colmajor_concat(force_list)
+        (N_f,3), length_prev_, plus-end velocity BC -- of the OWN fibers when target ranges are set.  colmajor=True:
+        A_list / force_list are already the concatenated column-major buffers (Eigen's .data()), passed through."""
+        if colmajor:
+            A = np.ascontiguousarray(A_list, dtype=np.float64).reshape(-1)
+            F = np.ascontiguousarray(force_list, dtype=np.float64).reshape(-1)
+        else:
+            A, F = self._colmajor_concat(A_list), self._colmajor_concat(force_list)
         xs = _arr(xs, 3)
         lp = np.ascontiguousarray(length_prev, dtype=np.float64)
         pl = np.ascontiguousarray(plus_bc_velocity, dtype=np.int32)
-        assert xs.shape[0] == self._pieces()[0] and lp.shape == pl.shape == (len(A_list),)
+        assert xs.shape[0] == self._pieces()[0] and lp.shape == pl.shape and (colmajor or lp.shape == (len(A_list),))
         _check(library().skb_flow_set_fiber_operators(self._h, _p(A), _p(F), _p(xs), _p(lp),
                                                       pl.ctypes.data_as(C.POINTER(C.c_int))))
 
@@ -718,8 +723,12 @@ class MultiFlow:
             raise ValueError(f"class matrices for n={n}: got {D.shape}, {P.shape}")
         _check(library().skb_mflow_set_fiber_class(self._h, n, _p(D), _p(P)))
 
-    def set_fiber_operators(self, A_list, force_list, xs, length_prev, plus_bc_velocity):
-        A, F = Flow._colmajor_concat(A_list), Flow._colmajor_concat(force_list)
+    def set_fiber_operators(self, A_list, force_list, xs, length_prev, plus_bc_velocity, colmajor=False):
+        if colmajor:
+            A = np.ascontiguousarray(A_list, dtype=np.float64).reshape(-1)
+            F = np.ascontiguousarray(force_list, dtype=np.float64).reshape(-1)
+        else:
+            A, F = Flow._colmajor_concat(A_list), Flow._colmajor_concat(force_list)
         xs = _arr(xs, 3)
         lp = np.ascontiguousarray(length_prev, dtype=np.float64)
         pl = np.ascontiguousarray(plus_bc_velocity, dtype=np.int32)

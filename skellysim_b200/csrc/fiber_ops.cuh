@@ -1,45 +1,95 @@
 // fiber_ops.cuh -- per-fiber dense operators of the GMRES matvec, device resident.
 //
-//   fiber_gemv_kernel      y_f = M_f x_f for every fiber f; M_f column-major as Eigen stores
-//                          FiberFiniteDifference::A_ (4n x 4n) and ::force_operator_ (3n x 4n).  HBM-bound: every
-//                          matrix element is read once per matvec, 8 B / FMA.
-//   fiber_velocity_kernel  the velocity / boundary part of FiberFiniteDifference::matvec
-//                          (src/core/fiber_finite_difference.cpp:276-312): -P_downsample_bc * vT + xs_vT + y_BC
+//   fiber_gemv_kernel<MODE>   y_f = M_f x_f for every fiber f; M_f column-major as Eigen stores
+//                             FiberFiniteDifference::A_ (4n x 4n) and ::force_operator_ (3n x 4n).  HBM-bound: every
+//                             matrix element is read once per matvec, 8 B / FMA.
+//       MODE 0  out[row] = (M x)[row]                                  (A_^-1 x: the fiber preconditioner)
+//       MODE 1  force layout of FiberContainerFiniteDifference::apply_fiber_force (fcfd.cpp:272-287)
+//       MODE 2  the whole of FiberFiniteDifference::matvec (src/core/fiber_finite_difference.cpp:276-312) in ONE pass:
+//               res = A_ x - P_downsample_bc vT(v) + xs_vT + y_BC -- the velocity / boundary part rides on the
+//               HBM-bound GEMV instead of a second launch that re-reads and re-writes res.
 //
-// Work decomposition of the GEMV: one CTA of 256 threads per (fiber, 64-row block); thread (lr, q) accumulates row
-// row0+lr over the columns j == q (mod 4); a warp reads 32 consecutive rows of one column = 256 contiguous bytes.
+// Work decomposition: one CTA of 256 threads per (fiber, 32-row block); thread (lr, q) accumulates row row0+lr over the
+// columns j == q (mod 8); a warp reads 32 consecutive rows of one column = 256 contiguous bytes.  32-row blocks tile
+// both operator heights (3n and 4n are multiples of 32 for every allowed n >= 32, fiber_finite_difference.cpp:522),
+// so no CTA is half empty.
 #pragma once
 #include <cuda_runtime.h>
 
 namespace skb {
 
-constexpr int kFiberGemvRows = 64;   // rows per CTA
-constexpr int kFiberGemvSlices = 4;  // column slices per row
+constexpr int kFiberGemvRows = 32;   // rows per CTA
+constexpr int kFiberGemvSlices = 8;  // column slices per row
 constexpr int kFiberGemvThreads = kFiberGemvRows * kFiberGemvSlices;
 
 struct FiberGemvItem {
     long long mat_off; // element offset of M_f in the concatenated operator buffer
     long long x_off;   // element offset of x_f (4 * node offset)
-    long long out_off; // MODE 0: element offset of y_f;  MODE 1: node offset of the fiber
+    long long out_off; // MODE 0/2: element offset of y_f;  MODE 1: node offset of the fiber
     int rows, cols;    // shape of M_f
     int row0;          // first row of this CTA
     int n_nodes;       // nodes of the fiber
+    int fiber, pad;    // index of the fiber among the resident ones (MODE 2: xs / length_prev / class / v_boundary)
 };
 
-// MODE 0: out[out_off + row] = (M x)[row]
-// MODE 1: force layout of FiberContainerFiniteDifference::apply_fiber_force (fcfd.cpp:272-287): row = k*n + i of
-//         force_operator_ * x goes to fw(k, node_off + i), i.e. AoS out[3*(out_off + i) + k]
+// everything MODE 2 needs beyond the GEMV operands; the fiber-indexed arrays start at the first resident fiber
+struct FiberVelArgs {
+    const double *xs;          // [N_own*3] tangents xs_
+    const double *v;           // [N_own*3] velocities at the fiber nodes
+    const double *length_prev; // [n_fibers]
+    const int *plus_velocity;  // [n_fibers] bc_plus_.first == Velocity
+    const double *class_mats;  // D_1_0 (n x n) and P_downsample_bc ((4n-14) x 4n) of every node count, column-major
+    const long long *class_D;  // [n_fibers] element offset of the fiber's D_1_0 in class_mats
+    const long long *class_P;  // [n_fibers] ... of its P_downsample_bc
+    const int2 *row_range;     // per class: [4n-14] first / one-past-last non-zero column of every row of P
+    const long long *class_R;  // [n_fibers] element offset of the fiber's row ranges
+    const double *v_boundary;  // [n_fibers*7] or nullptr
+};
+
 template <int MODE>
 __global__ void __launch_bounds__(kFiberGemvThreads)
     fiber_gemv_kernel(const FiberGemvItem *__restrict__ items, const double *__restrict__ mats,
-                      const double *__restrict__ x, double *__restrict__ out) {
+                      const double *__restrict__ x, double *__restrict__ out, const FiberVelArgs va) {
     extern __shared__ double fg_smem[];
     const FiberGemvItem it = items[blockIdx.x];
-    double *xs = fg_smem;                        // cols
-    double *part = fg_smem + ((it.cols + 1) & ~1); // kFiberGemvSlices x kFiberGemvRows
+    const int colsp = (it.cols + 1) & ~1;
+    double *xs_sh = fg_smem;             // cols
+    double *part = fg_smem + colsp;      // kFiberGemvSlices x kFiberGemvRows
+    double *vT = part + kFiberGemvThreads; // MODE 2: 4n
+    double *s_sh = vT + colsp;             // MODE 2: n
     for (int j = threadIdx.x; j < it.cols; j += kFiberGemvThreads)
-        xs[j] = x[it.x_off + j];
+        xs_sh[j] = x[it.x_off + j];
+    const int n = it.n_nodes;
+    if (MODE == 2) {
+        // vT = [v_x; v_y; v_z; D_1^T (xs . v)],  D_1 = D_1_0 * 2 / length_prev           (ffd.cpp:280-293)
+        const long long node_off = it.x_off / 4;
+        const double *xt = va.xs + 3 * node_off, *v = va.v + 3 * node_off;
+        for (int i = threadIdx.x; i < n; i += kFiberGemvThreads) {
+            const double vx = v[3 * i], vy = v[3 * i + 1], vz = v[3 * i + 2];
+            vT[i] = vx;
+            vT[n + i] = vy;
+            vT[2 * n + i] = vz;
+            s_sh[i] = xt[3 * i] * vx + xt[3 * i + 1] * vy + xt[3 * i + 2] * vz;
+        }
+    }
     __syncthreads();
+    if (MODE == 2) {
+        const double scale = 2.0 / va.length_prev[it.fiber];
+        const double *D = va.class_mats + va.class_D[it.fiber];
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        for (int j = warp; j < n; j += kFiberGemvThreads / 32) { // (D_1^T s)[j] = sum_i D_1(i, j) s_i, column j contiguous
+            const double *col = D + (long long)j * n;
+            double acc = 0.0;
+            for (int i = lane; i < n; i += 32)
+                acc = fma(col[i], s_sh[i], acc);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1)
+                acc += __shfl_xor_sync(0xffffffffu, acc, o);
+            if (lane == 0)
+                vT[3 * n + j] = scale * acc;
+        }
+        __syncthreads();
+    }
     const int lr = threadIdx.x & (kFiberGemvRows - 1), q = threadIdx.x / kFiberGemvRows;
     const int row = it.row0 + lr;
     double acc = 0.0;
@@ -55,10 +105,23 @@ __global__ void __launch_bounds__(kFiberGemvThreads)
                 v[u] = __ldg(m + (long long)(j + u * kFiberGemvSlices) * ld);
 #pragma unroll
             for (int u = 0; u < 8; ++u)
-                acc = fma(v[u], xs[j + u * kFiberGemvSlices], acc);
+                acc = fma(v[u], xs_sh[j + u * kFiberGemvSlices], acc);
         }
         for (; j < it.cols; j += kFiberGemvSlices)
-            acc = fma(__ldg(m + (long long)j * ld), xs[j], acc);
+            acc = fma(__ldg(m + (long long)j * ld), xs_sh[j], acc);
+        if (MODE == 2) {
+            // - (P_downsample_bc vT)[row] for row < 4n-14, over the row's non-zero columns only: P is block diagonal in
+            // the reference (three (n-4) x n blocks and one (n-2) x n, ffd.cpp:551-555), 75 % structural zeros
+            const int bc = 4 * n - 14;
+            if (row < bc) {
+                const int2 rg = va.row_range[va.class_R[it.fiber] + row];
+                const double *p = va.class_mats + va.class_P[it.fiber] + row;
+                double a2 = 0.0;
+                for (int c = rg.x + q; c < rg.y; c += kFiberGemvSlices)
+                    a2 = fma(__ldg(p + (long long)c * bc), vT[c], a2);
+                acc -= a2;
+            }
+        }
     }
     part[q * kFiberGemvRows + lr] = acc;
     __syncthreads();
@@ -67,114 +130,28 @@ __global__ void __launch_bounds__(kFiberGemvThreads)
 #pragma unroll
         for (int u = 1; u < kFiberGemvSlices; ++u)
             s += part[u * kFiberGemvRows + lr];
-        if (MODE == 0) {
-            out[it.out_off + row] = s;
-        } else {
-            const int k = row / it.n_nodes, i = row - k * it.n_nodes;
+        if (MODE == 1) {
+            const int k = row / n, i = row - k * n;
             out[3 * (it.out_off + i) + k] = s;
-        }
-    }
-}
-
-// One CTA per fiber of the launch (fiber_offset points at the first of them; xs, v, res, v_boundary, length_prev,
-// plus_velocity and the class offsets are indexed from that fiber).  res[4*off + r] += -(P vT)[r] (r < 4n-14) + xs_vT[r] + y_BC[r]   (ffd.cpp:276-312)
-//   vT = [v_x; v_y; v_z; D_1^T (xs_x v_x + xs_y v_y + xs_z v_z)],  D_1 = D_1_0 * 2 / length_prev   (:280-293)
-//   xs_vT[bc+3] = v_0 . xs_0;  xs_vT[bc+10] = v_{n-1} . xs_{n-1} when the plus end has a velocity BC  (:298-309)
-//   y_BC[bc .. bc+7) = v_boundary(:, fiber)                                                           (:303-306)
-// with bc = 4n - 14.  D_1_0 (n x n) and P_downsample_bc ((4n-14) x 4n) are column-major, shared by every fiber with
-// the same node count; class_D / class_P give their element offsets in `class_mats` per fiber.
-__global__ void __launch_bounds__(256)
-    fiber_velocity_kernel(const long long *__restrict__ fiber_offset, const double *__restrict__ xs_all,
-                          const double *__restrict__ v_all, const double *__restrict__ length_prev,
-                          const int *__restrict__ plus_velocity, const double *__restrict__ class_mats,
-                          const long long *__restrict__ class_D, const long long *__restrict__ class_P,
-                          const double *__restrict__ v_boundary, double *__restrict__ res) {
-    extern __shared__ double fv_smem[];
-    const int f = blockIdx.x;
-    const long long off = fiber_offset[f] - fiber_offset[0]; // node offset among the fibers of this launch
-    const int n = (int)(fiber_offset[f + 1] - fiber_offset[f]);
-    double *vT = fv_smem;      // 4n
-    double *s = fv_smem + 4 * n; // n
-    const double *xs = xs_all + 3 * off, *v = v_all + 3 * off;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const double vx = v[3 * i], vy = v[3 * i + 1], vz = v[3 * i + 2];
-        vT[i] = vx;
-        vT[n + i] = vy;
-        vT[2 * n + i] = vz;
-        s[i] = xs[3 * i] * vx + xs[3 * i + 1] * vy + xs[3 * i + 2] * vz;
-    }
-    __syncthreads();
-    const double scale = 2.0 / length_prev[f];
-    const double *D = class_mats + class_D[f];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, n_warps = blockDim.x >> 5;
-    for (int j = warp; j < n; j += n_warps) { // one warp per entry: (D_1^T s)[j] = sum_i D_1(i, j) s_i, column j contiguous
-        const double *col = D + (long long)j * n;
-        double acc = 0.0;
-        for (int i = lane; i < n; i += 32)
-            acc = fma(col[i], s[i], acc);
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1)
-            acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0)
-            vT[3 * n + j] = scale * acc;
-    }
-    __syncthreads();
-    // -(P vT): row r of P_downsample_bc by thread lr of column slice sl; S slices when the rows leave threads idle
-    const int bc = 4 * n - 14, n4 = 4 * n;
-    const double *P = class_mats + class_P[f];
-    const int rp32 = (bc + 31) & ~31;
-    const int S = 2 * rp32 <= (int)blockDim.x ? (int)blockDim.x / rp32 : 1; // column slices per row
-    const int rp = S == 1 ? (int)blockDim.x : rp32;                         // threads per slice
-    const int sl = threadIdx.x / rp, lr = threadIdx.x - sl * rp;
-    double *part = fv_smem + 5 * n;                        // S x rp <= blockDim.x partial sums
-    double *out = res + 4 * off;
-    if (S == 1) {
-        for (int r = lr; r < bc; r += rp) {
-            const double *p = P + r;
-            double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-            for (int j = 0; j + 3 < n4; j += 4) {
-                a0 = fma(p[(long long)j * bc], vT[j], a0);
-                a1 = fma(p[(long long)(j + 1) * bc], vT[j + 1], a1);
-                a2 = fma(p[(long long)(j + 2) * bc], vT[j + 2], a2);
-                a3 = fma(p[(long long)(j + 3) * bc], vT[j + 3], a3);
+        } else {
+            if (MODE == 2) {
+                // the 14 boundary rows: xs_vT and y_BC                                     (ffd.cpp:298-309)
+                const int t = row - (4 * n - 14);
+                if (t >= 0) {
+                    const long long node_off = it.x_off / 4;
+                    const double *xt = va.xs + 3 * node_off, *v = va.v + 3 * node_off;
+                    if (t == 3)
+                        s += v[0] * xt[0] + v[1] * xt[1] + v[2] * xt[2];
+                    if (va.v_boundary && t < 7)
+                        s += va.v_boundary[7 * (long long)it.fiber + t];
+                    if (t == 10 && va.plus_velocity[it.fiber]) {
+                        const int e = 3 * (n - 1);
+                        s += v[e] * xt[e] + v[e + 1] * xt[e + 1] + v[e + 2] * xt[e + 2];
+                    }
+                }
             }
-            out[r] -= (a0 + a1) + (a2 + a3);
+            out[it.out_off + row] = s;
         }
-    } else {
-        double a0 = 0.0, a1 = 0.0;
-        if (sl < S && lr < bc) {
-            const double *p = P + lr;
-            int j = sl;
-            for (; j + S < n4; j += 2 * S) {
-                a0 = fma(p[(long long)j * bc], vT[j], a0);
-                a1 = fma(p[(long long)(j + S) * bc], vT[j + S], a1);
-            }
-            if (j < n4)
-                a0 = fma(p[(long long)j * bc], vT[j], a0);
-        }
-        if (sl < S)
-            part[sl * rp + lr] = a0 + a1;
-        __syncthreads();
-        if (sl == 0 && lr < bc) {
-            double sum = part[lr];
-            for (int u = 1; u < S; ++u)
-                sum += part[u * rp + lr];
-            out[lr] -= sum;
-        }
-    }
-    // the 14 boundary rows: xs_vT and y_BC
-    if (threadIdx.x < 14) {
-        const int t = threadIdx.x;
-        double val = 0.0;
-        if (t == 3)
-            val += v[0] * xs[0] + v[1] * xs[1] + v[2] * xs[2];
-        if (v_boundary && t < 7)
-            val += v_boundary[7 * (long long)f + t];
-        if (t == 10 && plus_velocity[f]) {
-            const int e = 3 * (n - 1);
-            val += v[e] * xs[e] + v[e + 1] * xs[e + 1] + v[e + 2] * xs[e + 2];
-        }
-        out[bc + t] += val;
     }
 }
 

@@ -35,6 +35,12 @@ const char *last_error();
 void count_launch(int n);
 long long launch_count();
 
+// Large host -> device copy from PAGEABLE caller memory (per-timestep operator uploads, hundreds of MB): the bytes are
+// moved into pinned staging buffers by several host threads while the previous chunk is on the PCIe bus, instead of
+// the driver's single-threaded staging path.  Synchronous for the host buffer (it may be reused on return); the device
+// side is ordered on `st`.
+int upload_pageable(void *d_dst, const void *h_src, size_t bytes, cudaStream_t st);
+
 DeviceInfo query_device(int dev);
 LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_src_tiles, int force_T, int force_S);
 int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const double *d_f_packed, long long n_src,

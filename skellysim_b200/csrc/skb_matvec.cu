@@ -107,8 +107,8 @@ struct skb_flow {
     std::map<int, FiberClass> fiber_classes;
     bool ops_ready = false;
     int n_items_A = 0, n_items_F = 0;
-    size_t gemv_smem = 0, fvel_smem = 0;
-    DevBuf op_A, op_F, op_xs, op_len, op_plus, op_class, op_classD, op_classP, items_A, items_F;
+    size_t gemv_smem = 0;
+    DevBuf op_A, op_F, op_xs, op_len, op_plus, op_class, op_classD, op_classP, op_classR, op_ranges, items_A, items_F;
     DevBuf x_fib, res_fib, vb, res_shell, op_Ainv, tmp_b;
     long long op_A_elems = 0;               // elements of the concatenated A_ (and of A_^-1)
     unsigned long long ops_gen = 0, precond_gen = 0; // the preconditioner belongs to one set of operators
@@ -410,7 +410,7 @@ int skb_flow_destroy(skb_flow *fl) {
     DevBuf *bufs[] = {&fl->fiber_offset, &fl->fiber_length, &fl->r_fib, &fl->r_shell, &fl->r_body, &fl->centers,
                       &fl->pt_pos, &fl->pt_force, &fl->pt_torque, &fl->in_fib, &fl->in_shell, &fl->in_body, &fl->in_force, &fl->in_torque, &fl->vel, &fl->tmp,
                       &fl->op_A, &fl->op_F, &fl->op_xs, &fl->op_len, &fl->op_plus, &fl->op_class, &fl->op_classD,
-                      &fl->op_classP, &fl->items_A, &fl->items_F, &fl->x_fib, &fl->res_fib, &fl->vb, &fl->res_shell, &fl->op_Ainv, &fl->tmp_b};
+                      &fl->op_classP, &fl->op_classR, &fl->op_ranges, &fl->items_A, &fl->items_F, &fl->x_fib, &fl->res_fib, &fl->vb, &fl->res_shell, &fl->op_Ainv, &fl->tmp_b};
     for (DevBuf *b : bufs)
         b->release();
     fl->g_matvec.reset();
@@ -1301,15 +1301,29 @@ int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *fo
     }
     if (!A || !force_operator || !xs || !length_prev || !plus_bc_velocity)
         return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_operators: NULL argument");
-    // class matrices -> one device buffer, per-fiber offsets into it
+    // class matrices -> one device buffer, per-fiber offsets into it; per class also the non-zero column range of every
+    // row of P_downsample_bc (block diagonal in the reference, ffd.cpp:551-555: the kernel walks the range only)
     std::vector<double> h_class;
+    std::vector<int2> h_ranges;
     std::map<int, std::pair<long long, long long>> class_off;
+    std::map<int, long long> range_off;
     for (const auto &kv : fl->fiber_classes) {
         class_off[kv.first] = {(long long)h_class.size(), (long long)(h_class.size() + kv.second.D.size())};
         h_class.insert(h_class.end(), kv.second.D.begin(), kv.second.D.end());
         h_class.insert(h_class.end(), kv.second.P.begin(), kv.second.P.end());
+        const int nn = kv.first, bc = 4 * nn - 14;
+        range_off[nn] = (long long)h_ranges.size();
+        for (int r = 0; r < bc; ++r) {
+            int c0 = 4 * nn, c1 = 0;
+            for (int c = 0; c < 4 * nn; ++c)
+                if (kv.second.P[(size_t)c * bc + r] != 0.0) {
+                    c0 = std::min(c0, c);
+                    c1 = c + 1;
+                }
+            h_ranges.push_back(c1 > c0 ? make_int2(c0, c1) : make_int2(0, 0));
+        }
     }
-    std::vector<long long> cD((size_t)nfib), cP((size_t)nfib);
+    std::vector<long long> cD((size_t)nfib), cP((size_t)nfib), cR((size_t)nfib);
     std::vector<FiberGemvItem> itA, itF;
     long long offA = 0, offF = 0;
     int max_n = 0;
@@ -1324,17 +1338,18 @@ int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *fo
             return set_error(SKB_ERR_INVALID, "fiber %d: length_prev = %g", f0 + f, length_prev[f]);
         cD[f] = it->second.first;
         cP[f] = it->second.second;
+        cR[f] = range_off[n];
         max_n = std::max(max_n, n);
         const long long node_off = fl->h_fiber_off[(size_t)(f0 + f)] - node0;
         for (int r0 = 0; r0 < 4 * n; r0 += kFiberGemvRows)
-            itA.push_back(FiberGemvItem{offA, 4 * node_off, 4 * node_off, 4 * n, 4 * n, r0, n});
+            itA.push_back(FiberGemvItem{offA, 4 * node_off, 4 * node_off, 4 * n, 4 * n, r0, n, f, 0});
         for (int r0 = 0; r0 < 3 * n; r0 += kFiberGemvRows)
-            itF.push_back(FiberGemvItem{offF, 4 * node_off, node_off, 3 * n, 4 * n, r0, n});
+            itF.push_back(FiberGemvItem{offF, 4 * node_off, node_off, 3 * n, 4 * n, r0, n, f, 0});
         offA += 16LL * n * n;
         offF += 12LL * n * n;
     }
-    fl->gemv_smem = ((size_t)((4 * max_n + 1) & ~1) + kFiberGemvThreads) * sizeof(double);
-    fl->fvel_smem = ((size_t)5 * max_n + 256) * sizeof(double); // vT, s, column-slice partials
+    // x (4n) + slice partials + vT (4n) + s (n)
+    fl->gemv_smem = ((size_t)2 * ((4 * max_n + 1) & ~1) + kFiberGemvThreads + (size_t)max_n) * sizeof(double);
     if (fl->gemv_smem > 200 * 1024)
         return set_error(SKB_ERR_INVALID, "fiber with %d nodes exceeds the shared-memory fiber operator kernels", max_n);
     if (fl->gemv_smem > 48 * 1024) {
@@ -1342,24 +1357,27 @@ int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *fo
                                       (int)fl->gemv_smem));
         CUDA_TRY(cudaFuncSetAttribute(fiber_gemv_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)fl->gemv_smem));
+        CUDA_TRY(cudaFuncSetAttribute(fiber_gemv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)fl->gemv_smem));
     }
-    if (fl->fvel_smem > 48 * 1024)
-        CUDA_TRY(cudaFuncSetAttribute(fiber_velocity_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)fl->fvel_smem));
     const long long nf = fl->fb - fl->fa; // nodes of the own fibers
     auto put = [&](DevBuf &b, const void *h, size_t bytes) -> int {
         SKB_TRY(b.ensure(bytes));
         CUDA_TRY(cudaMemcpyAsync(b.ptr, h, bytes, cudaMemcpyHostToDevice, fl->stream));
         return SKB_OK;
     };
-    SKB_TRY(put(fl->op_A, A, (size_t)offA * 8));
-    SKB_TRY(put(fl->op_F, force_operator, (size_t)offF * 8));
+    SKB_TRY(fl->op_A.ensure((size_t)offA * 8));
+    SKB_TRY(fl->op_F.ensure((size_t)offF * 8));
+    SKB_TRY(upload_pageable(fl->op_A.ptr, A, (size_t)offA * 8, fl->stream));
+    SKB_TRY(upload_pageable(fl->op_F.ptr, force_operator, (size_t)offF * 8, fl->stream));
     SKB_TRY(put(fl->op_xs, xs, (size_t)nf * 24));
     SKB_TRY(put(fl->op_len, length_prev, (size_t)nfib * 8));
     SKB_TRY(put(fl->op_plus, plus_bc_velocity, (size_t)nfib * sizeof(int)));
     SKB_TRY(put(fl->op_class, h_class.data(), h_class.size() * 8));
     SKB_TRY(put(fl->op_classD, cD.data(), cD.size() * 8));
     SKB_TRY(put(fl->op_classP, cP.data(), cP.size() * 8));
+    SKB_TRY(put(fl->op_classR, cR.data(), cR.size() * 8));
+    SKB_TRY(put(fl->op_ranges, h_ranges.data(), h_ranges.size() * sizeof(int2)));
     SKB_TRY(put(fl->items_A, itA.data(), itA.size() * sizeof(FiberGemvItem)));
     SKB_TRY(put(fl->items_F, itF.data(), itF.size() * sizeof(FiberGemvItem)));
     SKB_TRY(fl->x_fib.ensure((size_t)nf * 32));
@@ -1385,9 +1403,7 @@ int skb_flow_set_fiber_preconditioner(skb_flow *fl, const double *A_inv) {
             return set_error(SKB_ERR_INVALID, "skb_flow_set_fiber_preconditioner: NULL argument");
         CUDA_TRY(cudaSetDevice(fl->dev));
         SKB_TRY(fl->op_Ainv.ensure((size_t)fl->op_A_elems * 8));
-        CUDA_TRY(cudaMemcpyAsync(fl->op_Ainv.ptr, A_inv, (size_t)fl->op_A_elems * 8, cudaMemcpyHostToDevice,
-                                 fl->stream));
-        CUDA_TRY(cudaStreamSynchronize(fl->stream));
+        SKB_TRY(upload_pageable(fl->op_Ainv.ptr, A_inv, (size_t)fl->op_A_elems * 8, fl->stream));
     }
     fl->precond_gen = fl->ops_gen;
     return SKB_OK;
@@ -1407,27 +1423,33 @@ static int fiber_force_dev(skb_flow *fl, const double *d_x, double *d_fw) {
     if (fl->n_items_F == 0)
         return SKB_OK;
     fiber_gemv_kernel<1><<<fl->n_items_F, kFiberGemvThreads, fl->gemv_smem, fl->cur>>>(
-        (const FiberGemvItem *)fl->items_F.ptr, (const double *)fl->op_F.ptr, d_x, d_fw);
+        (const FiberGemvItem *)fl->items_F.ptr, (const double *)fl->op_F.ptr, d_x, d_fw, FiberVelArgs{});
     CUDA_TRY(cudaGetLastError());
     count_launch(1);
     fl->launches += 1;
     return SKB_OK;
 }
 
-// res = A_ x - P_downsample_bc vT(v) + xs_vT + y_BC per fiber (ffd.cpp:276-312); on fl->cur
+// res = A_ x - P_downsample_bc vT(v) + xs_vT + y_BC per fiber (ffd.cpp:276-312), one launch; on fl->cur
 static int fiber_matvec_dev(skb_flow *fl, const double *d_x, const double *d_v, const double *d_vb, double *d_res) {
     if (fl->n_items_A == 0)
         return SKB_OK;
-    fiber_gemv_kernel<0><<<fl->n_items_A, kFiberGemvThreads, fl->gemv_smem, fl->cur>>>(
-        (const FiberGemvItem *)fl->items_A.ptr, (const double *)fl->op_A.ptr, d_x, d_res);
+    FiberVelArgs va;
+    va.xs = (const double *)fl->op_xs.ptr;
+    va.v = d_v;
+    va.length_prev = (const double *)fl->op_len.ptr;
+    va.plus_velocity = (const int *)fl->op_plus.ptr;
+    va.class_mats = (const double *)fl->op_class.ptr;
+    va.class_D = (const long long *)fl->op_classD.ptr;
+    va.class_P = (const long long *)fl->op_classP.ptr;
+    va.row_range = (const int2 *)fl->op_ranges.ptr;
+    va.class_R = (const long long *)fl->op_classR.ptr;
+    va.v_boundary = d_vb;
+    fiber_gemv_kernel<2><<<fl->n_items_A, kFiberGemvThreads, fl->gemv_smem, fl->cur>>>(
+        (const FiberGemvItem *)fl->items_A.ptr, (const double *)fl->op_A.ptr, d_x, d_res, va);
     CUDA_TRY(cudaGetLastError());
-    fiber_velocity_kernel<<<fl->op_f1 - fl->op_f0, 256, fl->fvel_smem, fl->cur>>>(
-        (const long long *)fl->fiber_offset.ptr + fl->op_f0, (const double *)fl->op_xs.ptr, d_v, (const double *)fl->op_len.ptr,
-        (const int *)fl->op_plus.ptr, (const double *)fl->op_class.ptr, (const long long *)fl->op_classD.ptr,
-        (const long long *)fl->op_classP.ptr, d_vb, d_res);
-    CUDA_TRY(cudaGetLastError());
-    count_launch(2);
-    fl->launches += 2;
+    count_launch(1);
+    fl->launches += 1;
     return SKB_OK;
 }
 
@@ -1437,7 +1459,7 @@ static int fiber_precond_dev(skb_flow *fl, const double *d_x, double *d_y) {
     if (fl->n_items_A == 0)
         return SKB_OK;
     fiber_gemv_kernel<0><<<fl->n_items_A, kFiberGemvThreads, fl->gemv_smem, fl->cur>>>(
-        (const FiberGemvItem *)fl->items_A.ptr, (const double *)fl->op_Ainv.ptr, d_x, d_y);
+        (const FiberGemvItem *)fl->items_A.ptr, (const double *)fl->op_Ainv.ptr, d_x, d_y, FiberVelArgs{});
     CUDA_TRY(cudaGetLastError());
     count_launch(1);
     fl->launches += 1;

@@ -18,6 +18,7 @@
 #include <memory>
 #include <mutex>
 #include <string>
+#include <thread>
 #include <vector>
 
 namespace skb {
@@ -231,6 +232,81 @@ void DevBuf::release() {
         cudaFree(ptr);
     ptr = nullptr;
     cap = 0;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pageable -> device upload through a pinned, multi-threaded staging ring
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct StagingRing {
+    static constexpr int kBufs = 4;
+    static constexpr size_t kChunk = 16u << 20;
+    void *buf[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+    bool ok = false;
+    std::mutex mu;
+    bool init() {
+        if (ok)
+            return true;
+        for (int i = 0; i < kBufs; ++i) {
+            if (cudaMallocHost(&buf[i], kChunk) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
+                (void)cudaGetLastError();
+                return false;
+            }
+        }
+        ok = true;
+        return true;
+    }
+};
+StagingRing g_ring; // pinned host memory is not tied to a device: one ring per process (calls are serialised)
+} // namespace
+
+int upload_pageable(void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
+    if (bytes == 0)
+        return SKB_OK;
+    std::lock_guard<std::mutex> lock(g_ring.mu);
+    if (bytes < (8u << 20) || !g_ring.init()) { // small, or no pinned memory to be had: the driver's own staging
+        cudaError_t e = cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st);
+        if (e != cudaSuccess)
+            return set_error(SKB_ERR_CUDA, "cudaMemcpyAsync H2D (%zu bytes): %s", bytes, cudaGetErrorString(e));
+        e = cudaStreamSynchronize(st);
+        return e == cudaSuccess ? SKB_OK : set_error(SKB_ERR_CUDA, "H2D copy: %s", cudaGetErrorString(e));
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    const int n_thr = (int)std::max(1u, std::min(8u, hw ? hw / 2 : 4u));
+    size_t done = 0;
+    int k = 0;
+    cudaError_t e = cudaSuccess;
+    while (done < bytes && e == cudaSuccess) {
+        const int b = k % StagingRing::kBufs;
+        const size_t len = std::min(StagingRing::kChunk, bytes - done);
+        if (k >= StagingRing::kBufs)
+            e = cudaEventSynchronize(g_ring.ev[b]); // the copy that last used this buffer has left it
+        if (e != cudaSuccess)
+            break;
+        const char *src = (const char *)h_src + done;
+        char *dst = (char *)g_ring.buf[b];
+        const size_t piece = (len + n_thr - 1) / n_thr;
+        std::vector<std::thread> th;
+        for (int t = 1; t < n_thr; ++t) {
+            const size_t o = std::min(len, (size_t)t * piece), l = std::min(piece, len - o);
+            if (l)
+                th.emplace_back([=] { std::memcpy(dst + o, src + o, l); });
+        }
+        std::memcpy(dst, src, std::min(piece, len));
+        for (auto &t : th)
+            t.join();
+        e = cudaMemcpyAsync((char *)d_dst + done, dst, len, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess)
+            e = cudaEventRecord(g_ring.ev[b], st);
+        done += len;
+        ++k;
+    }
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(st);
+    if (e != cudaSuccess)
+        return set_error(SKB_ERR_CUDA, "staged H2D copy (%zu bytes): %s", bytes, cudaGetErrorString(e));
+    return SKB_OK;
 }
 
 } // namespace skb

@@ -122,6 +122,44 @@ def test_apply_matvec_end_to_end(shape):
     assert np.array_equal(v_s, v_all[nf:nf + ns])
 
 
+@pytest.mark.parametrize("seed,clamp,pin", [(1, 0.0, 0.0), (2, 0.5, 0.5)])
+def test_apply_matvec_with_reference_shaped_operators(seed, clamp, pin):
+    """The same path on operators built the way the reference builds them (oracle/fiber_fd.py: Fornberg derivative
+    matrices, barycentric down-sampling, update_linear_operator / apply_bc_rectangular / update_force_operator):
+    P_downsample_bc is block diagonal (the kernel walks each row's non-zero columns only), D_1_0 banded, A_ carries its
+    14 boundary rows.  Allowed node counts only (fiber_finite_difference.cpp:522)."""
+    from oracle import fiber_fd
+    fib, shell, body = make_system(40 + seed, 45, 500, 260, 2, nodes=(8, 16, 24, 32, 48, 64, 96))
+    ops = fiber_fd.suspension_operators(fib["pos"], fib["n_nodes"], fib["lengths"], eta=0.9, seed=seed,
+                                        clamp_fraction=clamp, pin_fraction=pin)
+    for n, P in ops["P"].items():
+        assert np.count_nonzero(P) <= (4 * n - 14) * n        # block diagonal: at most n non-zeros per row
+    rng = np.random.default_rng(seed)
+    nf, ns = fib["pos"].shape[0], shell["pos"].shape[0]
+    x = rng.normal(size=4 * nf)
+    link = rng.normal(size=(len(ops["n_nodes"]), 7))
+    eta = 0.9
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        load_ops(fl, ops)
+        fl.set_fiber_preconditioner([np.linalg.inv(A) for A in ops["A"]])
+        res, v_s, v_b = fl.apply_matvec(x, shell["density"], body["density"], ft_of(body), eta, link)
+        fw = fl.apply_fiber_force(x)
+        y = fl.apply_fiber_preconditioner(x)
+    ref_res, ref_v = orc.apply_matvec_fibers(fib, shell, body, ops, x, eta, link)
+    _check(fw, orc.apply_fiber_force(ops["force"], x, ops["n_nodes"]))
+    _check(res, ref_res)
+    _check(v_s, ref_v[nf:nf + ns])
+    _check(v_b, ref_v[nf + ns:])
+    # fc.apply_preconditioner: LU solve in the reference, explicit inverse here; A_ of a discretised 4th-order
+    # operator is ill conditioned, so compare through the residual A y = x instead of y itself
+    off = 0
+    for A, n in zip(ops["A"], ops["n_nodes"]):
+        r = A @ y[4 * off:4 * off + 4 * n] - x[4 * off:4 * off + 4 * n]
+        assert np.abs(r).max() <= 1e-6 * max(1.0, np.abs(A).max() * np.abs(y[4 * off:4 * off + 4 * n]).max())
+        off += n
+
+
 def test_operator_errors():
     fib, shell, body = make_system(25, 6, 50, 0, 0, nodes=(8, 16))
     ops = make_ops(fib, 9)
@@ -186,7 +224,7 @@ def test_apply_matvec_with_periphery_dense_operator():
         two_step = dn.apply(skb.DENSE_STRESSLET_PLUS_COMPLEMENTARY, shell["density"].reshape(-1), v_s.reshape(-1))
         # wrong size is refused
         dn.set_matrix(skb.DENSE_STRESSLET_PLUS_COMPLEMENTARY, M[:-3, :-3])
-        with pytest.raises(skb.SkbError, match="periphery has"):
+        with pytest.raises(skb.SkbError, match="own rows"):
             fl.apply_matvec(x, shell["density"], body["density"], ft_of(body), eta, dense=dn)
     assert np.array_equal(res, res_d) and np.array_equal(v_b, v_b_d)
     assert np.array_equal(res_shell.reshape(-1), two_step)
