@@ -45,6 +45,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+os.environ.setdefault("NCCL_DEBUG", "WARN")  # (no "NCCL version ..." line on stdout next to the JSON line)
 
 SL_FLOP_PER_PAIR = 28  # SURVEY.md 8d / BASELINE.md 2.1 (kernels.cu:65-75)
 DL_FLOP_PER_PAIR = 40

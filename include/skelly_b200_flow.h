@@ -130,6 +130,10 @@ SKB_API int skb_flow_group_init(skb_flow *fl, int rank, int size);
 SKB_API int skb_flow_group_export(skb_flow *fl, void *handle_64_bytes);
 SKB_API int skb_flow_group_import(skb_flow *fl, int peer_rank, const void *handle_64_bytes);
 SKB_API int skb_flow_group_connect(skb_flow *fl, int peer_rank, skb_flow *peer);
+/* one matvec of this member alone (no flags, zero strengths) so that every buffer reaches its final size before the
+ * first real matvec: device-wide synchronisation by cudaMalloc / cudaFree must not happen while a peer ON THE SAME
+ * DEVICE waits on a flag.  Call after the ranges are set and all peers are connected; skb_mflow does it itself. */
+SKB_API int skb_flow_group_warmup(skb_flow *fl);
 /* after synchronising: *missing_peer = rank of a member whose flag never arrived within the time-out (a flag wait
  * gives up after ~10 s instead of hanging the GPU), or -1 */
 SKB_API int skb_flow_group_error(skb_flow *fl, int *missing_peer);

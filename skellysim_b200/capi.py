@@ -120,6 +120,7 @@ def library() -> C.CDLL:
         "skb_flow_group_import": ([ctxp, C.c_int, C.c_void_p], C.c_int),
         "skb_flow_group_connect": ([ctxp, C.c_int, ctxp], C.c_int),
         "skb_flow_group_error": ([ctxp, C.POINTER(C.c_int)], C.c_int),
+        "skb_flow_group_warmup": ([ctxp], C.c_int),
         "skb_flow_apply_matvec_device": ([ctxp, ctxp] + [C.c_void_p] * 6 + [C.c_double] + [C.c_void_p] * 4, C.c_int),
         "skb_partition_query": ([C.POINTER(C.c_int), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                  C.POINTER(C.c_int64)], C.c_int),
@@ -644,6 +645,9 @@ class Flow:
 
     def group_connect(self, peer_rank: int, peer: "Flow"):
         _check(library().skb_flow_group_connect(self._h, int(peer_rank), peer._h))
+
+    def group_warmup(self):
+        _check(library().skb_flow_group_warmup(self._h))
 
     def group_error(self) -> int:
         m = C.c_int(-1)

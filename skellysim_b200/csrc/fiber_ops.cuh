@@ -41,8 +41,9 @@ struct FiberVelArgs {
     const double *class_mats;  // D_1_0 (n x n) and P_downsample_bc ((4n-14) x 4n) of every node count, column-major
     const long long *class_D;  // [n_fibers] element offset of the fiber's D_1_0 in class_mats
     const long long *class_P;  // [n_fibers] ... of its P_downsample_bc
-    const int2 *row_range;     // per class: [4n-14] first / one-past-last non-zero column of every row of P
-    const long long *class_R;  // [n_fibers] element offset of the fiber's row ranges
+    const int2 *row_range;     // per class: [4n-14] first / one-past-last non-zero column of every row of P, then [n]
+                               // first / one-past-last non-zero row of every column of D_1_0 (banded: 5-point stencils)
+    const long long *class_R;  // [n_fibers] element offset of the fiber's ranges
     const double *v_boundary;  // [n_fibers*7] or nullptr
 };
 
@@ -60,36 +61,55 @@ __global__ void __launch_bounds__(kFiberGemvThreads)
     for (int j = threadIdx.x; j < it.cols; j += kFiberGemvThreads)
         xs_sh[j] = x[it.x_off + j];
     const int n = it.n_nodes;
+    int2 my_rg = make_int2(0, 0);
     if (MODE == 2) {
-        // vT = [v_x; v_y; v_z; D_1^T (xs . v)],  D_1 = D_1_0 * 2 / length_prev           (ffd.cpp:280-293)
+        // Which entries of vT = [v_x; v_y; v_z; D_1^T (xs . v)] (ffd.cpp:280-293) do this CTA's rows of P touch?  P is
+        // block diagonal, so a 32-row block needs one or two of the four segments -- and D_1^T s only for the last.
+        __shared__ int c_lo, c_hi;
+        if (threadIdx.x == 0) {
+            c_lo = 4 * n;
+            c_hi = 0;
+        }
+        __syncthreads();
+        const int bc = 4 * n - 14, row_t = it.row0 + (int)threadIdx.x;
+        if (threadIdx.x < kFiberGemvRows && row_t < bc) {
+            my_rg = va.row_range[va.class_R[it.fiber] + row_t];
+            if (my_rg.y > my_rg.x) {
+                atomicMin(&c_lo, my_rg.x);
+                atomicMax(&c_hi, my_rg.y);
+            }
+        }
+        __syncthreads();
+        const int lo = c_lo, hi = c_hi;
         const long long node_off = it.x_off / 4;
         const double *xt = va.xs + 3 * node_off, *v = va.v + 3 * node_off;
+        const bool need_D = hi > 3 * n;
         for (int i = threadIdx.x; i < n; i += kFiberGemvThreads) {
             const double vx = v[3 * i], vy = v[3 * i + 1], vz = v[3 * i + 2];
             vT[i] = vx;
             vT[n + i] = vy;
             vT[2 * n + i] = vz;
-            s_sh[i] = xt[3 * i] * vx + xt[3 * i + 1] * vy + xt[3 * i + 2] * vz;
+            if (need_D)
+                s_sh[i] = xt[3 * i] * vx + xt[3 * i + 1] * vy + xt[3 * i + 2] * vz;
         }
+        if (need_D) {
+            __syncthreads();
+            // (D_1^T s)[j] = sum_i D_1(i, j) s_i over the non-zero rows of column j, D_1 = D_1_0 * 2 / length_prev
+            const double scale = 2.0 / va.length_prev[it.fiber];
+            const double *D = va.class_mats + va.class_D[it.fiber];
+            const int2 *col_rg = va.row_range + va.class_R[it.fiber] + bc;
+            for (int j = threadIdx.x; j < n; j += kFiberGemvThreads) {
+                const int2 rg = col_rg[j];
+                const double *col = D + (long long)j * n;
+                double acc = 0.0;
+                for (int i = rg.x; i < rg.y; ++i)
+                    acc = fma(col[i], s_sh[i], acc);
+                vT[3 * n + j] = scale * acc;
+            }
+        }
+        (void)lo;
     }
     __syncthreads();
-    if (MODE == 2) {
-        const double scale = 2.0 / va.length_prev[it.fiber];
-        const double *D = va.class_mats + va.class_D[it.fiber];
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int j = warp; j < n; j += kFiberGemvThreads / 32) { // (D_1^T s)[j] = sum_i D_1(i, j) s_i, column j contiguous
-            const double *col = D + (long long)j * n;
-            double acc = 0.0;
-            for (int i = lane; i < n; i += 32)
-                acc = fma(col[i], s_sh[i], acc);
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1)
-                acc += __shfl_xor_sync(0xffffffffu, acc, o);
-            if (lane == 0)
-                vT[3 * n + j] = scale * acc;
-        }
-        __syncthreads();
-    }
     const int lr = threadIdx.x & (kFiberGemvRows - 1), q = threadIdx.x / kFiberGemvRows;
     const int row = it.row0 + lr;
     double acc = 0.0;
@@ -114,7 +134,7 @@ __global__ void __launch_bounds__(kFiberGemvThreads)
             // the reference (three (n-4) x n blocks and one (n-2) x n, ffd.cpp:551-555), 75 % structural zeros
             const int bc = 4 * n - 14;
             if (row < bc) {
-                const int2 rg = va.row_range[va.class_R[it.fiber] + row];
+                const int2 rg = va.row_range[va.class_R[it.fiber] + row]; // (L1-resident: read by the 8 slices of a row)
                 const double *p = va.class_mats + va.class_P[it.fiber] + row;
                 double a2 = 0.0;
                 for (int c = rg.x + q; c < rg.y; c += kFiberGemvSlices)

@@ -122,6 +122,7 @@ struct skb_flow {
         size_t off_flags = 0, off_fsl[2] = {0, 0}, off_fshell[2] = {0, 0}, off_xshell[2] = {0, 0}, off_upart = 0;
         long long n_fib = 0, n_shell = 0, n_pad_fib = 0, n_pad_shell = 0; // geometry the window was laid out for
         unsigned long long epoch = 0;
+        bool dry = false;             // warm-up pass: no flags, own window only (skb_flow_group_warmup)
         bool use_sym = false;         // fiber rows: symmetric block rows + pull-reduce (else own rows with the plain kernel)
         bool connected() const {
             for (int m = 0; m < size; ++m)
@@ -810,6 +811,8 @@ static int prepare_matvec_targets(skb_flow *fl) {
 // ---- group exchange steps (group_kernels.cuh) on fl->cur ---------------------------------------------------------
 static int group_flag(skb_flow *fl, int phase, bool do_signal, bool do_wait) {
     skb_flow::Group &G = fl->grp;
+    if (G.dry)
+        return SKB_OK;
     GroupFlagArgs a;
     for (int m = 0; m < G.size; ++m)
         a.flags[m] = G.at<unsigned long long>(m, G.off_flags);
@@ -832,7 +835,7 @@ static int group_flag(skb_flow *fl, int phase, bool do_signal, bool do_wait) {
 static int matvec_core_group(skb_flow *fl, const double *d_ff, const double *d_sd, const double *d_bd, const double *d_f,
                              const double *d_t, double eta, double *d_v) {
     skb_flow::Group &G = fl->grp;
-    if (!G.connected())
+    if (!G.dry && !G.connected())
         return set_error(SKB_ERR_STATE, "group member %d: not all peers are connected (skb_flow_group_import / _connect)",
                          G.rank);
     const long long ns = fl->n_shell, nf = fl->n_fib;
@@ -852,11 +855,12 @@ static int matvec_core_group(skb_flow *fl, const double *d_ff, const double *d_s
         a.sa = fl->sa;
         a.n_s = n_sw;
         a.two_eta = 2.0 * eta;
-        a.size = G.size;
-        for (int m = 0; m < G.size; ++m) {
-            a.f_sl[m] = G.at<double>(m, G.off_fsl[par]);
-            a.f_shell[m] = G.at<double>(m, G.off_fshell[par]);
-            a.x_shell[m] = G.at<double>(m, G.off_xshell[par]);
+        a.size = G.dry ? 1 : G.size;
+        for (int m = 0; m < a.size; ++m) {
+            const int who = G.dry ? G.rank : m;
+            a.f_sl[m] = G.at<double>(who, G.off_fsl[par]);
+            a.f_shell[m] = G.at<double>(who, G.off_fshell[par]);
+            a.x_shell[m] = G.at<double>(who, G.off_xshell[par]);
         }
         const long long work = 3 * n_fw + n_sw;
         if (work > 0) {
@@ -935,9 +939,9 @@ static int matvec_core_group(skb_flow *fl, const double *d_ff, const double *d_s
         SKB_TRY(group_flag(fl, 1, false, true));
         if (n_fw > 0) {
             GroupPullArgs a;
-            for (int m = 0; m < G.size; ++m)
-                a.u_part[m] = G.at<double>(m, G.off_upart);
-            a.size = G.size;
+            a.size = G.dry ? 1 : G.size;
+            for (int m = 0; m < a.size; ++m)
+                a.u_part[m] = G.at<double>(G.dry ? G.rank : m, G.off_upart);
             a.fa = fl->fa;
             a.n_f = n_fw;
             a.v = d_v;
@@ -1098,6 +1102,38 @@ int skb_flow_group_connect(skb_flow *fl, int peer_rank, skb_flow *peer) {
     }
     fl->grp.peer[peer_rank] = peer->grp.window;
     fl->grp.peer_ipc[peer_rank] = false;
+    return SKB_OK;
+}
+
+// One matvec of this member alone (no flags, own window only, zero strengths): every buffer of the path reaches its
+// steady-state size, so that no cudaMalloc / cudaFree -- which synchronise the whole DEVICE -- happens later while a
+// peer on the same device sits in a flag wait.  Needed when members share a GPU; harmless otherwise.
+int skb_flow_group_warmup(skb_flow *fl) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_group_warmup: NULL flow");
+    if (fl->grp.size <= 1)
+        return SKB_OK;
+    CUDA_TRY(cudaSetDevice(fl->dev));
+    SKB_TRY(prepare_matvec_targets(fl));
+    const long long n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa;
+    DevBuf z;
+    const size_t n_z = (size_t)std::max<long long>({4 * n_fw, 3 * n_sw, 3 * fl->n_body, 3LL * fl->n_bodies, 1LL});
+    SKB_TRY(z.ensure(n_z * 8));
+    CUDA_TRY(cudaMemsetAsync(z.ptr, 0, n_z * 8, fl->stream));
+    SKB_TRY(fl->vel.ensure((size_t)fl->n_win * 24 + 8));
+    SKB_TRY(fl->in_fib.ensure((size_t)n_fw * 24 + 8));
+    fl->cur = fl->stream;
+    fl->grp.dry = true;
+    const double *zp = (const double *)z.ptr;
+    int rc = matvec_core_group(fl, zp, zp, zp, zp, zp, 1.0, (double *)fl->vel.ptr);
+    fl->grp.dry = false;
+    cudaError_t e = cudaStreamSynchronize(fl->stream);
+    fl->grp.epoch = 0;
+    z.release();
+    if (rc != SKB_OK)
+        return rc;
+    if (e != cudaSuccess)
+        return set_error(SKB_ERR_CUDA, "skb_flow_group_warmup: %s", cudaGetErrorString(e));
     return SKB_OK;
 }
 
@@ -1321,6 +1357,15 @@ int skb_flow_set_fiber_operators(skb_flow *fl, const double *A, const double *fo
                     c1 = c + 1;
                 }
             h_ranges.push_back(c1 > c0 ? make_int2(c0, c1) : make_int2(0, 0));
+        }
+        for (int j = 0; j < nn; ++j) { // D_1_0 (n x n, column-major): non-zero row range of every column (banded)
+            int i0 = nn, i1 = 0;
+            for (int i = 0; i < nn; ++i)
+                if (kv.second.D[(size_t)j * nn + i] != 0.0) {
+                    i0 = std::min(i0, i);
+                    i1 = i + 1;
+                }
+            h_ranges.push_back(i1 > i0 ? make_int2(i0, i1) : make_int2(0, 0));
         }
     }
     std::vector<long long> cD((size_t)nfib), cP((size_t)nfib), cR((size_t)nfib);
@@ -1936,6 +1981,8 @@ static int mflow_prepare(skb_mflow *mf) {
         for (int h = 0; h < mf->n; ++h)
             if (g != h)
                 SKB_TRY(skb_flow_group_connect(mf->m[g], h, mf->m[h]));
+    for (int g = 0; g < mf->n; ++g) // all allocations up front: members may share a device (see skb_flow_group_warmup)
+        SKB_TRY(skb_flow_group_warmup(mf->m[g]));
     mf->part_dirty = false;
     mf->ops_ready = false;
     return SKB_OK;

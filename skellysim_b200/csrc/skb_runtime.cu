@@ -241,31 +241,44 @@ namespace {
 struct StagingRing {
     static constexpr int kBufs = 4;
     static constexpr size_t kChunk = 16u << 20;
+    static constexpr int kMaxDev = 64;
     void *buf[kBufs] = {nullptr, nullptr, nullptr, nullptr};
-    cudaEvent_t ev[kBufs] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[kMaxDev][kBufs] = {}; // events belong to a device: one set per device that uploads
+    bool ev_ok[kMaxDev] = {};
     bool ok = false;
     std::mutex mu;
-    bool init() {
-        if (ok)
-            return true;
-        for (int i = 0; i < kBufs; ++i) {
-            if (cudaMallocHost(&buf[i], kChunk) != cudaSuccess || cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming) != cudaSuccess) {
-                (void)cudaGetLastError();
-                return false;
-            }
+    bool init(int dev) {
+        if (dev < 0 || dev >= kMaxDev)
+            return false;
+        if (!ok) {
+            for (int i = 0; i < kBufs; ++i)
+                if (cudaMallocHost(&buf[i], kChunk) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    return false;
+                }
+            ok = true;
         }
-        ok = true;
+        if (!ev_ok[dev]) {
+            for (int i = 0; i < kBufs; ++i)
+                if (cudaEventCreateWithFlags(&ev[dev][i], cudaEventDisableTiming) != cudaSuccess) {
+                    (void)cudaGetLastError();
+                    return false;
+                }
+            ev_ok[dev] = true;
+        }
         return true;
     }
 };
-StagingRing g_ring; // pinned host memory is not tied to a device: one ring per process (calls are serialised)
+StagingRing g_ring; // pinned host memory is not tied to a device: one ring per process (uploads are serialised)
 } // namespace
 
 int upload_pageable(void *d_dst, const void *h_src, size_t bytes, cudaStream_t st) {
     if (bytes == 0)
         return SKB_OK;
     std::lock_guard<std::mutex> lock(g_ring.mu);
-    if (bytes < (8u << 20) || !g_ring.init()) { // small, or no pinned memory to be had: the driver's own staging
+    int dev = -1;
+    (void)cudaGetDevice(&dev); // the caller made the stream's device current
+    if (bytes < (8u << 20) || !g_ring.init(dev)) { // small, or no pinned memory to be had: the driver's own staging
         cudaError_t e = cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, st);
         if (e != cudaSuccess)
             return set_error(SKB_ERR_CUDA, "cudaMemcpyAsync H2D (%zu bytes): %s", bytes, cudaGetErrorString(e));
@@ -281,7 +294,7 @@ int upload_pageable(void *d_dst, const void *h_src, size_t bytes, cudaStream_t s
         const int b = k % StagingRing::kBufs;
         const size_t len = std::min(StagingRing::kChunk, bytes - done);
         if (k >= StagingRing::kBufs)
-            e = cudaEventSynchronize(g_ring.ev[b]); // the copy that last used this buffer has left it
+            e = cudaEventSynchronize(g_ring.ev[dev][b]); // the copy that last used this buffer has left it
         if (e != cudaSuccess)
             break;
         const char *src = (const char *)h_src + done;
@@ -298,7 +311,7 @@ int upload_pageable(void *d_dst, const void *h_src, size_t bytes, cudaStream_t s
             t.join();
         e = cudaMemcpyAsync((char *)d_dst + done, dst, len, cudaMemcpyHostToDevice, st);
         if (e == cudaSuccess)
-            e = cudaEventRecord(g_ring.ev[b], st);
+            e = cudaEventRecord(g_ring.ev[dev][b], st);
         done += len;
         ++k;
     }

@@ -102,6 +102,7 @@ def connect_group(flow, rank: int, world: int, group=None):
     for r in range(world):
         if r != rank:
             flow.group_import(r, handles[r])
+    flow.group_warmup()  # every buffer at its final size before the first flag wait
     dist.barrier(group=group)
 
 

@@ -305,3 +305,72 @@ def test_rank_apply_matvec_sequencing_and_collectives(tmp_path, world):
     assert np.array_equal(np.concatenate([p["res"] for p in parts]), ref_res)
     assert np.array_equal(np.concatenate([p["v_s"] for p in parts]), ref_v[nf:nf + ns])
     assert np.array_equal(np.concatenate([p["v_b"] for p in parts]), ref_v[nf + ns:])
+
+
+# ---- the peer-memory group protocol (group_kernels.cuh / matvec_core_group), emulated on CPU with gloo ----------------
+def _group_worker(rank, world, port, n_fibers, n_shell, block, out_dir):
+    """One group member: push (all-gather of the own strengths), partial fiber velocities from the member's serpentine
+    block rows of the symmetric fiber-fiber interaction (both directions of every block pair + own diagonal blocks),
+    complete sums on the own periphery rows, pull (sum of the members' partials on the own fiber rows)."""
+    sys.path.insert(0, ROOT)
+    import oracle as orc
+    from skellysim_b200 import capi
+    from skellysim_b200.distributed import sym_block_pairs
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(11)
+    n_nodes = rng.choice([8, 16, 24], size=n_fibers).astype(np.int32)
+    off = np.concatenate([[0], np.cumsum(n_nodes)])
+    nf = int(off[-1])
+    r_fib, r_shell = rng.uniform(-1, 1, (nf, 3)), rng.uniform(-2, 2, (n_shell, 3))
+    f = rng.uniform(-1, 1, (nf, 3))
+    f0, f1, s0, s1, _, _ = capi.partition_query(n_nodes, n_shell, 0, world, rank)
+    a, b = int(off[f0]), int(off[f1])
+    # PUSH: every member contributes the strengths of its own fibers only
+    pieces = [None] * world
+    dist.all_gather_object(pieces, (a, f[a:b]))
+    f_all = np.zeros((nf, 3))
+    for (pa, pf) in pieces:
+        f_all[pa:pa + pf.shape[0]] = pf
+    assert np.array_equal(f_all, f)
+    # partial sums over the member's block rows (both directions), blocks of `block` nodes
+    nb = -(-nf // block)
+    blk = lambda i: slice(i * block, min(nf, (i + 1) * block))
+    u_part = np.zeros((nf, 3))
+    for (i, j) in sym_block_pairs(nb, rank, world):
+        u_part[blk(i)] += orc.stokeslet_direct(r_fib[blk(j)], f_all[blk(j)], r_fib[blk(i)])
+        if j != i:
+            u_part[blk(j)] += orc.stokeslet_direct(r_fib[blk(i)], f_all[blk(i)], r_fib[blk(j)])
+    v_shell_own = orc.stokeslet_direct(r_fib, f_all, r_shell[s0:s1])         # remainder rows: complete on the owner
+    # PULL: own fiber rows = sum over the members' partials
+    t = torch.from_numpy(u_part)
+    dist.all_reduce(t)
+    np.save(os.path.join(out_dir, f"g_{rank}.npy"), np.concatenate([t.numpy()[a:b], v_shell_own]))
+    np.save(os.path.join(out_dir, f"r_{rank}.npy"), np.array([a, b, s0, s1]))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world,n_fibers,n_shell,block", [(2, 9, 21, 32), (3, 14, 5, 16), (2, 3, 0, 64)])
+def test_group_protocol_tiles_the_global_result(tmp_path, world, n_fibers, n_shell, block):
+    import oracle as orc
+    port = _free_port()
+    mp.spawn(_group_worker, args=(world, port, n_fibers, n_shell, block, str(tmp_path)), nprocs=world, join=True)
+    rng = np.random.default_rng(11)
+    n_nodes = rng.choice([8, 16, 24], size=n_fibers).astype(np.int32)
+    nf = int(n_nodes.sum())
+    r_fib, r_shell = rng.uniform(-1, 1, (nf, 3)), rng.uniform(-2, 2, (n_shell, 3))
+    f = rng.uniform(-1, 1, (nf, 3))
+    ref = orc.stokeslet_direct(r_fib, f, np.concatenate([r_fib, r_shell]))
+    fib_rows, shell_rows = [], []
+    for r in range(world):
+        a, b, s0, s1 = np.load(tmp_path / f"r_{r}.npy")
+        got = np.load(tmp_path / f"g_{r}.npy")
+        want = np.concatenate([ref[a:b], ref[nf + s0:nf + s1]])
+        assert got.shape == want.shape
+        assert np.abs(got - want).max() <= 1e-12 * np.abs(ref).max()
+        fib_rows.append((a, b))
+        shell_rows.append((s0, s1))
+    assert fib_rows[0][0] == 0 and fib_rows[-1][1] == nf and shell_rows[-1][1] == n_shell
+    for (x, y) in zip(fib_rows, fib_rows[1:]):
+        assert x[1] == y[0]

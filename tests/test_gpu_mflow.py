@@ -140,6 +140,8 @@ def test_group_members_in_one_process_by_hand():
             fl.group_init(g, 2)
         members[0].group_connect(1, members[1])
         members[1].group_connect(0, members[0])
+        for fl in members:   # members share GPU 0: all allocations before the first flag wait
+            fl.group_warmup()
         outs, streams = [], [torch.cuda.Stream(), torch.cuda.Stream()]
         dev = torch.device("cuda", 0)
         t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
@@ -148,9 +150,12 @@ def test_group_members_in_one_process_by_hand():
             ins = [t(fib["forces"][off[f0]:off[f1]]), t(shell["density"][s0:s1]), t(body["density"]), t(body["forces"]),
                    t(body["torques"])]
             out = torch.empty(((off[f1] - off[f0]) + (s1 - s0) + (b1 - b0), 3), dtype=torch.float64, device=dev)
-            torch.cuda.synchronize()
-            fl.matvec_device(*[x.data_ptr() for x in ins], eta, out.data_ptr(), streams[g].cuda_stream)
             outs.append((out, ins))
+        torch.cuda.synchronize()
+        # (no host synchronisation between the two launches: member 0 sits in its flag wait until member 1 has pushed)
+        for g, fl in enumerate(members):
+            out, ins = outs[g]
+            fl.matvec_device(*[x.data_ptr() for x in ins], eta, out.data_ptr(), streams[g].cuda_stream)
         torch.cuda.synchronize()
         assert all(fl.group_error() < 0 for fl in members)
         for g in range(2):
