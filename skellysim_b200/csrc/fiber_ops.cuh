@@ -61,6 +61,18 @@ __global__ void __launch_bounds__(kFiberGemvThreads)
     for (int j = threadIdx.x; j < it.cols; j += kFiberGemvThreads)
         xs_sh[j] = x[it.x_off + j];
     const int n = it.n_nodes;
+    // the first batch of this thread's matrix elements goes out to HBM NOW: the requests are in flight while the
+    // velocity preamble of MODE 2 (a few shared-memory passes and barriers) runs
+    const int lr0 = threadIdx.x & (kFiberGemvRows - 1), q0 = threadIdx.x / kFiberGemvRows;
+    const bool row_ok = it.row0 + lr0 < it.rows;
+    const bool first_ok = row_ok && q0 + 7 * kFiberGemvSlices < it.cols;
+    double v0[8];
+    if (first_ok) {
+        const double *m0 = mats + it.mat_off + it.row0 + lr0;
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            v0[u] = __ldg(m0 + (long long)(q0 + u * kFiberGemvSlices) * it.rows);
+    }
     int2 my_rg = make_int2(0, 0);
     if (MODE == 2) {
         // Which entries of vT = [v_x; v_y; v_z; D_1^T (xs . v)] (ffd.cpp:280-293) do this CTA's rows of P touch?  P is
@@ -117,6 +129,12 @@ __global__ void __launch_bounds__(kFiberGemvThreads)
         const double *m = mats + it.mat_off + row;
         const long long ld = it.rows;
         int j = q;
+        if (first_ok) { // (loaded before the preamble)
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                acc = fma(v0[u], xs_sh[j + u * kFiberGemvSlices], acc);
+            j += 8 * kFiberGemvSlices;
+        }
         // 8 independent loads in flight per thread
         for (; j + 7 * kFiberGemvSlices < it.cols; j += 8 * kFiberGemvSlices) {
             double v[8];

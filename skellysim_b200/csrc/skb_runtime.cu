@@ -122,7 +122,9 @@ LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_sr
         const long long tile_t = (long long)kCtaThreads * T;
         const long long n_tiles_t = (n_trg + tile_t - 1) / tile_t;
         // efficiency of the inner loop vs T (LDS + loop overhead amortised over T pairs); calibrated on B200
-        const double t_pen = (T == 1) ? 1.12 : (T == 2) ? 1.05 : (T == 4) ? 1.0 : 0.955; // profiles/r1_probe_perf_v3.json
+        // measured Stokeslet rates on B200: T=8 712, T=4 691, T=2 ~614 Gpairs/s (profiles/r1_probe_perf_v3.json,
+        // profiles/r2_launches_bench.md); T=1 extrapolated
+        const double t_pen = (T == 1) ? 1.25 : (T == 2) ? 1.11 : (T == 4) ? 0.985 : 0.955;
         const int s_max = std::min(n_src_tiles, kMaxSplits);
         for (int S = 1; S <= s_max; ++S) {
             if (force_S > 0 && S != std::min(force_S, s_max))
