@@ -847,6 +847,8 @@ def main():
             rs.matvec_device(s * inner + i)
 
     def step_e2e(s):
+        if world > 1 and args.exchange == "nccl":  # A/B leg: device path only
+            return step_device(s)
         for i in range(inner):
             rs.matvec_e2e(s * inner + i)
 

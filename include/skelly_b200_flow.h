@@ -134,6 +134,9 @@ SKB_API int skb_flow_group_connect(skb_flow *fl, int peer_rank, skb_flow *peer);
  * first real matvec: device-wide synchronisation by cudaMalloc / cudaFree must not happen while a peer ON THE SAME
  * DEVICE waits on a flag.  Call after the ranges are set and all peers are connected; skb_mflow does it itself. */
 SKB_API int skb_flow_group_warmup(skb_flow *fl);
+/* profiling aid: from now on evaluate this member's share alone (no flags, own window only): the per-rank device time
+ * of an n-way group measured on ONE GPU.  The results are the member's partial view, not the group's. */
+SKB_API int skb_flow_group_set_solo(skb_flow *fl, int solo);
 /* after synchronising: *missing_peer = rank of a member whose flag never arrived within the time-out (a flag wait
  * gives up after ~10 s instead of hanging the GPU), or -1 */
 SKB_API int skb_flow_group_error(skb_flow *fl, int *missing_peer);

@@ -1,5 +1,5 @@
 cd $GRAFT_REPO_ROOT
 mkdir -p gpurun_out
-nvidia-smi -L
-(timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_n2.log 2>&1; tail -8 gpurun_out/pytest_n2.log)
-(BENCH_VERBOSE=1 timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 > gpurun_out/bench_c3_n2.json 2> gpurun_out/bench_c3_n2.err; tail -12 gpurun_out/bench_c3_n2.err; head -c 5000 gpurun_out/bench_c3_n2.json)
+(timeout 1500 python -m pytest tests -m gpu -x -q > gpurun_out/pytest_full.log 2>&1; tail -6 gpurun_out/pytest_full.log)
+for w in 1 2 4 8; do timeout 300 python scripts/rank_share.py $w 0 c3; done 2>&1 | grep "^{" | tee gpurun_out/rank_share.jsonl
+(ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches_r2_share8.csv -s 140 -c 60 env REPS=6 python scripts/rank_share.py 8 0 c3 > gpurun_out/ncu_share8.log 2>&1; tail -2 gpurun_out/ncu_share8.log)

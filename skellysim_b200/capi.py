@@ -121,6 +121,7 @@ def library() -> C.CDLL:
         "skb_flow_group_connect": ([ctxp, C.c_int, ctxp], C.c_int),
         "skb_flow_group_error": ([ctxp, C.POINTER(C.c_int)], C.c_int),
         "skb_flow_group_warmup": ([ctxp], C.c_int),
+        "skb_flow_group_set_solo": ([ctxp, C.c_int], C.c_int),
         "skb_flow_apply_matvec_device": ([ctxp, ctxp] + [C.c_void_p] * 6 + [C.c_double] + [C.c_void_p] * 4, C.c_int),
         "skb_partition_query": ([C.POINTER(C.c_int), C.c_int, C.c_int64, C.c_int64, C.c_int, C.c_int,
                                  C.POINTER(C.c_int64)], C.c_int),
@@ -648,6 +649,9 @@ class Flow:
 
     def group_warmup(self):
         _check(library().skb_flow_group_warmup(self._h))
+
+    def group_set_solo(self, solo: bool):
+        _check(library().skb_flow_group_set_solo(self._h, int(bool(solo))))
 
     def group_error(self) -> int:
         m = C.c_int(-1)

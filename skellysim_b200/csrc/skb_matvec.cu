@@ -1137,6 +1137,15 @@ int skb_flow_group_warmup(skb_flow *fl) {
     return SKB_OK;
 }
 
+// Profiling aid: evaluate this member's share ALONE from now on (no flags, own window only) -- the per-rank device time
+// of an n-way group on one GPU.  Results are the member's partial view, not the group's.
+int skb_flow_group_set_solo(skb_flow *fl, int solo) {
+    if (!fl || fl->grp.size <= 1)
+        return set_error(SKB_ERR_INVALID, "skb_flow_group_set_solo: not a group member");
+    fl->grp.dry = solo != 0;
+    return SKB_OK;
+}
+
 int skb_flow_group_error(skb_flow *fl, int *missing_peer) {
     if (!fl || !missing_peer)
         return set_error(SKB_ERR_INVALID, "skb_flow_group_error: NULL");
@@ -1800,6 +1809,10 @@ int skb_flow_apply_matvec_device(skb_flow *fl, skb_dense *dn, const double *d_x_
         return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec_device: NULL argument for a non-empty class");
     if (fl->grp.size == 1 && fl->n_win == 0)
         return SKB_OK;
+    if (fl->grp.size == 1 && fl->n_win != fl->n_fib + fl->n_shell + fl->n_body)
+        return set_error(SKB_ERR_INVALID, "skb_flow_apply_matvec_device: a flow that owns only part of the rows must be a "
+                                          "group member (skb_flow_group_init): the fiber forces of the other rows' "
+                                          "fibers have to come from somewhere");
     fl->cur = (cudaStream_t)stream;
     SKB_TRY(apply_matvec_core(fl, dn, d_x_fibers, d_x_shell, d_body_densities, d_body_forces, d_body_torques,
                               d_fiber_link_conditions, eta, d_res_fibers, d_out_shell, d_v_bodies));

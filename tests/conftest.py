@@ -4,6 +4,11 @@ import sys
 import numpy as np
 import pytest
 
+try:  # torch first: it must load ITS bundled libnccl.so.2 before the library dlopens "libnccl.so.2" for a multi-device
+    import torch  # noqa: F401  context (a system copy loaded earlier would be reused by torch and may be older)
+except Exception:  # pragma: no cover
+    torch = None
+
 # two group members on ONE GPU (tests/test_gpu_mflow.py) spin-wait on each other's flags from different streams: give
 # every stream its own hardware queue, so that no launch is serialised behind a waiting kernel (read at CUDA init)
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
