@@ -66,10 +66,6 @@ struct PairArgs {
     long long n_src;       // valid sources (the last tile is only walked up to here, rounded up to even)
     int n_src_tiles;       // ceil(n_src / kSrcTile)
     int tiles_per_split;   // source tiles handled by one blockIdx.y
-    int diag_tiles;        // 0: off.  >0: block-diagonal mode -- target tile b only meets source tiles
-                           // [b*diag_tiles, (b+1)*diag_tiles), one per blockIdx.y (the diagonal blocks the
-                           // symmetric kernel leaves out)
-    int diag_part, diag_parts; // block-diagonal mode: only blocks owned by this part are evaluated
     const int *src_fid;    // [n_src_pad] fiber id per source  (EXCL kernels only: same-fiber pairs contribute 0)
     const int *trg_fid;    // [n_trg]     fiber id per target
 };
@@ -435,15 +431,11 @@ __global__ void __launch_bounds__(kCtaThreads, MINB) pair_sum_kernel(const PairA
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem + L::bar_offset);
     uint64_t *empty_bar = full_bar + kStages;
 
-    if (a.diag_tiles > 0 && sym_row_owner((int)blockIdx.x, a.diag_parts) != a.diag_part)
-        return; // another rank's diagonal block (its slab is never read here)
     const int tid = threadIdx.x;
     const int lane = tid & 31;
     const long long t_base = (long long)blockIdx.x * kTileT;
-    // block-diagonal mode: CTA (b, y) meets source tile b*diag_tiles + y only (gridDim.y == diag_tiles)
-    const int per_cta = a.diag_tiles > 0 ? 1 : a.tiles_per_split;
-    const int first_tile = a.diag_tiles > 0 ? (int)blockIdx.x * a.diag_tiles + (int)blockIdx.y
-                                            : (int)blockIdx.y * a.tiles_per_split;
+    const int per_cta = a.tiles_per_split;
+    const int first_tile = (int)blockIdx.y * a.tiles_per_split;
     int n_tiles = a.n_src_tiles - first_tile;
     n_tiles = n_tiles < per_cta ? n_tiles : per_cta;
     if (n_tiles < 0)

@@ -45,8 +45,8 @@ DeviceInfo query_device(int dev);
 LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_src_tiles, int force_T, int force_S);
 int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const double *d_f_packed, long long n_src,
                     long long n_src_pad, const double *d_r_trg, long long n_trg, double *d_partial,
-                    const LaunchPlan &plan, cudaStream_t st, int diag_tiles = 0, int diag_part = 0,
-                    int diag_parts = 1, const int *d_src_fid = nullptr, const int *d_trg_fid = nullptr);
+                    const LaunchPlan &plan, cudaStream_t st, const int *d_src_fid = nullptr,
+                    const int *d_trg_fid = nullptr);
 int launch_reduce(const double *d_partial, double *d_u, long long n_trg, int n_splits, double scale, int accumulate,
                   cudaStream_t st);
 
@@ -85,8 +85,8 @@ struct SourceSet {
     // symmetric (Newton's third law) path of the Stokeslet self-interaction, sym_kernels.cuh
     int self_state = -1;       // -1 unknown, 0 targets do not start with these sources, 1 they do
     bool sym_plan_valid = false;
-    int sym_T = 0, sym_nb = 0, sym_items = 0, sym_part = 0, sym_parts = 1;
-    skb::DevBuf sym_item_buf, sym_row_begin, sym_P, sym_F, sym_diag, sym_flag;
+    int sym_T = 0, sym_nb = 0, sym_items = 0, sym_part = 0, sym_parts = 1, sym_owned = 0;
+    skb::DevBuf sym_item_buf, sym_row_begin, sym_P, sym_F, sym_diag /* owned block rows */, sym_flag;
     long long sym_pairs = 0; // ordered (target, source) pairs one launch of the symmetric kernel covers (both directions)
 };
 

@@ -159,8 +159,7 @@ LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_sr
 
 int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const double *d_f_packed, long long n_src,
                     long long n_src_pad, const double *d_r_trg, long long n_trg, double *d_partial,
-                    const LaunchPlan &plan, cudaStream_t st, int diag_tiles, int diag_part, int diag_parts,
-                    const int *d_src_fid, const int *d_trg_fid) {
+                    const LaunchPlan &plan, cudaStream_t st, const int *d_src_fid, const int *d_trg_fid) {
     PairArgs a;
     a.src_fid = d_src_fid;
     a.trg_fid = d_trg_fid;
@@ -172,9 +171,6 @@ int launch_pair_sum(const DeviceInfo &di, int kind, const double *d_r_src, const
     a.n_src = n_src;
     a.n_src_tiles = (int)((n_src + kSrcTile - 1) / kSrcTile);
     a.tiles_per_split = plan.tiles_per_split;
-    a.diag_tiles = diag_tiles;
-    a.diag_part = diag_part;
-    a.diag_parts = diag_parts < 1 ? 1 : diag_parts;
     (void)n_src_pad;
     dim3 grid(plan.grid_x, plan.n_splits, 1);
     cudaError_t e = cudaSuccess;
@@ -377,7 +373,8 @@ static int ctx_create_impl(const int *ids, int n, skb_ctx **out) {
             return set_error(SKB_ERR_NO_DEVICE, "device %d is sm_%d%d; this library is built for sm_100a only", dev,
                              d.info.cc_major, d.info.cc_minor);
         CUDA_TRY(cudaStreamCreateWithFlags(&d.stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaStreamCreateWithFlags(&d.aux_stream, cudaStreamNonBlocking));
+        // (d.aux_stream is created on first use by the symmetric path: most contexts of a flow never need one, and a
+        // device has a finite number of hardware queues for independent streams)
         CUDA_TRY(cudaEventCreateWithFlags(&d.ev_fork, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&d.ev_join, cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreateWithFlags(&d.ev_fork2, cudaEventDisableTiming));
@@ -827,8 +824,8 @@ static int sym_owned_rows(int nb, int part, int parts) {
     return n;
 }
 
-// Work items of the symmetric kernel: (I, groups [g0, g1)) over the strict upper triangle of nb blocks, restricted to
-// the block rows owned by `part`.  Units are 32-node groups (kSymGroupsPerBlock per block).  Guided sizes: most of the
+// Work items of the symmetric kernel: (I, groups [g0, g1)) over the upper triangle of nb blocks INCLUDING the block
+// diagonal (row I starts at its own first group), restricted to the block rows owned by `part`.  Units are 32-node groups (kSymGroupsPerBlock per block).  Guided sizes: most of the
 // work goes out in large items (about a quarter of a CTA slot's share each), the last ~30 % in items a quarter of that
 // size and the last ~8 % in single stages (4 groups = 17 us of one CTA slot), so that all CTA slots drain together: the
 // hardware hands the next item to whichever slot frees up first, in `order` (large items first).  item.slot is the
@@ -848,7 +845,7 @@ void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymIt
     long long work = 0; // groups x blocks owned by this part
     for (int I = 0; I < nb; ++I)
         if (sym_row_owner(I, parts) == part)
-            work += (long long)gpb * (nb - 1 - I);
+            work += (long long)gpb * (nb - I);
     const long long slots = (long long)num_sms * occ;
     long long big = work / std::max<long long>(1, slots * waves);
     big = std::max<long long>(sg, std::min<long long>(big / sg * sg, 1024LL * sg));
@@ -862,9 +859,7 @@ void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymIt
         if (sym_row_owner(I, parts) != part)
             continue;
         const int my_prow = prow++; // every owned row has a P row, in increasing I (sym_reduce_kernel counts the same way)
-        const int first = gpb * (I + 1), len = gpb * (nb - 1 - I);
-        if (len <= 0)
-            continue;
+        const int first = gpb * I, len = gpb * (nb - I); // from the block's own groups (the block diagonal) onwards
         const int n_chunks = (int)((len + big - 1) / big);
         for (int c = 0; c < n_chunks; ++c) { // near-equal chunks, cut at stage boundaries
             const int a = (int)((long long)(len / sg) * c / n_chunks) * sg;
@@ -962,7 +957,13 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
             return SKB_OK;
         }
         SKB_TRY(s.sym_F.ensure(order.size() * (size_t)block * 24 + 16));
-        SKB_TRY(s.sym_diag.ensure((size_t)T * (size_t)s.n_pad * 24));
+        std::vector<int> owned;
+        for (int I = 0; I < (int)nb; ++I)
+            if (sym_row_owner(I, d.sym_parts) == d.sym_part)
+                owned.push_back(I);
+        SKB_TRY(s.sym_diag.ensure(owned.size() * sizeof(int) + 16)); // (block rows of P's rows, for sym_reduce_kernel)
+        CUDA_TRY(cudaMemcpyAsync(s.sym_diag.ptr, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        s.sym_owned = (int)owned.size();
         CUDA_TRY(cudaMemcpyAsync(s.sym_item_buf.ptr, order.data(), order.size() * sizeof(SymItem),
                                  cudaMemcpyHostToDevice, st));
         CUDA_TRY(cudaMemcpyAsync(s.sym_row_begin.ptr, row_begin.data(), row_begin.size() * sizeof(int),
@@ -975,7 +976,7 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
                 continue;
             const long long nI = std::max<long long>(0, std::min<long long>(s.n, (I + 1) * block) - I * block);
             const long long after = std::max<long long>(0, s.n - (I + 1) * block);
-            pairs += 2 * nI * after;
+            pairs += 2 * nI * after + nI * nI; // both directions beyond the block + the block diagonal
         }
         s.sym_pairs = pairs;
         s.sym_T = T;
@@ -994,6 +995,8 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
                     int *launches) {
     SourceSet &s = d.src[SKB_STOKESLET];
     const double *f_packed = s.f_cur;
+    if (!d.aux_stream)
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.aux_stream, cudaStreamNonBlocking));
     const int T = s.sym_T;
     const long long block = (long long)kSymThreads * T;
     SymArgs a;
@@ -1005,7 +1008,6 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
     a.n_pad = s.n_pad;
     a.nb = s.sym_nb;
     cudaError_t e = cudaSuccess;
-    CUDA_TRY(cudaEventRecord(d.ev_fork2, st)); // strengths are packed: the diagonal blocks may start from here
     if (s.sym_items > 0) {
         a.fid = s.excl ? (const int *)s.excl_ids.ptr : nullptr;
         CUDA_TRY(cudaEventRecord(d.ev_s0, st));
@@ -1018,32 +1020,17 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
             return set_error(SKB_ERR_CUDA, "pair_sym_kernel launch failed: %s", cudaGetErrorString(e));
         count_launch(1);
     }
-    // block diagonal with the plain kernel, beside the symmetric kernel on the auxiliary stream: target tile b
-    // (128*T nodes) x its own T source tiles, one CTA per (block, source tile)
-    LaunchPlan dp;
-    dp.T = T;
-    dp.n_splits = T;
-    dp.tiles_per_split = 1;
-    dp.grid_x = (unsigned)((s.n + block - 1) / block);
-    CUDA_TRY(cudaStreamWaitEvent(d.aux_stream, d.ev_fork2, 0)); // recorded before the symmetric launch
-    SKB_TRY(launch_pair_sum(d.info, SKB_STOKESLET, (const double *)s.r.ptr, f_packed, s.n,
-                            s.n_pad, (const double *)s.r.ptr, s.n, (double *)s.sym_diag.ptr, dp, d.aux_stream, T,
-                            s.sym_part, s.sym_parts, s.excl ? (const int *)s.excl_ids.ptr : nullptr,
-                            s.excl ? (const int *)s.excl_ids.ptr : nullptr));
-    CUDA_TRY(cudaEventRecord(d.ev_join2, d.aux_stream));
-    CUDA_TRY(cudaStreamWaitEvent(st, d.ev_join2, 0));
     const long long n3 = 3 * s.n;
     const double scale = scale_mul / (8.0 * M_PI);
     sym_reduce_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(
-        (const double *)s.sym_diag.ptr, (const double *)s.sym_P.ptr, (const double *)s.sym_F.ptr,
-        (const int *)s.sym_row_begin.ptr, (int)block, s.n_pad, n3, scale, accumulate, d_u_out, s.sym_part,
-        s.sym_parts, T, s.n);
+        (const double *)s.sym_P.ptr, (const double *)s.sym_F.ptr, (const int *)s.sym_row_begin.ptr,
+        (const int *)s.sym_diag.ptr, s.sym_owned, (int)block, s.n_pad, n3, scale, accumulate, d_u_out);
     e = cudaGetLastError();
     if (e != cudaSuccess)
         return set_error(SKB_ERR_CUDA, "sym_reduce_kernel launch failed: %s", cudaGetErrorString(e));
     count_launch(1);
     if (launches)
-        *launches += 3;
+        *launches += 2;
     (void)ctx;
     return SKB_OK;
 }
@@ -1116,6 +1103,8 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
     double *d_u_std = (n_sym > 0 && opts.d_u_rem) ? opts.d_u_rem : d_u_out + 3 * n_sym;
     const double scale = scale_mul * (kind == SKB_STOKESLET ? 1.0 : -3.0) / (8.0 * M_PI);
     cudaStream_t st_std = st;
+    if (n_sym > 0 && !d.aux_stream)
+        CUDA_TRY(cudaStreamCreateWithFlags(&d.aux_stream, cudaStreamNonBlocking));
     if (n_sym > 0 && n_trg_std > 0) { // fork: the remainder fills the SMs the symmetric kernel's tail leaves idle
         CUDA_TRY(cudaEventRecord(d.ev_fork, st));
         CUDA_TRY(cudaStreamWaitEvent(d.aux_stream, d.ev_fork, 0));
@@ -1143,7 +1132,7 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
         plan = plan_launch(d.info, kind, n_trg_std, (int)((s.n + kSrcTile - 1) / kSrcTile), ctx->force_T, ctx->force_S);
         SKB_TRY(d.partial.ensure((size_t)plan.n_splits * (size_t)n_trg_std * 24));
         SKB_TRY(launch_pair_sum(d.info, kind, (const double *)s.r.ptr, s.f_cur, s.n, s.n_pad, d_r_trg_std, n_trg_std,
-                                (double *)d.partial.ptr, plan, st_std, 0, 0, 1, d_src_ids, d_trg_ids));
+                                (double *)d.partial.ptr, plan, st_std, d_src_ids, d_trg_ids));
         // 3. combine splits, scale: 1/(8 pi) (kernels.cu:59) or -3/(8 pi) (kernels.cu:26,51)
         SKB_TRY(launch_reduce((const double *)d.partial.ptr, d_u_std, n_trg_std, plan.n_splits, scale, accumulate,
                               st_std));

@@ -8,8 +8,10 @@
 //
 // Layout of the work: nodes are cut into blocks of kSymThreads*T (the "I side": each thread keeps T nodes in registers:
 // position, strength and the forward accumulators u_I += G f_J) and into GROUPS of 32 nodes (the "J side").  A work
-// item is (block I, groups [g0, g1)), all groups beyond block I (strict upper triangle; the block diagonal and the
-// non-square remainder go through pair_sum_kernel).  Items are as fine as one group (512*T/4 x 32 pairs), so the
+// item is (block I, groups [g0, g1)) from block I's own first group onwards: the groups beyond block I are the strict
+// upper triangle (both directions from one geometry pass); the groups of block I itself are the block diagonal, where
+// the forward sums alone already cover every ordered pair (their reverse sums land in a part of P nobody reads).  The
+// non-square remainder (targets beyond the sources) goes through pair_sum_kernel.  Items are as fine as one group (512*T/4 x 32 pairs), so the
 // planner can hand out large items first and small ones last (build_sym_items): the kernel's tail -- and the tail of
 // every rank's share under multi-GPU sharding -- is a few tens of microseconds, not one block pair (0.27 ms).
 // J groups are staged in shared memory by TMA, up to 4 groups per stage in a 4-stage ring; within a warp the 32 lanes
@@ -20,6 +22,7 @@
 // the reverse partial P[row(I)][J nodes].  The final combination (sym_reduce_kernel) is a fixed-order sum.
 #pragma once
 #include "pair_kernels.cuh"
+#include <type_traits>
 
 namespace skb {
 
@@ -50,7 +53,7 @@ constexpr int kSymStageNodes = kSymGroup * kSymStageGroups;
 constexpr int kSymGroupsPerBlock = kSymThreads * kSymT / kSymGroup;
 
 struct SymItem {
-    int I, g0, g1, slot; // I block, J groups [g0, g1) (all beyond block I), forward-partial slab index
+    int I, g0, g1, slot; // I block, J groups [g0, g1) (from block I's own first group on), forward-partial slab index
     int prow, pad;       // row of P this item writes: index of I among the block rows owned by this part
 };
 
@@ -81,7 +84,9 @@ template <int T> struct SymSmem {
 // of FiberContainerFiniteDifference::flow's "all pairs, then subtract the fiber's own block"
 // (fiber_container_finite_difference.cpp:203-210).  The fiber ids are compared in the integer pipe next to the r == 0
 // rule and mask the same reciprocal-square-root seed: no FP64 instruction is added.
-template <int T, bool EXCL = false>
+// REV = false: forward direction only (22 FP64 instructions per pair) -- the groups of block I itself, where the forward
+// sums alone cover every ordered pair of the block diagonal.
+template <int T, bool EXCL = false, bool REV = true>
 __device__ __forceinline__ void stokeslet_pairpairs(const double (&tx)[T], const double (&ty)[T],
                                                     const double (&tz)[T], const double (&hx)[T],
                                                     const double (&hy)[T], const double (&hz)[T], double rx, double ry,
@@ -120,19 +125,19 @@ __device__ __forceinline__ void stokeslet_pairpairs(const double (&tx)[T], const
         fr[c] = gx * dx[c];
 #pragma unroll
     for (int c = 0; c < T; ++c)
-        hr[c] = hx[c] * dx[c];
+        hr[c] = REV ? hx[c] * dx[c] : 0.0;
 #pragma unroll
     for (int c = 0; c < T; ++c)
         fr[c] = fma(gy, dy[c], fr[c]);
 #pragma unroll
     for (int c = 0; c < T; ++c)
-        hr[c] = fma(hy[c], dy[c], hr[c]);
+        hr[c] = REV ? fma(hy[c], dy[c], hr[c]) : 0.0;
 #pragma unroll
     for (int c = 0; c < T; ++c)
         fr[c] = fma(gz, dz[c], fr[c]);
 #pragma unroll
     for (int c = 0; c < T; ++c)
-        hr[c] = fma(hz[c], dz[c], hr[c]);
+        hr[c] = REV ? fma(hz[c], dz[c], hr[c]) : 0.0;
 #pragma unroll
     for (int c = 0; c < T; ++c)
         r2[c] = r2[c] * y[c];
@@ -156,18 +161,20 @@ __device__ __forceinline__ void stokeslet_pairpairs(const double (&tx)[T], const
         fr[c] = fr[c] * q[c];
 #pragma unroll
     for (int c = 0; c < T; ++c)
-        hr[c] = hr[c] * q[c];
+        hr[c] = REV ? hr[c] * q[c] : 0.0;
 #pragma unroll
     for (int c = 0; c < T; ++c) {
         ufx[c] = fma(y[c], fma(dx[c], fr[c], gx), ufx[c]);
         ufy[c] = fma(y[c], fma(dy[c], fr[c], gy), ufy[c]);
         ufz[c] = fma(y[c], fma(dz[c], fr[c], gz), ufz[c]);
     }
+    if constexpr (REV) {
 #pragma unroll
-    for (int c = 0; c < T; ++c) {
-        urx = fma(y[c], fma(dx[c], hr[c], hx[c]), urx);
-        ury = fma(y[c], fma(dy[c], hr[c], hy[c]), ury);
-        urz = fma(y[c], fma(dz[c], hr[c], hz[c]), urz);
+        for (int c = 0; c < T; ++c) {
+            urx = fma(y[c], fma(dx[c], hr[c], hx[c]), urx);
+            ury = fma(y[c], fma(dy[c], hr[c], hy[c]), ury);
+            urz = fma(y[c], fma(dz[c], hr[c], hz[c]), urz);
+        }
     }
 }
 
@@ -241,8 +248,8 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
         const int *ids = reinterpret_cast<const int *>(smem + s * L::stage_bytes + kSymStageNodes * 48);
         double *slab_set = slabs + (k & 1) * kWarps * L::slab_doubles; // double-buffered: one barrier per stage
         double *my_slab = slab_set + warp * L::slab_doubles;
-#pragma unroll 1
-        for (int gi = 0; gi < ng; ++gi) {
+        auto walk_group = [&](int gi, auto rev_tag) {
+            constexpr bool REV = decltype(rev_tag)::value;
             const int base = gi * kSymGroup;
             double urx = 0.0, ury = 0.0, urz = 0.0;
 #if SKB_SYM_PREFETCH
@@ -276,8 +283,8 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
                 const int rid = EXCL ? ids[idx] : 0;
 #endif
                 if constexpr (T <= 4) {
-                    stokeslet_pairpairs<T, EXCL>(tx, ty, tz, hx, hy, hz, rx, ry, rz, gx, gy, gz, ufx, ufy, ufz, urx, ury,
-                                                 urz, tfid, rid);
+                    stokeslet_pairpairs<T, EXCL, REV>(tx, ty, tz, hx, hy, hz, rx, ry, rz, gx, gy, gz, ufx, ufy, ufz, urx,
+                                                      ury, urz, tfid, rid);
                 } else { // chains in groups of 4: bounds the live temporaries
 #pragma unroll
                     for (int g0 = 0; g0 < T; g0 += 4) {
@@ -290,23 +297,34 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
                             bx[c] = hx[g0 + c], by[c] = hy[g0 + c], bz[c] = hz[g0 + c];
                             cx[c] = ufx[g0 + c], cy[c] = ufy[g0 + c], cz[c] = ufz[g0 + c];
                         }
-                        stokeslet_pairpairs<4, EXCL>(ax, ay, az, bx, by, bz, rx, ry, rz, gx, gy, gz, cx, cy, cz, urx, ury,
-                                                     urz, ti, rid);
+                        stokeslet_pairpairs<4, EXCL, REV>(ax, ay, az, bx, by, bz, rx, ry, rz, gx, gy, gz, cx, cy, cz, urx,
+                                                          ury, urz, ti, rid);
 #pragma unroll
                         for (int c = 0; c < 4; ++c)
                             ufx[g0 + c] = cx[c], ufy[g0 + c] = cy[c], ufz[g0 + c] = cz[c];
                     }
                 }
-                // the record moves to lane - 1 for the next step; its accumulator goes with it
-                const int from = (lane + 1) & 31;
-                urx = __shfl_sync(0xffffffffu, urx, from);
-                ury = __shfl_sync(0xffffffffu, ury, from);
-                urz = __shfl_sync(0xffffffffu, urz, from);
+                if constexpr (REV) {
+                    // the record moves to lane - 1 for the next step; its accumulator goes with it
+                    const int from = (lane + 1) & 31;
+                    urx = __shfl_sync(0xffffffffu, urx, from);
+                    ury = __shfl_sync(0xffffffffu, ury, from);
+                    urz = __shfl_sync(0xffffffffu, urz, from);
+                }
             }
             // after 32 steps lane l holds the finished sum of node base + l over this warp's 32*T targets
+            // (forward-only groups park zeros: that part of P is never read)
             my_slab[3 * (base + lane) + 0] = urx;
             my_slab[3 * (base + lane) + 1] = ury;
             my_slab[3 * (base + lane) + 2] = urz;
+        };
+#pragma unroll 1
+        for (int gi = 0; gi < ng; ++gi) {
+            // groups of block I itself = the block diagonal: forward sums only (uniform over the CTA)
+            if ((g_first + gi) / (kBlock / kSymGroup) == item.I)
+                walk_group(gi, std::false_type());
+            else
+                walk_group(gi, std::true_type());
         }
         __syncwarp();
         if (lane == 0)
@@ -334,29 +352,23 @@ __global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymAr
 }
 
 // Fixed-order combination for the symmetric path, one thread per velocity component of node `n` (block b):
-//   u = (acc ? u : 0) + scale * ( diag[n] + sum_{owned I < b} P[prow(I)][n] + sum_{items of row b} F[item][n - b*block] )
-__global__ void sym_reduce_kernel(const double *__restrict__ diag, const double *__restrict__ P,
-                                  const double *__restrict__ F, const int *__restrict__ row_item_begin, int block,
-                                  long long n_pad, long long n_valid3, double scale, int accumulate,
-                                  double *__restrict__ u, int part, int n_parts, int n_diag, long long n_valid) {
+//   u = (acc ? u : 0) + scale * ( sum_{owned I < b} P[prow(I)][n] + sum_{items of row b} F[item][n - b*block] )
+// owned_rows[prow] = block row I of P's row prow (increasing); row b's own items cover the block diagonal as well
+// (their groups start at block b itself), so nothing else is added.
+__global__ void sym_reduce_kernel(const double *__restrict__ P, const double *__restrict__ F,
+                                  const int *__restrict__ row_item_begin, const int *__restrict__ owned_rows,
+                                  int n_owned, int block, long long n_pad, long long n_valid3, double scale,
+                                  int accumulate, double *__restrict__ u) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; // component index 3*n + k
     if (i >= n_valid3)
         return;
     const long long node = i / 3;
     const int b = (int)(node / block);
-    // only rows owned by this part were evaluated here (n_parts == 1: all of them)
     double acc = 0.0;
-    if (sym_row_owner(b, n_parts) == part)
-        for (int y = 0; y < n_diag; ++y) // diagonal block, one slab per source tile of the block
-            acc += diag[(size_t)y * n_valid * 3 + i];
-    int prow = 0; // P holds only the rows this part owns, in increasing I
-    for (int I = 0; I < b; ++I)
-        if (sym_row_owner(I, n_parts) == part) {
-            acc += P[((size_t)prow * n_pad) * 3 + i];
-            ++prow;
-        }
+    for (int prow = 0; prow < n_owned && owned_rows[prow] < b; ++prow) // reverse partials of the rows above
+        acc += P[((size_t)prow * n_pad) * 3 + i];
     const long long local = i - (long long)b * block * 3;
-    for (int it = row_item_begin[b]; it < row_item_begin[b + 1]; ++it)
+    for (int it = row_item_begin[b]; it < row_item_begin[b + 1]; ++it) // forward partials (empty for rows not owned)
         acc += F[(size_t)it * block * 3 + local];
     acc *= scale;
     u[i] = accumulate ? u[i] + acc : acc;

@@ -53,18 +53,17 @@ def test_symmetric_work_list_covers_the_upper_triangle_exactly_once(nb, parts):
             for s in range(row_begin[b], row_begin[b + 1]):
                 assert by_slot[s][0] == b                          # row b's slabs are contiguous
         for (i, g0, g1, _) in items:
-            assert 0 <= i and gpb * (i + 1) <= g0 < g1 <= gpb * nb  # only groups beyond block i
+            assert 0 <= i and gpb * i <= g0 < g1 <= gpb * nb        # block i's own groups (the diagonal) and beyond
             assert g0 % 4 == 0                                     # items start on a stage boundary
             covered.setdefault(i, []).append((g0, g1))
     total = 0
-    for i in range(nb - 1):
+    for i in range(nb):
         rs = sorted(covered.get(i, []))
-        assert rs[0][0] == gpb * (i + 1) and rs[-1][1] == gpb * nb  # the whole row ...
+        assert rs[0][0] == gpb * i and rs[-1][1] == gpb * nb        # the whole row, diagonal block included ...
         for (a0, a1), (b0, b1) in zip(rs, rs[1:]):
             assert a1 == b0                                        # ... exactly once
         total += rs[-1][1] - rs[0][0]
-    assert total == gpb * nb * (nb - 1) // 2
-    assert (nb - 1) not in covered
+    assert total == gpb * nb * (nb + 1) // 2
 
 
 @pytest.mark.parametrize("nb,parts", [(32, 1), (94, 1), (94, 8), (266, 8), (977, 8)])
