@@ -124,7 +124,8 @@ LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_sr
         // efficiency of the inner loop vs T (LDS + loop overhead amortised over T pairs); calibrated on B200
         // measured Stokeslet rates on B200: T=8 712, T=4 691, T=2 ~614 Gpairs/s (profiles/r1_probe_perf_v3.json,
         // profiles/r2_launches_bench.md); T=1 extrapolated
-        const double t_pen = (T == 1) ? 1.25 : (T == 2) ? 1.11 : (T == 4) ? 0.985 : 0.955;
+        // and the few-target sweep profiles/r2_small_targets.md (T=1 wins below ~2000 targets)
+        const double t_pen = (T == 1) ? 1.18 : (T == 2) ? 1.11 : (T == 4) ? 0.985 : 0.955;
         const int s_max = std::min(n_src_tiles, kMaxSplits);
         for (int S = 1; S <= s_max; ++S) {
             if (force_S > 0 && S != std::min(force_S, s_max))
@@ -138,7 +139,8 @@ LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_sr
             // CTAs beyond the resident limit run in later waves; same total either way
             const double resident = (double)std::min<long long>(per_sm, occ);
             // latency hiding: want >= ~12 independent pair chains per scheduler (1 warp/CTA/SMSP, T chains each)
-            const double chains = resident * T;
+            // (T <= 2 evaluates two sources per iteration: 2 T chains per warp, stokeslet_two_sources)
+            const double chains = resident * (T <= 2 ? 2 * T : T);
             const double lat_pen = chains >= 12.0 ? 1.0 : (12.0 / chains) * 0.5 + 0.5;
             // fixed per-CTA cost (barrier init, target staging, partial write) in units of source tiles
             const double cta_overhead = 0.5;
