@@ -82,6 +82,13 @@ SKB_API int skb_flow_matvec(skb_flow *fl, const double *fib_forces, const double
                             const double *body_densities, const double *body_forces_torques, double eta,
                             double *v_all);
 
+/* The (fiber node, periphery node) pairs of a matvec are visited twice -- the fibers' Stokeslets act on the periphery
+ * (system.cpp:299) and the periphery's stresslets on the fibers (system.cpp:304,313-315).  By default (mode -1: when both
+ * classes are large enough and all fiber rows are in the target list) one kernel evaluates both directions from one pass
+ * over the pairs (37 instead of 49 FP64 instructions per visited pair); results agree with the two separate evaluator
+ * calls to rounding.  0: never (two calls, as the reference issues them); 1: whenever applicable. */
+SKB_API int skb_flow_set_cross(skb_flow *fl, int mode);
+
 /* Opt-in: the matvec's fiber self term.  fused == 0 (default): the reference's way -- all pairs,
  * then `vel -= fib.stokeslet_ * wf` per fiber (fiber_container_finite_difference.cpp:203-210) on the device.
  * fused != 0: the pair kernels skip every intra-fiber pair (per-node fiber id compared in the integer pipe), nothing is
@@ -244,6 +251,7 @@ SKB_API int skb_mflow_set_periphery(skb_mflow *mf, const double *node_pos, const
 SKB_API int skb_mflow_set_bodies(skb_mflow *mf, const double *node_pos, const double *node_normal, int64_t n_nodes,
                                  const double *centers, int n_bodies);
 SKB_API int skb_mflow_set_self_exclusion(skb_mflow *mf, int fused);
+SKB_API int skb_mflow_set_cross(skb_mflow *mf, int mode);
 /* which fibers / periphery rows / body rows device `member` owns (any pointer may be NULL) */
 SKB_API int skb_mflow_partition(skb_mflow *mf, int member, int *fiber_begin, int *fiber_end, int64_t *shell_begin,
                                 int64_t *shell_end, int64_t *body_begin, int64_t *body_end);

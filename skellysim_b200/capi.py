@@ -115,6 +115,8 @@ def library() -> C.CDLL:
         "skb_flow_velocity_at_targets": ([ctxp, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_set_target_window": ([ctxp, C.c_int64, C.c_int64], C.c_int),
         "skb_flow_set_self_exclusion": ([ctxp, C.c_int], C.c_int),
+        "skb_flow_set_cross": ([ctxp, C.c_int], C.c_int),
+        "skb_mflow_set_cross": ([ctxp, C.c_int], C.c_int),
         "skb_flow_group_init": ([ctxp, C.c_int, C.c_int], C.c_int),
         "skb_flow_group_export": ([ctxp, C.c_void_p], C.c_int),
         "skb_flow_group_import": ([ctxp, C.c_int, C.c_void_p], C.c_int),
@@ -451,6 +453,10 @@ class Flow:
                                                       float(eta), _p(vel)))
         return vel
 
+    def set_cross(self, mode: int):
+        """Fiber <-> periphery pairs of the matvec in one geometry pass: -1 auto (default), 0 never, 1 whenever applicable."""
+        _check(library().skb_flow_set_cross(self._h, int(mode)))
+
     def set_self_exclusion(self, fused: bool):
         """Matvec self term: False = the reference's compute-then-subtract (default); True = the pair kernels skip
         intra-fiber pairs."""
@@ -716,6 +722,9 @@ class MultiFlow:
 
     def set_self_exclusion(self, fused: bool):
         _check(library().skb_mflow_set_self_exclusion(self._h, int(bool(fused))))
+
+    def set_cross(self, mode: int):
+        _check(library().skb_mflow_set_cross(self._h, int(mode)))
 
     def partition(self, member: int):
         f0, f1 = C.c_int(), C.c_int()

@@ -131,6 +131,31 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
                    double *d_u_out, int accumulate, cudaStream_t st, bool record_events, int *launches,
                    LaunchPlan *plan_out, double scale_mul, const EvalOpts &opts = EvalOpts());
 
+// strengths -> the kernels' packed, padded layout in s.f_packed (what eval_on_device does first); sets s.f_cur
+int pack_on_device(DeviceState &d, int kind, StrengthMode mode, const double *d_f_raw, double two_eta, cudaStream_t st,
+                   int *launches);
+
+// fiber <-> periphery in one geometry pass (cross_kernels.cuh): plan and partial buffers of one (fiber rows, periphery)
+// shape
+struct CrossState {
+    bool valid = false;
+    long long node0 = -1, n_rows = -1, n_sh = -1, n_sh_pad = -1;
+    int n_blocks = 0, n_items = 0, num_sms = 0;
+    DevBuf items, row_begin, P, F;
+    void release() {
+        items.release(), row_begin.release(), P.release(), F.release();
+        valid = false;
+    }
+};
+long long cross_block_nodes();
+// u_fib[n_rows x 3] (=|+=) scale_dl * (stresslet sums of ALL periphery nodes at fiber nodes [node0, node0 + n_rows));
+// u_shell[n_sh x 3] (=|+=) scale_sl * (Stokeslet sums of those fiber nodes at every periphery node).
+// r_fib / h: positions and packed Stokeslet strengths of all fiber nodes (padded); r_sh / s6: periphery, padded.
+int cross_eval(CrossState &cs, const DeviceInfo &di, const double *d_r_fib, const double *d_h, long long node0,
+               long long n_rows, const double *d_r_sh, const double *d_s6, long long n_sh, long long n_sh_pad,
+               double scale_dl, double scale_sl, double *d_u_fib, int acc_fib, double *d_u_shell, int acc_shell,
+               cudaStream_t st, int *launches);
+
 struct SymItem;
 long long sym_block_nodes(); // nodes per block of the symmetric kernel (its I side)
 void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymItem> &order,

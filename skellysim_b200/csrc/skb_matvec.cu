@@ -67,6 +67,9 @@ struct skb_flow {
     skb_ctx *fib[2] = {nullptr, nullptr}, *shell[2] = {nullptr, nullptr}, *body[2] = {nullptr, nullptr};
     TargetCache tc_fib, tc_shell, tc_body;
     bool mv_dirty = true;
+    int cross_mode = -1;    // fiber <-> periphery cross kernel in the matvec: -1 auto, 0 off, 1 on whenever applicable
+    bool use_cross = false; // decided by prepare_matvec_targets
+    CrossState cross;
     bool self_excl = false; // matvec: skip intra-fiber pairs in the kernels instead of compute-then-subtract (N3, opt-in)
     long long win_begin = 0, win_end = -1; // target window of the matvec in [fibers|shell|bodies] rows; -1 = all
     bool use_ranges = false;               // skb_flow_set_target_ranges instead of a contiguous window
@@ -120,6 +123,7 @@ struct skb_flow {
         void *peer[kMaxGroup] = {};   // base address of every member's window as mapped here (peer[rank] == window)
         bool peer_ipc[kMaxGroup] = {};
         size_t off_flags = 0, off_fsl[2] = {0, 0}, off_fshell[2] = {0, 0}, off_xshell[2] = {0, 0}, off_upart = 0;
+        size_t off_upart_shell = 0;   // partial periphery velocities (cross kernel: own fibers -> ALL periphery rows)
         long long n_fib = 0, n_shell = 0, n_pad_fib = 0, n_pad_shell = 0; // geometry the window was laid out for
         unsigned long long epoch = 0;
         bool dry = false;             // warm-up pass: no flags, own window only (skb_flow_group_warmup)
@@ -418,6 +422,7 @@ int skb_flow_destroy(skb_flow *fl) {
     fl->g_vat.reset();
     group_release(fl);
     fl->scratch_u.release();
+    fl->cross.release();
     if (fl->h_stage)
         cudaFreeHost(fl->h_stage);
     if (fl->ev0) cudaEventDestroy(fl->ev0);
@@ -766,6 +771,17 @@ static int prepare_matvec_targets(skb_flow *fl) {
         // the self-interaction is big enough for that kernel; otherwise the member's own rows with the plain kernel
         fl->grp.use_sym = nf >= 2LL * sym_block_nodes();
     }
+    // fiber <-> periphery pairs in one pass (cross_kernels.cuh) when both classes are big enough to matter and the
+    // symmetric kernel carries the fiber rows (so that the fiber evaluator's remaining targets are the body rows only)
+    static const int cross_env = [] {
+        const char *e = getenv("SKB_CROSS");
+        return e ? atoi(e) : -1;
+    }();
+    const int cmode = fl->cross_mode >= 0 ? fl->cross_mode : cross_env;
+    const bool sym_rows = grouped ? fl->grp.use_sym
+                                  : (fl->fa == 0 && fl->fb == nf && fl->sa == 0 && fl->sb == ns &&
+                                     nf >= (cmode == 1 ? 2LL * sym_block_nodes() : 4096));
+    fl->use_cross = cmode != 0 && sym_rows && n_fw > 0 && ns >= (cmode == 1 ? 1 : 256);
     // target lists of apply_matvec: r_all = [fibers | shell | bodies] (system.cpp:284-291),
     // r_fibbody = [fibers | bodies] (system.cpp:301-303), both restricted to this rank's pieces
     std::vector<double> r_win, r_fb;
@@ -773,18 +789,26 @@ static int prepare_matvec_targets(skb_flow *fl) {
     r_win.insert(r_win.end(), fl->h_r_fib.begin() + 3 * fl->fa, fl->h_r_fib.begin() + 3 * fl->fb);
     r_win.insert(r_win.end(), fl->h_r_shell.begin() + 3 * fl->sa, fl->h_r_shell.begin() + 3 * fl->sb);
     r_win.insert(r_win.end(), fl->h_r_body.begin() + 3 * fl->ba, fl->h_r_body.begin() + 3 * fl->bb);
-    r_fb.insert(r_fb.end(), fl->h_r_fib.begin() + 3 * fl->fa, fl->h_r_fib.begin() + 3 * fl->fb);
+    if (!fl->use_cross)
+        r_fb.insert(r_fb.end(), fl->h_r_fib.begin() + 3 * fl->fa, fl->h_r_fib.begin() + 3 * fl->fb);
     r_fb.insert(r_fb.end(), fl->h_r_body.begin() + 3 * fl->ba, fl->h_r_body.begin() + 3 * fl->bb);
     if (grouped && fl->grp.use_sym) {
-        // fiber sources meet [ALL fiber nodes | own shell rows | own body rows]
+        // fiber sources meet [ALL fiber nodes | own shell rows | own body rows]; with the cross kernel the periphery
+        // rows are not targets of this evaluator
         std::vector<double> r_sym;
         r_sym.reserve((size_t)(nf + n_sw + n_bw) * 3);
         r_sym.insert(r_sym.end(), fl->h_r_fib.begin(), fl->h_r_fib.end());
-        r_sym.insert(r_sym.end(), fl->h_r_shell.begin() + 3 * fl->sa, fl->h_r_shell.begin() + 3 * fl->sb);
+        if (!fl->use_cross)
+            r_sym.insert(r_sym.end(), fl->h_r_shell.begin() + 3 * fl->sa, fl->h_r_shell.begin() + 3 * fl->sb);
         r_sym.insert(r_sym.end(), fl->h_r_body.begin() + 3 * fl->ba, fl->h_r_body.begin() + 3 * fl->bb);
         SKB_TRY(skb_ctx_set_symmetric(fl->fib[1], 1));
         SKB_TRY(skb_ctx_set_sym_partition(fl->fib[1], fl->grp.rank, fl->grp.size));
-        SKB_TRY(skb_set_targets(fl->fib[1], r_sym.data(), nf + n_sw + n_bw));
+        SKB_TRY(skb_set_targets(fl->fib[1], r_sym.data(), (long long)r_sym.size() / 3));
+    } else if (fl->use_cross) {
+        std::vector<double> r_fibbody(fl->h_r_fib.begin() + 3 * fl->fa, fl->h_r_fib.begin() + 3 * fl->fb);
+        r_fibbody.insert(r_fibbody.end(), fl->h_r_body.begin() + 3 * fl->ba, fl->h_r_body.begin() + 3 * fl->bb);
+        SKB_TRY(skb_ctx_set_sym_partition(fl->fib[1], 0, 1));
+        SKB_TRY(skb_set_targets(fl->fib[1], r_fibbody.data(), (long long)r_fibbody.size() / 3));
     } else {
         SKB_TRY(skb_ctx_set_sym_partition(fl->fib[1], 0, 1));
         SKB_TRY(skb_set_targets(fl->fib[1], r_win.data(), fl->n_win));
@@ -884,14 +908,25 @@ static int matvec_core_group(skb_flow *fl, const double *d_ff, const double *d_s
             EvalOpts o;
             o.d_u_sym = u_part;
             o.sym_accumulate = 0;
-            o.d_u_rem = d_v + 3 * n_fw;
+            o.d_u_rem = fl->use_cross ? d_v + 3 * (n_fw + n_sw) : d_v + 3 * n_fw; // cross: body rows only
             SKB_TRY(eval_on_device(fl->fib[1], df, SKB_STOKESLET, kPacked, f_sl, 0.0, (double *)fl->scratch_u.ptr, 0,
                                    fl->cur, false, &fl->launches, nullptr, 1.0 / eta, o));
             if (!fl->fib[1]->last_was_sym)
                 return set_error(SKB_ERR_STATE, "group member %d: the symmetric kernel declined (memory for the reverse "
                                                 "partials?); lower SKB_SYM_MAX_BYTES pressure or use fewer nodes per GPU",
                                  G.rank);
-            fl->pairs += nf * nf / G.size + nf * (n_sw + n_bw);
+            fl->pairs += nf * nf / G.size + nf * ((fl->use_cross ? 0 : n_sw) + n_bw);
+            if (fl->use_cross && ns > 0) {
+                // own fibers x ALL periphery nodes in one pass: stresslet sums at the own fiber rows (complete) and
+                // this member's partial Stokeslet sums at every periphery row (pulled together after flag B)
+                DeviceState &dsh = fl->shell[1]->devs[0];
+                const SourceSet &sf = df.src[SKB_STOKESLET], &ss = dsh.src[SKB_STRESSLET];
+                SKB_TRY(cross_eval(fl->cross, df.info, (const double *)sf.r.ptr, f_sl, fl->fa, n_fw,
+                                   (const double *)ss.r.ptr, f_shell, ns, ss.n_pad, -3.0 / (8.0 * M_PI * eta),
+                                   1.0 / (8.0 * M_PI * eta), d_v, 0, G.at<double>(G.rank, G.off_upart_shell), 0, fl->cur,
+                                   &fl->launches));
+                fl->pairs += 2 * n_fw * ns;
+            }
             SKB_TRY(group_flag(fl, 1, true, false)); // my partial sums are complete
         } else {
             SKB_TRY(eval_on_device(fl->fib[1], df, SKB_STOKESLET, kPacked, f_sl, 0.0, d_v, 0, fl->cur, false,
@@ -901,10 +936,26 @@ static int matvec_core_group(skb_flow *fl, const double *d_ff, const double *d_s
     } else if (fl->n_win > 0) {
         CUDA_TRY(cudaMemsetAsync(d_v, 0, (size_t)fl->n_win * 24, fl->cur));
     }
-    const bool fib_rows_pending = G.use_sym && fl->n_fibers > 0; // d_v's fiber rows are not written yet
+    const bool fib_rows_pending = G.use_sym && fl->n_fibers > 0; // d_v's fiber rows are not complete yet
+    const bool crossed = fl->use_cross && G.use_sym && fl->n_fibers > 0 && ns > 0;
     // 4. v_fibers, v_bodies += shell.flow(r_fibbody, x_shell, eta)   (system.cpp:304,313-315)
-    bool fib_rows_set = !fib_rows_pending;
-    if (ns > 0 && n_fw + n_bw > 0) {
+    bool fib_rows_set = !fib_rows_pending || (crossed && n_fw > 0); // (the cross kernel wrote the own fiber rows)
+    if (crossed) {
+        if (n_sw > 0) // own periphery rows: body flow accumulates first, the members' Stokeslet partials are pulled in below
+            CUDA_TRY(cudaMemsetAsync(d_v + 3 * n_fw, 0, (size_t)n_sw * 24, fl->cur));
+        if (n_bw > 0) { // periphery -> own body rows
+            DeviceState &dsh = fl->shell[1]->devs[0];
+            SKB_TRY(fl->tmp.ensure((size_t)n_bw * 24 + 8));
+            SKB_TRY(eval_on_device(fl->shell[1], dsh, SKB_STRESSLET, kPacked, f_shell, 2.0 * eta, (double *)fl->tmp.ptr, 0,
+                                   fl->cur, false, &fl->launches, nullptr, 1.0 / eta));
+            add_inplace_kernel<<<(unsigned)((3 * n_bw + 255) / 256), 256, 0, fl->cur>>>(
+                d_v + 3 * (n_fw + n_sw), (const double *)fl->tmp.ptr, 3 * n_bw);
+            CUDA_TRY(cudaGetLastError());
+            count_launch(1);
+            fl->launches += 1;
+            fl->pairs += ns * n_bw;
+        }
+    } else if (ns > 0 && n_fw + n_bw > 0) {
         DeviceState &dsh = fl->shell[1]->devs[0];
         SKB_TRY(fl->tmp.ensure((size_t)(n_fw + n_bw) * 24 + 8));
         double *d_tmp = (double *)fl->tmp.ptr;
@@ -951,6 +1002,20 @@ static int matvec_core_group(skb_flow *fl, const double *d_ff, const double *d_s
             count_launch(1);
             fl->launches += 1;
         }
+        if (crossed && n_sw > 0) { // own periphery rows += the members' Stokeslet partials
+            GroupPullArgs a;
+            a.size = G.dry ? 1 : G.size;
+            for (int m = 0; m < a.size; ++m)
+                a.u_part[m] = G.at<double>(G.dry ? G.rank : m, G.off_upart_shell);
+            a.fa = fl->sa;
+            a.n_f = n_sw;
+            a.v = d_v + 3 * n_fw;
+            a.accumulate = 1;
+            group_pull_kernel<<<(unsigned)((3 * n_sw + 255) / 256), 256, 0, fl->cur>>>(a);
+            CUDA_TRY(cudaGetLastError());
+            count_launch(1);
+            fl->launches += 1;
+        }
     }
     // 7. self term of the own fibers (fcfd.cpp:203-210), unless the kernels already skipped intra-fiber pairs
     if (n_fw > 0 && !df.src[SKB_STOKESLET].excl) {
@@ -965,6 +1030,66 @@ static int matvec_core_group(skb_flow *fl, const double *d_ff, const double *d_s
     return SKB_OK;
 }
 
+// The same with the fiber <-> periphery pairs in one geometry pass (cross_kernels.cuh): whole system on this device.
+//   fiber evaluator targets  = [fibers | bodies]   (symmetric fiber-fiber block + the body rows)
+//   cross kernel             : stresslet of every periphery node at the fiber nodes, Stokeslet of every fiber node at
+//                              the periphery nodes (system.cpp:299 and :304,313-315 from one pass over the pairs)
+//   periphery evaluator      = [bodies] only
+static int matvec_core_cross(skb_flow *fl, const double *d_ff, const double *d_sd, const double *d_bd, const double *d_f,
+                             const double *d_t, double eta, double *d_v) {
+    const long long ns = fl->n_shell, nf = fl->n_fib;
+    const long long n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba; // == nf, ns, nb here
+    DeviceState &df = fl->fib[1]->devs[0];
+    DeviceState &dsh = fl->shell[1]->devs[0];
+    double *d_v_body = d_v + 3 * (n_fw + n_sw);
+    // fc.flow at [fibers | bodies]: the symmetric kernel writes the fiber rows, the plain kernel the body rows.  Should the
+    // symmetric path decline (memory), everything lands contiguously in the scratch buffer and is moved into place.
+    SKB_TRY(fl->scratch_u.ensure((size_t)df.n_trg * 24 + 8));
+    EvalOpts o;
+    o.d_u_sym = d_v;
+    o.d_u_rem = d_v_body;
+    SKB_TRY(eval_on_device(fl->fib[1], df, SKB_STOKESLET, kRaw, d_ff, 0.0, (double *)fl->scratch_u.ptr, 0, fl->cur, false,
+                           &fl->launches, nullptr, 1.0 / eta, o));
+    if (!fl->fib[1]->last_was_sym) {
+        CUDA_TRY(cudaMemcpyAsync(d_v, fl->scratch_u.ptr, (size_t)n_fw * 24, cudaMemcpyDeviceToDevice, fl->cur));
+        if (n_bw > 0)
+            CUDA_TRY(cudaMemcpyAsync(d_v_body, (const double *)fl->scratch_u.ptr + 3 * n_fw, (size_t)n_bw * 24,
+                                     cudaMemcpyDeviceToDevice, fl->cur));
+    }
+    fl->pairs += nf * (n_fw + n_bw);
+    if (!df.src[SKB_STOKESLET].excl) { // fcfd.cpp:203-210
+        const size_t smem = (size_t)fl->max_fiber_nodes * 6 * sizeof(double);
+        fiber_self_subtract_kernel<<<fl->n_fibers, 128, smem, fl->cur>>>(
+            (const double *)fl->r_fib.ptr, df.src[SKB_STOKESLET].f_cur, (const long long *)fl->fiber_offset.ptr,
+            1.0 / (8.0 * M_PI * eta), kReg * kReg, kEps, d_v, fl->fa, fl->fb);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        fl->launches += 1;
+    }
+    // periphery strengths 2 eta n (x) rho -> sym6 (periphery.cpp:68-71), once for both uses
+    SKB_TRY(pack_on_device(dsh, SKB_STRESSLET, kNormalDensity, d_sd, 2.0 * eta, fl->cur, &fl->launches));
+    const SourceSet &sf = df.src[SKB_STOKESLET], &ss = dsh.src[SKB_STRESSLET];
+    SKB_TRY(cross_eval(fl->cross, df.info, (const double *)sf.r.ptr, sf.f_cur, fl->fa, n_fw, (const double *)ss.r.ptr,
+                       ss.f_cur, ns, ss.n_pad, -3.0 / (8.0 * M_PI * eta), 1.0 / (8.0 * M_PI * eta), d_v, 1,
+                       d_v + 3 * n_fw, 0, fl->cur, &fl->launches));
+    fl->pairs += 2 * n_fw * ns;
+    // periphery -> body rows (system.cpp:313-315)
+    if (n_bw > 0) {
+        SKB_TRY(fl->tmp.ensure((size_t)n_bw * 24 + 8));
+        SKB_TRY(eval_on_device(fl->shell[1], dsh, SKB_STRESSLET, kPacked, ss.f_cur, 2.0 * eta, (double *)fl->tmp.ptr, 0,
+                               fl->cur, false, &fl->launches, nullptr, 1.0 / eta));
+        add_inplace_kernel<<<(unsigned)((3 * n_bw + 255) / 256), 256, 0, fl->cur>>>(d_v_body, (const double *)fl->tmp.ptr,
+                                                                                  3 * n_bw);
+        CUDA_TRY(cudaGetLastError());
+        count_launch(1);
+        fl->launches += 1;
+        fl->pairs += ns * n_bw;
+    }
+    // v_all += bc.flow(r_all, x_bodies, body_link_conditions, eta)     system.cpp:316
+    SKB_TRY(bodies_dev(fl, fl->body[1], d_bd, d_f, d_t, eta, d_v, 1));
+    return SKB_OK;
+}
+
 // device-side matvec flow on fl->cur: all strengths resident, d_v = window rows of v_all
 static int matvec_core(skb_flow *fl, const double *d_ff, const double *d_sd, const double *d_bd, const double *d_f,
                        const double *d_t, double eta, double *d_v) {
@@ -974,6 +1099,8 @@ static int matvec_core(skb_flow *fl, const double *d_ff, const double *d_sd, con
     const long long n_win = fl->n_win, n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba;
     if (n_win == 0)
         return SKB_OK;
+    if (fl->use_cross)
+        return matvec_core_cross(fl, d_ff, d_sd, d_bd, d_f, d_t, eta, d_v);
     // v_all = fc.flow(r_all, fw, eta)                                  system.cpp:299
     // (this rank's fiber rows come first, so the self term applies to targets [0, n_fw) of its list)
     SKB_TRY(fibers_dev(fl, fl->fib[1], d_ff, eta, n_fw > 0, d_v, 0, fl->fa, fl->fb));
@@ -1049,6 +1176,7 @@ int skb_flow_group_init(skb_flow *fl, int rank, int size) {
         G.off_xshell[b] = take((size_t)G.n_shell * 24 + 16);
     }
     G.off_upart = take((size_t)G.n_fib * 24 + 16);
+    G.off_upart_shell = take((size_t)G.n_shell * 24 + 16);
     G.window_bytes = off;
     CUDA_TRY(cudaMalloc(&G.window, G.window_bytes));
     CUDA_TRY(cudaMemset(G.window, 0, G.window_bytes)); // flags at epoch 0, strength pads zero for good
@@ -1158,6 +1286,15 @@ int skb_flow_group_error(skb_flow *fl, int *missing_peer) {
                         cudaMemcpyDeviceToHost));
     if (w)
         *missing_peer = (int)(w - 1);
+    return SKB_OK;
+}
+
+int skb_flow_set_cross(skb_flow *fl, int mode) {
+    if (!fl || mode < -1 || mode > 1)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_cross: mode must be -1 (auto), 0 (off) or 1 (on)");
+    fl->cross_mode = mode;
+    fl->mv_dirty = true;
+    fl->geom_version++;
     return SKB_OK;
 }
 
@@ -2099,6 +2236,15 @@ int skb_mflow_set_bodies(skb_mflow *mf, const double *node_pos, const double *no
         mf->part_dirty = true;
     mf->n_body = n_nodes;
     mf->n_bodies = n_bodies;
+    return SKB_OK;
+}
+
+int skb_mflow_set_cross(skb_mflow *mf, int mode) {
+    if (!mf)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_cross: NULL");
+    for (int g = 0; g < mf->n; ++g)
+        SKB_TRY(skb_flow_set_cross(mf->m[g], mode));
+    mf->part_dirty = true; // the members' target lists change: re-run the warm-up
     return SKB_OK;
 }
 

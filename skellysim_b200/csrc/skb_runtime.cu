@@ -6,6 +6,7 @@
 // No CPU fallback exists here: every path ends in a CUDA launch or an error code.
 #include "pair_kernels.cuh"
 #include "sym_kernels.cuh"
+#include "cross_kernels.cuh"
 #include "skb_internal.hpp"
 
 #include <algorithm>
@@ -1040,6 +1041,124 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
 } // namespace skb
 
 namespace skb {
+
+long long cross_block_nodes() { return kCrossBlock; }
+
+// Work items of the cross kernel: rectangles (fiber block I, periphery groups [g0, g1)), every block meets every group;
+// guided sizes as for the symmetric kernel (large items first, a fine tail).
+static void build_cross_items(int n_blocks, int n_groups, int num_sms, std::vector<SymItem> &order,
+                              std::vector<int> &row_begin) {
+    const int sg = kSymStageGroups;
+    const long long work = (long long)n_blocks * n_groups;
+    const long long slots = (long long)num_sms * kCrossMinB;
+    long long big = work / std::max<long long>(1, slots * 4);
+    big = std::max<long long>(sg, std::min<long long>(big / sg * sg, 1024LL * sg));
+    const long long mid = std::max<long long>(sg, big / 4 / sg * sg);
+    struct Piece {
+        int I, g0, g1;
+    };
+    std::vector<Piece> pieces;
+    for (int I = 0; I < n_blocks; ++I) {
+        const int n_chunks = (int)((n_groups + big - 1) / big);
+        for (int c = 0; c < n_chunks; ++c) {
+            const int a = (int)((long long)(n_groups / sg) * c / n_chunks) * sg;
+            const int b = c + 1 == n_chunks ? n_groups : (int)((long long)(n_groups / sg) * (c + 1) / n_chunks) * sg;
+            if (b > a)
+                pieces.push_back(Piece{I, a, b});
+        }
+    }
+    std::stable_sort(pieces.begin(), pieces.end(),
+                     [](const Piece &x, const Piece &y) { return (x.g1 - x.g0) > (y.g1 - y.g0); });
+    std::vector<Piece> fine;
+    long long done = 0;
+    const long long fine_work = std::min<long long>(work * 8 / 100, slots * 6 * sg);
+    const long long mid_work = std::min<long long>(work * 30 / 100, fine_work + slots * 6 * mid);
+    for (const Piece &pc : pieces) {
+        const long long len = pc.g1 - pc.g0, left = work - done;
+        const long long unit = left <= fine_work ? sg : left <= mid_work ? mid : len;
+        for (long long g = pc.g0; g < pc.g1; g += unit)
+            fine.push_back(Piece{pc.I, (int)g, (int)std::min<long long>(pc.g1, g + unit)});
+        done += len;
+    }
+    std::sort(fine.begin(), fine.end(),
+              [](const Piece &x, const Piece &y) { return x.I != y.I ? x.I < y.I : x.g0 < y.g0; });
+    std::vector<SymItem> items(fine.size());
+    row_begin.assign(n_blocks + 1, 0);
+    for (size_t i = 0; i < fine.size(); ++i) {
+        items[i] = SymItem{fine[i].I, fine[i].g0, fine[i].g1, (int)i, fine[i].I, 0};
+        row_begin[fine[i].I + 1] = (int)i + 1;
+    }
+    for (int b = 0; b < n_blocks; ++b)
+        row_begin[b + 1] = std::max(row_begin[b + 1], row_begin[b]);
+    order = items;
+    std::stable_sort(order.begin(), order.end(),
+                     [](const SymItem &x, const SymItem &y) { return (x.g1 - x.g0) > (y.g1 - y.g0); });
+}
+
+int cross_eval(CrossState &cs, const DeviceInfo &di, const double *d_r_fib, const double *d_h, long long node0,
+               long long n_rows, const double *d_r_sh, const double *d_s6, long long n_sh, long long n_sh_pad,
+               double scale_dl, double scale_sl, double *d_u_fib, int acc_fib, double *d_u_shell, int acc_shell,
+               cudaStream_t st, int *launches) {
+    if (n_rows <= 0 || n_sh <= 0)
+        return SKB_OK;
+    const long long block = kCrossBlock;
+    const int n_blocks = (int)((n_rows + block - 1) / block);
+    const int n_groups = (int)((n_sh + kSymGroup - 1) / kSymGroup);
+    if (!cs.valid || cs.node0 != node0 || cs.n_rows != n_rows || cs.n_sh != n_sh || cs.n_sh_pad != n_sh_pad ||
+        cs.num_sms != di.num_sms) {
+        std::vector<SymItem> order;
+        std::vector<int> row_begin;
+        build_cross_items(n_blocks, n_groups, di.num_sms, order, row_begin);
+        SKB_TRY(cs.items.ensure(order.size() * sizeof(SymItem) + 16));
+        SKB_TRY(cs.row_begin.ensure(row_begin.size() * sizeof(int)));
+        SKB_TRY(cs.P.ensure((size_t)n_blocks * (size_t)n_sh_pad * 24));
+        SKB_TRY(cs.F.ensure(order.size() * (size_t)block * 24 + 16));
+        CUDA_TRY(cudaMemcpyAsync(cs.items.ptr, order.data(), order.size() * sizeof(SymItem), cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaMemcpyAsync(cs.row_begin.ptr, row_begin.data(), row_begin.size() * sizeof(int),
+                                 cudaMemcpyHostToDevice, st));
+        CUDA_TRY(cudaStreamSynchronize(st)); // host vectors go out of scope
+        cs.node0 = node0, cs.n_rows = n_rows, cs.n_sh = n_sh, cs.n_sh_pad = n_sh_pad;
+        cs.n_blocks = n_blocks, cs.n_items = (int)order.size(), cs.num_sms = di.num_sms;
+        cs.valid = true;
+    }
+    CrossArgs a;
+    a.r_fib = d_r_fib;
+    a.h = d_h;
+    a.r_sh = d_r_sh;
+    a.s6 = d_s6;
+    a.items = (const SymItem *)cs.items.ptr;
+    a.P = (double *)cs.P.ptr;
+    a.F = (double *)cs.F.ptr;
+    a.n_sh_pad = n_sh_pad;
+    a.node0 = node0;
+    a.n_rows = n_rows;
+    using L = CrossSmem<kCrossT>;
+    auto kern = pair_cross_kernel<kCrossT, kCrossMinB>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 64 && !attr_set[dev]) {
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total_bytes));
+        attr_set[dev] = true;
+    }
+    kern<<<cs.n_items, kSymThreads, L::total_bytes, st>>>(a);
+    CUDA_TRY(cudaGetLastError());
+    const long long nr3 = 3 * n_rows, ns3 = 3 * n_sh;
+    cross_reduce_fib_kernel<<<(unsigned)((nr3 + 255) / 256), 256, 0, st>>>(
+        (const double *)cs.F.ptr, (const int *)cs.row_begin.ptr, (int)block, nr3, scale_dl, acc_fib, d_u_fib);
+    cross_reduce_shell_kernel<<<(unsigned)((ns3 + 255) / 256), 256, 0, st>>>((const double *)cs.P.ptr, n_blocks,
+                                                                              n_sh_pad, ns3, scale_sl, acc_shell,
+                                                                              d_u_shell);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(3);
+    if (launches)
+        *launches += 3;
+    return SKB_OK;
+}
+
+} // namespace skb
+
+namespace skb {
 __global__ void excl_target_ids_kernel(const int *__restrict__ src_ids, long long n_src, long long trg_begin,
                                        long long n_trg, int *__restrict__ out) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -1047,6 +1166,30 @@ __global__ void excl_target_ids_kernel(const int *__restrict__ src_ids, long lon
         const long long g = trg_begin + i; // global target row: the leading n_src rows are the sources themselves
         out[i] = g < n_src ? src_ids[g] : -1;
     }
+}
+
+int pack_on_device(DeviceState &d, int kind, StrengthMode mode, const double *d_f_raw, double two_eta, cudaStream_t st,
+                   int *launches) {
+    SourceSet &s = d.src[kind];
+    const int bs = 256;
+    s.f_cur = (const double *)s.f_packed.ptr;
+    if (s.n <= 0)
+        return SKB_OK;
+    if (kind == SKB_STOKESLET) {
+        pack_sl_kernel<<<(unsigned)((s.n_pad * 3 + bs - 1) / bs), bs, 0, st>>>(
+            d_f_raw, s.has_weights ? (const double *)s.weights.ptr : nullptr, (double *)s.f_packed.ptr, s.n, s.n_pad);
+    } else if (mode == kRaw) {
+        pack_dl9_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(d_f_raw, (double *)s.f_packed.ptr, s.n,
+                                                                             s.n_pad);
+    } else {
+        pack_dl_normal_density_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(
+            (const double *)s.normals.ptr, d_f_raw, two_eta, (double *)s.f_packed.ptr, s.n, s.n_pad);
+    }
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    if (launches)
+        *launches += 1;
+    return SKB_OK;
 }
 
 int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, const double *d_f_raw, double two_eta,
@@ -1062,25 +1205,10 @@ int eval_on_device(skb_ctx *ctx, DeviceState &d, int kind, StrengthMode mode, co
         return SKB_OK;
     }
     // 1. strengths -> packed, padded layout
-    s.f_cur = (const double *)s.f_packed.ptr;
-    if (mode == kPacked) {
+    if (mode == kPacked)
         s.f_cur = d_f_raw;
-    } else {
-        if (kind == SKB_STOKESLET) {
-            pack_sl_kernel<<<(unsigned)((s.n_pad * 3 + bs - 1) / bs), bs, 0, st>>>(
-                d_f_raw, s.has_weights ? (const double *)s.weights.ptr : nullptr, (double *)s.f_packed.ptr, s.n, s.n_pad);
-        } else if (mode == kRaw) {
-            pack_dl9_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(d_f_raw, (double *)s.f_packed.ptr, s.n,
-                                                                                 s.n_pad);
-        } else {
-            pack_dl_normal_density_kernel<<<(unsigned)((s.n_pad + bs - 1) / bs), bs, 0, st>>>(
-                (const double *)s.normals.ptr, d_f_raw, two_eta, (double *)s.f_packed.ptr, s.n, s.n_pad);
-        }
-        CUDA_TRY(cudaGetLastError());
-        count_launch(1);
-        if (launches)
-            *launches += 1;
-    }
+    else
+        SKB_TRY(pack_on_device(d, kind, mode, d_f_raw, two_eta, st, launches));
     if (record_events)
         CUDA_TRY(cudaEventRecord(d.ev_k0, st));
     // fused self-exclusion (opt-in): ids only make sense when the sources are the leading targets

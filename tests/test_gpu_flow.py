@@ -280,3 +280,27 @@ def test_graphs_can_be_disabled(monkeypatch):
         for _ in range(4):
             v = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), 1.0)
     _check(v, orc.matvec_flow(fib, shell, body, 1.0))
+
+
+@pytest.mark.parametrize("n_fibers,n_shell,n_body,n_bodies", [(130, 700, 360, 3), (130, 700, 0, 0), (90, 33, 100, 1)])
+def test_matvec_cross_kernel_matches_the_two_call_form(n_fibers, n_shell, n_body, n_bodies, monkeypatch):
+    """Fiber <-> periphery pairs in one geometry pass (cross_kernels.cuh: the fibers' Stokeslets on the periphery and the
+    periphery's stresslets on the fibers share d, r^2, 1/r) against the oracle and against the two separate evaluator
+    calls the reference issues (system.cpp:299, :304)."""
+    monkeypatch.setenv("SKB_SYMMETRIC", "1")
+    fib, shell, body = make_system(500 + n_fibers, n_fibers, n_shell, n_body, n_bodies, nodes=(16, 32, 48, 64, 96))
+    eta = 0.6
+    ref = orc.matvec_flow(fib, shell, body, eta)
+    with skb.Flow(0) as fl:
+        load(fl, fib, shell, body)
+        fl.set_cross(0)
+        v_two = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+        fl.set_cross(1)
+        v_cross = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+        v_again = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+        fl.set_self_exclusion(True)
+        v_excl = fl.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+    _check(v_two, ref)
+    _check(v_cross, ref)
+    _check(v_excl, ref)
+    assert np.array_equal(v_cross, v_again), "bitwise reproducible"

@@ -63,6 +63,22 @@ def test_mflow_matvec_matches_oracle(n_fibers, nodes):
             assert a[1] == b[0] and a[3] == b[2] and a[5] == b[4]
 
 
+def test_mflow_matvec_with_cross_kernel():
+    # own fibers x ALL periphery nodes in one pass per member; the members' partial Stokeslet sums at the periphery rows are
+    # pulled together like the fiber rows' partials
+    fib, shell, body = make_system(9, 120, 600, 200, 2, nodes=(16, 32, 48, 64, 96))
+    eta = 1.4
+    ref = orc.matvec_flow(fib, shell, body, eta)
+    for devs in device_lists():
+        with skb.MultiFlow(devs) as mf:
+            load_m(mf, fib, shell, body)
+            mf.set_cross(1)
+            v = mf.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+            v2 = mf.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+        _check(v, ref)
+        assert np.array_equal(v, v2)
+
+
 def test_mflow_matvec_with_fused_self_exclusion():
     fib, shell, body = make_system(7, 120, 500, 200, 2, nodes=(16, 32, 48, 64, 96))
     eta = 0.8
