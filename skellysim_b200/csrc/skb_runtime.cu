@@ -142,7 +142,10 @@ LaunchPlan plan_launch(const DeviceInfo &di, int kind, long long n_trg, int n_sr
             // latency hiding: want >= ~12 independent pair chains per scheduler (1 warp/CTA/SMSP, T chains each)
             // (T <= 2 evaluates two sources per iteration: 2 T chains per warp, stokeslet_two_sources)
             const double chains = resident * (T <= 2 ? 2 * T : T);
-            const double lat_pen = chains >= 12.0 ? 1.0 : (12.0 / chains) * 0.5 + 0.5;
+            // (and CTA slots left empty on the busiest SM cost latency hiding too: 441 CTAs of T=2 on 888 slots measured
+            // slower than 875, profiles/r2_small_targets.md)
+            const double fill = std::min(1.0, (double)per_sm / (double)occ);
+            const double lat_pen = (chains >= 12.0 ? 1.0 : (12.0 / chains) * 0.5 + 0.5) * (1.0 + 0.25 * (1.0 - fill));
             // fixed per-CTA cost (barrier init, target staging, partial write) in units of source tiles
             const double cta_overhead = 0.5;
             double cost = (double)per_sm * ((double)per + cta_overhead) * T * t_pen * lat_pen;
