@@ -202,6 +202,7 @@ int skb_dense_set_matrix(skb_dense *dn, int op, const double *A, int64_t n_rows,
         CUDA_TRY(cudaSetDevice(d.dev));
         SKB_TRY(d.A[op].ensure((size_t)d.n_rows[op] * (size_t)n_cols * 8));
         SKB_TRY(upload_pageable(d.A[op].ptr, A + d.row_begin[op] * n_cols, (size_t)d.n_rows[op] * n_cols * 8, d.stream));
+        SKB_TRY(d.ticket.ensure(8)); // (not at the first apply: no allocation on the matvec path, see skb_flow_group_warmup)
     }
     for (auto &d : dn->devs) {
         CUDA_TRY(cudaSetDevice(d.dev));

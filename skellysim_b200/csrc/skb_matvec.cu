@@ -2376,6 +2376,31 @@ static int mflow_collect_stats(skb_mflow *mf) {
     return SKB_OK;
 }
 
+// Size every member's transfer buffers on the CALLING thread, before any member starts launching: cudaMalloc /
+// cudaFree may synchronise the whole device and must not run while a peer on the same device sits in a flag wait.
+static int mflow_size_io(skb_mflow *mf, size_t n_ft) {
+    for (int g = 0; g < mf->n; ++g) {
+        CUDA_TRY(cudaSetDevice(mf->devs[g]));
+        skb_mflow::IO &io = mf->io[g];
+        const long long a = mf->fiber_off.empty() ? 0 : mf->fiber_off[(size_t)mf->f0[g]],
+                        b = mf->fiber_off.empty() ? 0 : mf->fiber_off[(size_t)mf->f1[g]];
+        const size_t n_fw = (size_t)(b - a), n_sw = (size_t)(mf->s1[g] - mf->s0[g]), n_bw = (size_t)(mf->b1[g] - mf->b0[g]);
+        const size_t n_fibers = (size_t)(mf->f1[g] - mf->f0[g]);
+        SKB_TRY(io.x.ensure(n_fw * 32 + 8));
+        SKB_TRY(io.ff.ensure(n_fw * 24 + 8));
+        SKB_TRY(io.xs.ensure(n_sw * 24 + 8));
+        SKB_TRY(io.bd.ensure((size_t)mf->n_body * 24 + 8));
+        SKB_TRY(io.f.ensure(n_ft * 8 + 8));
+        SKB_TRY(io.t.ensure(n_ft * 8 + 8));
+        SKB_TRY(io.link.ensure(n_fibers * 56 + 8));
+        SKB_TRY(io.res.ensure(n_fw * 32 + 8));
+        SKB_TRY(io.outs.ensure(n_sw * 24 + 8));
+        SKB_TRY(io.vb.ensure(n_bw * 24 + 8));
+        SKB_TRY(io.v.ensure((n_fw + n_sw + n_bw) * 24 + 8));
+    }
+    return SKB_OK;
+}
+
 // v_all over [fibers | periphery | bodies] like skb_flow_matvec; complete host arrays in and out
 int skb_mflow_matvec(skb_mflow *mf, const double *fib_forces, const double *shell_density, const double *body_densities,
                      const double *body_forces_torques, double eta, double *v_all) {
@@ -2389,6 +2414,7 @@ int skb_mflow_matvec(skb_mflow *mf, const double *fib_forces, const double *shel
     std::vector<double> f, t;
     if (mf->n_bodies > 0)
         split_forces_torques(body_forces_torques, mf->n_bodies, f, t);
+    SKB_TRY(mflow_size_io(mf, f.size()));
     SKB_TRY(mf->workers->run([&](int g) -> int {
         skb_flow *fl = mf->m[g];
         skb_mflow::IO &io = mf->io[g];
@@ -2446,6 +2472,7 @@ int skb_mflow_apply_matvec(skb_mflow *mf, const double *x_fibers, const double *
     std::vector<double> f, t;
     if (mf->n_bodies > 0)
         split_forces_torques(body_forces_torques, mf->n_bodies, f, t);
+    SKB_TRY(mflow_size_io(mf, f.size()));
     SKB_TRY(mf->workers->run([&](int g) -> int {
         skb_flow *fl = mf->m[g];
         skb_mflow::IO &io = mf->io[g];

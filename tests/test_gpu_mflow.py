@@ -84,11 +84,14 @@ def test_mflow_matvec_with_fused_self_exclusion():
     eta = 0.8
     ref = orc.matvec_flow(fib, shell, body, eta)
     for devs in ([0, 0], [0, 0, 0]):
-        with skb.MultiFlow(devs) as mf:
-            load_m(mf, fib, shell, body)
-            mf.set_self_exclusion(True)
-            v = mf.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
-        _check(v, ref)
+        for cross in (0, 1):
+            with skb.MultiFlow(devs) as mf:
+                load_m(mf, fib, shell, body)
+                mf.set_cross(cross)
+                mf.set_self_exclusion(True)
+                print("exclusion: devices", devs, "cross", cross, flush=True)
+                v = mf.matvec(fib["forces"], shell["density"], body["density"], ft_of(body), eta)
+            _check(v, ref)
 
 
 @pytest.mark.parametrize("with_dense", [False, True])
