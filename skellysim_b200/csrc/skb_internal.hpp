@@ -86,7 +86,7 @@ struct SourceSet {
     int self_state = -1;       // -1 unknown, 0 targets do not start with these sources, 1 they do
     bool sym_plan_valid = false;
     int sym_T = 0, sym_nb = 0, sym_items = 0, sym_part = 0, sym_parts = 1, sym_owned = 0;
-    skb::DevBuf sym_item_buf, sym_row_begin, sym_P, sym_F, sym_diag /* owned block rows */, sym_flag;
+    skb::DevBuf sym_item_buf, sym_row_begin, sym_P, sym_F, sym_row_ids /* block row I of every row of sym_P */, sym_flag;
     long long sym_pairs = 0; // ordered (target, source) pairs one launch of the symmetric kernel covers (both directions)
 };
 

@@ -444,7 +444,7 @@ int skb_ctx_destroy(skb_ctx *ctx) {
             s.sym_row_begin.release();
             s.sym_P.release();
             s.sym_F.release();
-            s.sym_diag.release();
+            s.sym_row_ids.release();
             s.sym_flag.release();
             s.f_raw.release();
             s.f_packed.release();
@@ -967,8 +967,8 @@ static int sym_prepare(skb_ctx *ctx, DeviceState &d, cudaStream_t st, int *use) 
         for (int I = 0; I < (int)nb; ++I)
             if (sym_row_owner(I, d.sym_parts) == d.sym_part)
                 owned.push_back(I);
-        SKB_TRY(s.sym_diag.ensure(owned.size() * sizeof(int) + 16)); // (block rows of P's rows, for sym_reduce_kernel)
-        CUDA_TRY(cudaMemcpyAsync(s.sym_diag.ptr, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice, st));
+        SKB_TRY(s.sym_row_ids.ensure(owned.size() * sizeof(int) + 16)); // (block rows of P's rows, for sym_reduce_kernel)
+        CUDA_TRY(cudaMemcpyAsync(s.sym_row_ids.ptr, owned.data(), owned.size() * sizeof(int), cudaMemcpyHostToDevice, st));
         s.sym_owned = (int)owned.size();
         CUDA_TRY(cudaMemcpyAsync(s.sym_item_buf.ptr, order.data(), order.size() * sizeof(SymItem),
                                  cudaMemcpyHostToDevice, st));
@@ -1030,7 +1030,7 @@ static int sym_eval(skb_ctx *ctx, DeviceState &d, double *d_u_out, int accumulat
     const double scale = scale_mul / (8.0 * M_PI);
     sym_reduce_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(
         (const double *)s.sym_P.ptr, (const double *)s.sym_F.ptr, (const int *)s.sym_row_begin.ptr,
-        (const int *)s.sym_diag.ptr, s.sym_owned, (int)block, s.n_pad, n3, scale, accumulate, d_u_out);
+        (const int *)s.sym_row_ids.ptr, s.sym_owned, (int)block, s.n_pad, n3, scale, accumulate, d_u_out);
     e = cudaGetLastError();
     if (e != cudaSuccess)
         return set_error(SKB_ERR_CUDA, "sym_reduce_kernel launch failed: %s", cudaGetErrorString(e));
