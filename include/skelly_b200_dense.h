@@ -45,6 +45,12 @@ SKB_API int skb_dense_apply(skb_dense *dn, int op, const double *x, const double
  * device inside skb_flow_apply_matvec_dense (skelly_b200_flow.h). */
 SKB_API int skb_dense_apply_device(skb_dense *dn, int op, const double *d_x, const double *d_v_add, double *d_y,
                                    void *stream);
+/* y = A x with the BACKGROUND streamer (csrc/stream_kernels.cuh): one 64-thread CTA per SM, the matrix moved by TMA bulk
+ * copies -- small enough to share every SM with the FP64-bound pair kernels, so that an HBM-bound operator launched on
+ * a side stream costs (almost) no time of the matvec.  Same contract as skb_dense_apply_device without v_add; falls
+ * back to the classic kernel when n_cols is odd or d_x is not 16-byte aligned.  skb_flow_apply_matvec_* use it for
+ * Periphery::matvec (periphery.cpp:38-47) unless skb_flow_set_overlap(fl, 0). */
+SKB_API int skb_dense_apply_background_device(skb_dense *dn, int op, const double *d_x, double *d_y, void *stream);
 /* shape given to skb_dense_set_matrix (n_rows = -1 before it was called) */
 SKB_API int skb_dense_shape(const skb_dense *dn, int op, int64_t *n_rows, int64_t *n_cols);
 

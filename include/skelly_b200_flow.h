@@ -96,6 +96,12 @@ SKB_API int skb_flow_set_cross(skb_flow *fl, int mode);
  * the reference's regularised branch acts (distinct nodes of one fiber closer than 1e-5, kernels.cpp:176-184).  Applies
  * to skb_flow_matvec / skb_flow_apply_matvec with all fiber nodes in the target list. */
 SKB_API int skb_flow_set_self_exclusion(skb_flow *fl, int fused);
+/* Overlap of the HBM-bound dense operator with the FP64-bound pair kernels (default on): skb_flow_apply_matvec_dense /
+ * _device hand stresslet_plus_complementary * x_shell (Periphery::matvec, periphery.cpp:38-47) to the background row
+ * streamer (skb_dense_apply_background_device) on a side stream as soon as x_shell is complete on the device, and add
+ * v_shell when both are there.  0: one GEMV kernel at the end of the stream instead (the round-1 order).  The results
+ * differ in the last bits only (another summation order inside a row). */
+SKB_API int skb_flow_set_overlap(skb_flow *fl, int on);
 
 /* Restrict the matvec to rows [begin, end) of the target list [fibers | periphery | bodies] (end < 0: all).
  * For one-rank-per-GPU hosts: every rank loads the full geometry, all-gathers the strengths, and evaluates its own
@@ -252,6 +258,7 @@ SKB_API int skb_mflow_set_bodies(skb_mflow *mf, const double *node_pos, const do
                                  const double *centers, int n_bodies);
 SKB_API int skb_mflow_set_self_exclusion(skb_mflow *mf, int fused);
 SKB_API int skb_mflow_set_cross(skb_mflow *mf, int mode);
+SKB_API int skb_mflow_set_overlap(skb_mflow *mf, int on); /* skb_flow_set_overlap on every member */
 /* which fibers / periphery rows / body rows device `member` owns (any pointer may be NULL) */
 SKB_API int skb_mflow_partition(skb_mflow *mf, int member, int *fiber_begin, int *fiber_end, int64_t *shell_begin,
                                 int64_t *shell_end, int64_t *body_begin, int64_t *body_end);

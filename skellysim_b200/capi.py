@@ -115,6 +115,9 @@ def library() -> C.CDLL:
         "skb_flow_velocity_at_targets": ([ctxp, _dp, C.c_int64, _dp, _dp, _dp, _dp, C.c_double, _dp], C.c_int),
         "skb_flow_set_target_window": ([ctxp, C.c_int64, C.c_int64], C.c_int),
         "skb_flow_set_self_exclusion": ([ctxp, C.c_int], C.c_int),
+        "skb_flow_set_overlap": ([ctxp, C.c_int], C.c_int),
+        "skb_mflow_set_overlap": ([ctxp, C.c_int], C.c_int),
+        "skb_dense_apply_background_device": ([ctxp, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p], C.c_int),
         "skb_flow_set_cross": ([ctxp, C.c_int], C.c_int),
         "skb_mflow_set_cross": ([ctxp, C.c_int], C.c_int),
         "skb_flow_group_init": ([ctxp, C.c_int, C.c_int], C.c_int),
@@ -462,6 +465,10 @@ class Flow:
         intra-fiber pairs."""
         _check(library().skb_flow_set_self_exclusion(self._h, int(bool(fused))))
 
+    def set_overlap(self, on: bool):
+        """Periphery dense operator beside the pair kernels on a side stream (default) or as one kernel at the end."""
+        _check(library().skb_flow_set_overlap(self._h, int(bool(on))))
+
     def set_target_window(self, begin: int, end: int = -1):
         """Evaluate only rows [begin, end) of [fibers | periphery | bodies] in matvec() (one rank's block)."""
         _check(library().skb_flow_set_target_window(self._h, int(begin), int(end)))
@@ -726,6 +733,9 @@ class MultiFlow:
     def set_cross(self, mode: int):
         _check(library().skb_mflow_set_cross(self._h, int(mode)))
 
+    def set_overlap(self, on: bool):
+        _check(library().skb_mflow_set_overlap(self._h, int(bool(on))))
+
     def partition(self, member: int):
         f0, f1 = C.c_int(), C.c_int()
         r = [C.c_int64() for _ in range(4)]
@@ -854,6 +864,12 @@ class Dense:
         """Single-device handle, operands already on its device (addresses as ints, 0 = NULL v_add); asynchronous."""
         _check(library().skb_dense_apply_device(self._h, int(op), C.c_void_p(d_x), C.c_void_p(d_v_add) if d_v_add else None,
                                                 C.c_void_p(d_y), C.c_void_p(stream) if stream else None))
+
+    def apply_background_device(self, op: int, d_x: int, d_y: int, stream: int = 0):
+        """y = A x with the background row streamer (one small CTA per SM, TMA-fed): the form that can share the SMs
+        with the pair kernels.  Single-device handle, device addresses as ints; asynchronous."""
+        _check(library().skb_dense_apply_background_device(self._h, int(op), C.c_void_p(d_x), C.c_void_p(d_y),
+                                                           C.c_void_p(stream) if stream else None))
 
     def stats(self) -> dict:
         s = DenseStats()

@@ -141,6 +141,14 @@ __global__ void add_inplace_kernel(double *__restrict__ dst, const double *__res
         dst[i] += src[i];
 }
 
+// out[i] = a[i] + b[i]
+__global__ void add_out_kernel(double *__restrict__ out, const double *__restrict__ a, const double *__restrict__ b,
+                               long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n)
+        out[i] = a[i] + b[i];
+}
+
 // per-node trapezoid weights 0.5 * L * weights_0 (fiber_container_finite_difference.cpp:186,
 // fiber_finite_difference.cpp:545-548): weights_0 = 2/(n-1), halved at both ends
 __global__ void fiber_weights_kernel(const long long *__restrict__ fiber_offset, const double *__restrict__ length,

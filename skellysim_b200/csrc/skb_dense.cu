@@ -1,6 +1,7 @@
 // skb_dense.cu -- the periphery's dense operators (Periphery::matvec / apply_preconditioner,
 // SkellySim src/core/periphery.cpp:21-47) as an HBM-bound row-major GEMV on B200.  include/skelly_b200_dense.h.
 #include "skb_internal.hpp"
+#include "stream_kernels.cuh"
 #include "../../include/skelly_b200_dense.h"
 
 #include <algorithm>
@@ -107,7 +108,7 @@ struct DenseDev {
     cudaStream_t stream = nullptr;
     cudaEvent_t e0 = nullptr, e1 = nullptr, t0 = nullptr, t1 = nullptr;
     long long row_begin[2] = {0, 0}, n_rows[2] = {0, 0};
-    DevBuf A[2], x, v, y, ticket;
+    DevBuf A[2], x, v, y, ticket, ticket_bg;
 };
 
 } // namespace
@@ -117,6 +118,21 @@ struct skb_dense {
     long long rows[2] = {-1, -1}, cols[2] = {0, 0};
     skb_dense_stats stats{};
 };
+
+// Loads dense_stream_kernel on the current device and fixes its attributes.  Also called ahead of the first matvec
+// (skb_matvec.cu: overlap_buffers) so that nothing is loaded lazily while a group member spins on a flag.
+int skb::dense_stream_preload(int dev) {
+    static bool done[64] = {false};
+    if (dev >= 0 && dev < 64 && done[dev])
+        return SKB_OK;
+    CUDA_TRY(cudaFuncSetAttribute(dense_stream_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kStreamSmemBytes));
+    // the same shared-memory configuration as the pair kernels it is meant to sit beside (skb_runtime.cu)
+    CUDA_TRY(cudaFuncSetAttribute(dense_stream_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                  cudaSharedmemCarveoutMaxShared));
+    if (dev >= 0 && dev < 64)
+        done[dev] = true;
+    return SKB_OK;
+}
 
 extern "C" {
 
@@ -176,6 +192,7 @@ int skb_dense_destroy(skb_dense *dn) {
         d.v.release();
         d.y.release();
         d.ticket.release();
+        d.ticket_bg.release();
         if (d.e0) cudaEventDestroy(d.e0);
         if (d.e1) cudaEventDestroy(d.e1);
         if (d.t0) cudaEventDestroy(d.t0);
@@ -202,6 +219,7 @@ int skb_dense_set_matrix(skb_dense *dn, int op, const double *A, int64_t n_rows,
         CUDA_TRY(cudaSetDevice(d.dev));
         SKB_TRY(d.A[op].ensure((size_t)d.n_rows[op] * (size_t)n_cols * 8));
         SKB_TRY(upload_pageable(d.A[op].ptr, A + d.row_begin[op] * n_cols, (size_t)d.n_rows[op] * n_cols * 8, d.stream));
+        SKB_TRY(d.ticket_bg.ensure(8));
         SKB_TRY(d.ticket.ensure(8)); // (not at the first apply: no allocation on the matvec path, see skb_flow_group_warmup)
     }
     for (auto &d : dn->devs) {
@@ -304,6 +322,47 @@ int skb_dense_apply_device(skb_dense *dn, int op, const double *d_x, const doubl
     CUDA_TRY(cudaMemsetAsync(d.ticket.ptr, 0, 8, st));
     dense_gemv_kernel<<<d.num_sms * occ, 256, 0, st>>>((const double *)d.A[op].ptr, d_x, d_v_add, d_y, n_rows, n_cols,
                                                       vec_ok, (unsigned long long *)d.ticket.ptr);
+    CUDA_TRY(cudaGetLastError());
+    count_launch(1);
+    dn->stats.kernel_ms = 0;
+    dn->stats.total_ms = 0;
+    dn->stats.bytes = 8 * n_rows * n_cols;
+    return SKB_OK;
+}
+
+int skb_dense_apply_background_device(skb_dense *dn, int op, const double *d_x, double *d_y, void *stream) {
+    if (!dn || (op != 0 && op != 1))
+        return set_error(SKB_ERR_INVALID, "skb_dense_apply_background_device: bad arguments");
+    if (dn->rows[op] < 0)
+        return set_error(SKB_ERR_STATE, "skb_dense_apply_background_device: skb_dense_set_matrix(op=%d) has not been "
+                                        "called", op);
+    if (dn->devs.size() != 1)
+        return set_error(SKB_ERR_INVALID, "skb_dense_apply_background_device needs a single-device handle (this one "
+                                          "spans %d)", (int)dn->devs.size());
+    const long long n_rows = dn->rows[op], n_cols = dn->cols[op];
+    if (n_rows == 0)
+        return SKB_OK;
+    if ((n_cols > 0 && !d_x) || !d_y)
+        return set_error(SKB_ERR_INVALID, "skb_dense_apply_background_device: NULL x or y");
+    // the TMA streamer needs 16-byte aligned rows and x; anything else takes the classic kernel on the same stream
+    if (n_cols % 2 != 0 || ((uintptr_t)d_x & 15) != 0 || n_cols == 0)
+        return skb_dense_apply_device(dn, op, d_x, nullptr, d_y, stream);
+    DenseDev &d = dn->devs[0];
+    cudaStream_t st = (cudaStream_t)stream;
+    CUDA_TRY(cudaSetDevice(d.dev));
+    SKB_TRY(dense_stream_preload(d.dev));
+    SKB_TRY(d.ticket_bg.ensure(8));
+    CUDA_TRY(cudaMemsetAsync(d.ticket_bg.ptr, 0, 8, st));
+    StreamArgs a;
+    a.A = (const double *)d.A[op].ptr;
+    a.x = d_x;
+    a.y = d_y;
+    a.n_rows = n_rows;
+    a.n_cols = n_cols;
+    a.next_group = (unsigned long long *)d.ticket_bg.ptr;
+    const long long n_groups = (n_rows + kStreamRows - 1) / kStreamRows;
+    const unsigned grid = (unsigned)std::min<long long>(d.num_sms, n_groups);
+    dense_stream_kernel<<<grid, kStreamThreads, kStreamSmemBytes, st>>>(a);
     CUDA_TRY(cudaGetLastError());
     count_launch(1);
     dn->stats.kernel_ms = 0;

@@ -156,6 +156,9 @@ int cross_eval(CrossState &cs, const DeviceInfo &di, const double *d_r_fib, cons
                double scale_dl, double scale_sl, double *d_u_fib, int acc_fib, double *d_u_shell, int acc_shell,
                cudaStream_t st, int *launches);
 
+// background row streamer (skb_dense.cu, stream_kernels.cuh): load the kernel and fix its attributes on `dev`
+int dense_stream_preload(int dev);
+
 struct SymItem;
 long long sym_block_nodes(); // nodes per block of the symmetric kernel (its I side)
 void build_sym_items(int nb, int part, int parts, int num_sms, std::vector<SymItem> &order,

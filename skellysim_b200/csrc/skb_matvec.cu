@@ -136,6 +136,17 @@ struct skb_flow {
         }
         template <class T> T *at(int member, size_t off) const { return reinterpret_cast<T *>((char *)peer[member] + off); }
     } grp;
+    // Periphery::matvec's dense operator beside the pair kernels (stream_kernels.cuh): forked onto bg_stream once its
+    // input (the complete x_shell) is there, joined before res_shell is assembled
+    struct Overlap {
+        bool enabled = true;       // skb_flow_set_overlap
+        cudaStream_t stream = nullptr;
+        cudaEvent_t fork = nullptr, join = nullptr;
+        DevBuf y;                  // A x of the own periphery rows
+        skb_dense *dn = nullptr;   // pending background product of the call in flight (nullptr: none)
+        const double *d_x = nullptr;
+        bool launched = false;
+    } bg;
     DevBuf scratch_u; // group mode: landing zone of eval_on_device's default output (never read)
     // staging
     DevBuf in_fib, in_shell, in_body, in_force, in_torque, vel, tmp;
@@ -385,6 +396,8 @@ int skb_flow_create(int device, skb_flow **out) {
     CUDA_TRY(cudaEventCreate(&fl->evt1));
     if (const char *e = getenv("SKB_GRAPHS"))
         fl->graphs_enabled = atoi(e) != 0;
+    if (const char *e = getenv("SKB_OVERLAP")) // A/B switch of skb_flow_set_overlap's default
+        fl->bg.enabled = atoi(e) != 0;
     for (int k = 0; k < 2; ++k) {
         SKB_TRY(ensure_ctx(fl.get(), &fl->fib[k]));
         SKB_TRY(ensure_ctx(fl.get(), &fl->shell[k]));
@@ -423,6 +436,10 @@ int skb_flow_destroy(skb_flow *fl) {
     group_release(fl);
     fl->scratch_u.release();
     fl->cross.release();
+    fl->bg.y.release();
+    if (fl->bg.fork) cudaEventDestroy(fl->bg.fork);
+    if (fl->bg.join) cudaEventDestroy(fl->bg.join);
+    if (fl->bg.stream) cudaStreamDestroy(fl->bg.stream);
     if (fl->h_stage)
         cudaFreeHost(fl->h_stage);
     if (fl->ev0) cudaEventDestroy(fl->ev0);
@@ -833,6 +850,39 @@ static int prepare_matvec_targets(skb_flow *fl) {
 }
 
 // ---- group exchange steps (group_kernels.cuh) on fl->cur ---------------------------------------------------------
+// The pending dense product of apply_matvec_core goes out on the side stream, ordered after everything on fl->cur so far
+// (its input is complete), and runs beside whatever fl->cur launches next.  The side stream has the highest priority:
+// its 148 one-warp CTAs are placed before the pair kernel's CTAs fill the SMs.
+static int overlap_buffers(skb_flow *fl, long long n_rows) {
+    skb_flow::Overlap &B = fl->bg;
+    if (!B.stream) {
+        int lo = 0, hi = 0;
+        CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        CUDA_TRY(cudaStreamCreateWithPriority(&B.stream, cudaStreamNonBlocking, hi));
+        CUDA_TRY(cudaEventCreateWithFlags(&B.fork, cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreateWithFlags(&B.join, cudaEventDisableTiming));
+        // nothing may be loaded lazily later, while a group member on this device spins on a flag
+        SKB_TRY(dense_stream_preload(fl->dev));
+        cudaFuncAttributes fa;
+        CUDA_TRY(cudaFuncGetAttributes(&fa, add_out_kernel));
+    }
+    SKB_TRY(B.y.ensure((size_t)n_rows * 8 + 8));
+    return SKB_OK;
+}
+static int overlap_launch(skb_flow *fl) {
+    skb_flow::Overlap &B = fl->bg;
+    if (!B.dn || B.launched)
+        return SKB_OK;
+    CUDA_TRY(cudaEventRecord(B.fork, fl->cur));
+    CUDA_TRY(cudaStreamWaitEvent(B.stream, B.fork, 0));
+    SKB_TRY(skb_dense_apply_background_device(B.dn, SKB_DENSE_STRESSLET_PLUS_COMPLEMENTARY, B.d_x, (double *)B.y.ptr,
+                                              B.stream));
+    CUDA_TRY(cudaEventRecord(B.join, B.stream));
+    B.launched = true;
+    fl->launches += 1;
+    return SKB_OK;
+}
+
 static int group_flag(skb_flow *fl, int phase, bool do_signal, bool do_wait) {
     skb_flow::Group &G = fl->grp;
     if (G.dry)
@@ -897,6 +947,7 @@ static int matvec_core_group(skb_flow *fl, const double *d_ff, const double *d_s
     }
     // 2. every member's strengths have landed here
     SKB_TRY(group_flag(fl, 0, true, true));
+    SKB_TRY(overlap_launch(fl)); // (x_shell is complete in the window from here on)
     const double *f_sl = G.at<double>(G.rank, G.off_fsl[par]);
     const double *f_shell = G.at<double>(G.rank, G.off_fshell[par]);
     double *u_part = G.at<double>(G.rank, G.off_upart);
@@ -1099,6 +1150,7 @@ static int matvec_core(skb_flow *fl, const double *d_ff, const double *d_sd, con
     const long long n_win = fl->n_win, n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba;
     if (n_win == 0)
         return SKB_OK;
+    SKB_TRY(overlap_launch(fl));
     if (fl->use_cross)
         return matvec_core_cross(fl, d_ff, d_sd, d_bd, d_f, d_t, eta, d_v);
     // v_all = fc.flow(r_all, fw, eta)                                  system.cpp:299
@@ -1250,6 +1302,8 @@ int skb_flow_group_warmup(skb_flow *fl) {
     CUDA_TRY(cudaMemsetAsync(z.ptr, 0, n_z * 8, fl->stream));
     SKB_TRY(fl->vel.ensure((size_t)fl->n_win * 24 + 8));
     SKB_TRY(fl->in_fib.ensure((size_t)n_fw * 24 + 8));
+    if (n_sw > 0 && fl->bg.enabled)
+        SKB_TRY(overlap_buffers(fl, 3 * n_sw));
     fl->cur = fl->stream;
     fl->grp.dry = true;
     const double *zp = (const double *)z.ptr;
@@ -1295,6 +1349,13 @@ int skb_flow_set_cross(skb_flow *fl, int mode) {
     fl->cross_mode = mode;
     fl->mv_dirty = true;
     fl->geom_version++;
+    return SKB_OK;
+}
+
+int skb_flow_set_overlap(skb_flow *fl, int on) {
+    if (!fl)
+        return set_error(SKB_ERR_INVALID, "skb_flow_set_overlap: NULL flow");
+    fl->bg.enabled = on != 0;
     return SKB_OK;
 }
 
@@ -1808,6 +1869,18 @@ static int apply_matvec_core(skb_flow *fl, skb_dense *dn, const double *d_x, con
     const long long n_fw = fl->fb - fl->fa, n_sw = fl->sb - fl->sa, n_bw = fl->bb - fl->ba;
     SKB_TRY(fl->in_fib.ensure((size_t)n_fw * 24 + 8));
     SKB_TRY(fl->vel.ensure((size_t)fl->n_win * 24 + 8));
+    // res_shell's dense part, stresslet_plus_complementary_ * x_shell (system.cpp:319, periphery.cpp:38-47), depends on
+    // x_shell only: it is handed to the background streamer, which matvec_core launches as soon as x_shell is complete
+    // on this device -- the caller's vector without a group, the gathered copy in the window with one
+    skb_flow::Overlap &B = fl->bg;
+    B.dn = nullptr;
+    B.launched = false;
+    const bool dense_rows = dn && n_sw > 0 && d_out_shell;
+    if (dense_rows && B.enabled) {
+        SKB_TRY(overlap_buffers(fl, 3 * n_sw));
+        B.dn = dn;
+        B.d_x = fl->grp.size > 1 ? fl->grp.at<double>(fl->grp.rank, fl->grp.off_xshell[(fl->grp.epoch + 1) & 1]) : d_xs;
+    }
     // MatrixXd fw = fc.apply_fiber_force(x_fibers)                       system.cpp:298
     SKB_TRY(fiber_force_dev(fl, d_x, (double *)fl->in_fib.ptr));
     // v_all of system.cpp:299-316 (own rows)
@@ -1816,10 +1889,17 @@ static int apply_matvec_core(skb_flow *fl, skb_dense *dn, const double *d_x, con
     SKB_TRY(fiber_matvec_dev(fl, d_x, (const double *)fl->vel.ptr, d_link, d_res_fib));
     const double *d_v_shell = (const double *)fl->vel.ptr + 3 * n_fw;
     if (n_sw > 0 && d_out_shell) {
-        if (dn) {
-            // res_shell = shell.matvec(x_shell, v_shell) = stresslet_plus_complementary_ * x_shell + v_shell
-            // (system.cpp:319, periphery.cpp:38-47): the handle holds this member's rows, x_shell is complete -- the
-            // caller's vector without a group, the gathered copy in the window with one
+        if (dense_rows && B.launched) {
+            // res_shell = A x (background) + v_shell
+            CUDA_TRY(cudaStreamWaitEvent(fl->cur, B.join, 0));
+            add_out_kernel<<<(unsigned)((3 * n_sw + 255) / 256), 256, 0, fl->cur>>>(d_out_shell, (const double *)B.y.ptr,
+                                                                                   d_v_shell, 3 * n_sw);
+            CUDA_TRY(cudaGetLastError());
+            count_launch(1);
+            fl->launches += 1;
+        } else if (dn) {
+            // res_shell = shell.matvec(x_shell, v_shell) = stresslet_plus_complementary_ * x_shell + v_shell in one
+            // kernel at the end of the stream (skb_flow_set_overlap(fl, 0))
             const double *d_x_full = d_xs;
             if (fl->grp.size > 1)
                 d_x_full = fl->grp.at<double>(fl->grp.rank, fl->grp.off_xshell[fl->grp.epoch & 1]);
@@ -1830,6 +1910,7 @@ static int apply_matvec_core(skb_flow *fl, skb_dense *dn, const double *d_x, con
             CUDA_TRY(cudaMemcpyAsync(d_out_shell, d_v_shell, (size_t)n_sw * 24, cudaMemcpyDeviceToDevice, fl->cur));
         }
     }
+    B.dn = nullptr;
     if (n_bw > 0 && d_v_bodies)
         CUDA_TRY(cudaMemcpyAsync(d_v_bodies, (const double *)fl->vel.ptr + 3 * (n_fw + n_sw), (size_t)n_bw * 24,
                                  cudaMemcpyDeviceToDevice, fl->cur));
@@ -2248,6 +2329,14 @@ int skb_mflow_set_cross(skb_mflow *mf, int mode) {
     return SKB_OK;
 }
 
+int skb_mflow_set_overlap(skb_mflow *mf, int on) {
+    if (!mf)
+        return set_error(SKB_ERR_INVALID, "skb_mflow_set_overlap: NULL");
+    for (int g = 0; g < mf->n; ++g)
+        SKB_TRY(skb_flow_set_overlap(mf->m[g], on));
+    return SKB_OK;
+}
+
 int skb_mflow_set_self_exclusion(skb_mflow *mf, int fused) {
     if (!mf)
         return set_error(SKB_ERR_INVALID, "skb_mflow_set_self_exclusion: NULL");
@@ -2397,6 +2486,8 @@ static int mflow_size_io(skb_mflow *mf, size_t n_ft) {
         SKB_TRY(io.outs.ensure(n_sw * 24 + 8));
         SKB_TRY(io.vb.ensure(n_bw * 24 + 8));
         SKB_TRY(io.v.ensure((n_fw + n_sw + n_bw) * 24 + 8));
+        if (mf->has_dense && n_sw > 0 && mf->m[g]->bg.enabled)
+            SKB_TRY(overlap_buffers(mf->m[g], 3 * (long long)n_sw));
     }
     return SKB_OK;
 }

@@ -9,6 +9,10 @@
 #include "cross_kernels.cuh"
 #include "skb_internal.hpp"
 
+#ifndef SKB_CARVEOUT_MAX
+#define SKB_CARVEOUT_MAX 1
+#endif
+
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -803,6 +807,13 @@ static cudaError_t launch_sym(const SymArgs &a, int n_items, cudaStream_t st) {
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total_bytes);
         if (e != cudaSuccess)
             return e;
+#if SKB_CARVEOUT_MAX
+        // one shared-memory configuration for this kernel and the background row streamer (stream_kernels.cuh): an SM
+        // switches configuration only when idle, so a different preference would keep the two from sharing it
+        e = cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess)
+            return e;
+#endif
         attr_set[dev] = true;
     }
     kern<<<n_items, kSymThreads, L::total_bytes, st>>>(a);
@@ -1142,6 +1153,10 @@ int cross_eval(CrossState &cs, const DeviceInfo &di, const double *d_r_fib, cons
     cudaGetDevice(&dev);
     if (dev < 64 && !attr_set[dev]) {
         CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, L::total_bytes));
+#if SKB_CARVEOUT_MAX
+        CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                      cudaSharedmemCarveoutMaxShared));
+#endif
         attr_set[dev] = true;
     }
     kern<<<cs.n_items, kSymThreads, L::total_bytes, st>>>(a);

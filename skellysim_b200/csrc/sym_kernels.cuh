@@ -178,8 +178,18 @@ __device__ __forceinline__ void stokeslet_pairpairs(const double (&tx)[T], const
     }
 }
 
+// SKB_SYM_MAXNREG caps the registers per thread below what (kSymThreads, MINB) allows: at 240 the two resident CTAs
+// leave 4 096 registers of the SM free -- room for the 64-thread CTA of the background row streamer (stream_kernels.cuh).
+#ifndef SKB_SYM_MAXNREG
+#define SKB_SYM_MAXNREG 240 // measured: 10.21 ms at 240 against 10.30 at 254 and 10.46 at 248 (profiles/r2_sym_variants.md)
+#endif
+#if SKB_SYM_MAXNREG > 0
+#define SKB_SYM_BOUNDS __maxnreg__(SKB_SYM_MAXNREG)
+#else
+#define SKB_SYM_BOUNDS __launch_bounds__(kSymThreads, MINB)
+#endif
 template <int T, int MINB, bool EXCL = false>
-__global__ void __launch_bounds__(kSymThreads, MINB) pair_sym_kernel(const SymArgs a) {
+__global__ void SKB_SYM_BOUNDS pair_sym_kernel(const SymArgs a) {
     using L = SymSmem<T>;
     constexpr int kBlock = L::block;
     constexpr int kWarps = kSymThreads / 32;
