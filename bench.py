@@ -716,6 +716,23 @@ def dense_leg(skb, hbm_peak_gbs, local_rank, n_nodes=6000, reps=10):
             ts.append(1e3 * (time.perf_counter() - t0))
             ks.append(dn.stats()["kernel_ms"])
         bytes_ = dn.stats()["bytes"]
+        # the same product with the background row streamer, alone on the GPU (its job is to run BESIDE the pair kernels,
+        # see the `overlap` leg; alone, one small CTA per SM does not reach the copy peak)
+        import torch
+        dev = torch.device("cuda", local_rank)
+        d_x = torch.from_numpy(x).to(dev)
+        d_y = torch.zeros(n, dtype=torch.float64, device=dev)
+        st = torch.cuda.current_stream(dev).cuda_stream
+        bs = []
+        for _ in range(reps + 2):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            dn.apply_background_device(skb.DENSE_STRESSLET_PLUS_COMPLEMENTARY, d_x.data_ptr(), d_y.data_ptr(), st)
+            e1.record()
+            torch.cuda.synchronize()
+            bs.append(e0.elapsed_time(e1))
+        kb = float(np.median(bs[2:]))
+        yb = d_y.cpu().numpy()
     rows = np.random.default_rng(0).choice(n, 32, replace=False)
     ref = A[rows] @ x + v[rows]
     err = float(np.max(np.abs(y[rows] - ref) / (np.abs(A[rows]) @ np.abs(x) + np.abs(v[rows]))))
@@ -724,7 +741,10 @@ def dense_leg(skb, hbm_peak_gbs, local_rank, n_nodes=6000, reps=10):
             "kernel_ms": k, "e2e_ms": float(np.median(ts)), "bytes": int(bytes_),
             "roofline": {"bound": "hbm", "achieved": bytes_ / (k * 1e-3) / 1e9, "peak": hbm_peak_gbs, "unit": "GB/s",
                          "frac": bytes_ / (k * 1e-3) / 1e9 / hbm_peak_gbs},
-            "max_backward_err": err}
+            "max_backward_err": err,
+            "background_streamer": {"kernel_ms_alone": kb, "gbs_alone": bytes_ / (kb * 1e-3) / 1e9,
+                                    "max_backward_err": float(np.max(np.abs(yb[rows] - A[rows] @ x) /
+                                                                     (np.abs(A[rows]) @ np.abs(x))))}}
 
 
 def fiber_ops_leg(rs: RankSystem, hbm_peak_gbs, reps=10):
@@ -753,6 +773,33 @@ def fiber_ops_leg(rs: RankSystem, hbm_peak_gbs, reps=10):
             "set_operators_ms": rs.set_operators_ms,
             "roofline": {"bound": "hbm", "achieved": gbs, "peak": hbm_peak_gbs, "unit": "GB/s",
                          "frac": gbs / hbm_peak_gbs}}
+
+
+def overlap_leg(rs: RankSystem, reps=10):
+    """A/B of skb_flow_set_overlap on the headline workload: the periphery's dense operator beside the pair kernels
+    (background row streamer on a side stream, csrc/stream_kernels.cuh) against one GEMV kernel at the end of the stream."""
+    torch = rs.torch
+
+    def run():
+        for k in range(3):
+            rs.matvec_device(k)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for k in range(reps):
+            rs.matvec_device(k)
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    on = run()
+    rs.fl.set_overlap(False)
+    off = run()
+    rs.fl.set_overlap(True)
+    return {"ms_per_matvec_overlap_on": on, "ms_per_matvec_overlap_off": off,
+            "what": "stresslet_plus_complementary * x_shell (periphery.cpp:38-47, HBM-bound) streamed by a 3-warp CTA per "
+                    "SM beside pair_sym_kernel (FP64-bound) vs. run after the pair kernels; back-to-back matvecs, no L2 "
+                    "flush"}
 
 
 def inprocess_leg(skb, n_devices: int):
@@ -1002,6 +1049,8 @@ def main():
             _log("cpu baseline done")
         out["solve"] = solve_leg(torch, skb, rs)
         out["fiber_operators"] = fiber_ops_leg(rs, hbm_peak)
+        if rs.dn:
+            out["overlap"] = overlap_leg(rs)
         _log("solve + fiber legs done")
     rs.close()
     del rs

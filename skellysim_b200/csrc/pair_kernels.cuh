@@ -537,6 +537,39 @@ __global__ void reduce_partials_kernel(const double *__restrict__ partial, doubl
     u[i] = accumulate ? u[i] + acc : acc;
 }
 
+// The same for FEW targets and MANY splits (the planner cuts 1e5 sources into ~1 000 splits when a call has a few
+// hundred targets: the body rows of a rank): one thread per element then walks ~1 000 dependent loads (10 us).  Here a
+// CTA owns 32 consecutive elements, its 16 warps take the splits round-robin (coalesced 256-byte loads, two independent
+// running sums each), and the warps' sums are added in warp order: still a fixed order, bitwise reproducible.
+constexpr int kReduceWideWarps = 16;
+__global__ void __launch_bounds__(32 * kReduceWideWarps)
+    reduce_partials_wide_kernel(const double *__restrict__ partial, double *__restrict__ u, long long n3, int n_splits,
+                                double scale, int accumulate) {
+    __shared__ double sh[kReduceWideWarps][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const long long i = (long long)blockIdx.x * 32 + lane;
+    double a0 = 0.0, a1 = 0.0;
+    if (i < n3) {
+        int s = w;
+        for (; s + kReduceWideWarps < n_splits; s += 2 * kReduceWideWarps) {
+            a0 += partial[(size_t)s * n3 + i];
+            a1 += partial[(size_t)(s + kReduceWideWarps) * n3 + i];
+        }
+        if (s < n_splits)
+            a0 += partial[(size_t)s * n3 + i];
+    }
+    sh[w][lane] = a0 + a1;
+    __syncthreads();
+    if (w == 0 && i < n3) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < kReduceWideWarps; ++k)
+            acc += sh[k][lane];
+        acc *= scale;
+        u[i] = accumulate ? u[i] + acc : acc;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // Strength packing (once per matvec, O(n_src)).
 // ---------------------------------------------------------------------------------------------

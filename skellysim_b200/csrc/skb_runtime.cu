@@ -207,8 +207,12 @@ int launch_reduce(const double *d_partial, double *d_u, long long n_trg, int n_s
                   cudaStream_t st) {
     const long long n3 = 3 * n_trg;
     const int bs = 256;
-    reduce_partials_kernel<<<(unsigned)((n3 + bs - 1) / bs), bs, 0, st>>>(d_partial, d_u, n3, n_splits, scale,
-                                                                          accumulate);
+    if (n_splits >= 4 * kReduceWideWarps && n3 <= 32LL * 4096) // few targets, many splits
+        reduce_partials_wide_kernel<<<(unsigned)((n3 + 31) / 32), 32 * kReduceWideWarps, 0, st>>>(
+            d_partial, d_u, n3, n_splits, scale, accumulate);
+    else
+        reduce_partials_kernel<<<(unsigned)((n3 + bs - 1) / bs), bs, 0, st>>>(d_partial, d_u, n3, n_splits, scale,
+                                                                              accumulate);
     cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess)
         return set_error(SKB_ERR_CUDA, "reduce_partials_kernel launch failed: %s", cudaGetErrorString(e));
