@@ -649,6 +649,18 @@ def stokeslet_call_leg(torch, skb, g, dev, local_rank, reps=10):
             "sym_kernel_ms": sym_ms, "sym_kernel_pairs_per_s": (sym_pairs / (sym_ms * 1e-3)) if sym_ms else None}
 
 
+def ref_kernel_only_ms(path=None):
+    """Median duration (ms) of the reference's tiled_driver kernel in the committed ncu launch list, or None."""
+    import csv
+    path = path or os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_ref_gpu_kernel.csv")
+    try:
+        ns = [float(r[-1].replace(",", "")) for r in csv.reader(open(path))
+              if len(r) > 5 and r[0].isdigit() and "tiled_driver" in r[4] and r[-2] == "ns"]
+    except (OSError, ValueError):
+        return None
+    return float(np.median(ns)) * 1e-6 if ns else None
+
+
 def ref_gpu_leg(g, reps=5):
     """The reference's own CUDA path (src/core/kernels.cu compiled unmodified for sm_100 into oracle/_ref) on the same
     GPU, same C3 Stokeslet call: end to end (its cudaMalloc + copies + kernel + free, kernels.cu:148-178)."""
@@ -670,16 +682,11 @@ def ref_gpu_leg(g, reps=5):
            "note": "wall clock of the reference's entry point: 4 cudaMalloc + 3 H2D + kernel + D2H + 4 cudaFree"}
     # its kernel alone cannot be timed from outside the entry point; the committed ncu launch list of this very leg
     # (profiles/r2_ref_gpu_kernel.csv, `ncu --metrics gpu__time_duration.sum -k regex:driver`) is quoted instead
-    prof = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r2_ref_gpu_kernel.csv")
-    try:
-        import csv
-        ns = [float(r[-1]) for r in csv.reader(open(prof)) if r and r[0].isdigit() and "tiled_driver" in r[4]]
-        if ns and g["workload"] == "c3":
-            out["kernel_only_ms_ncu"] = float(np.median(ns)) * 1e-6
-            out["pairs_per_s_kernel_ncu"] = pairs / (float(np.median(ns)) * 1e-9)
-            out["kernel_only_source"] = "profiles/r2_ref_gpu_kernel.csv (recorded on a B200 of this pool, not in this run)"
-    except OSError:
-        pass
+    k_ms = ref_kernel_only_ms() if g["workload"] == "c3" else None
+    if k_ms:
+        out["kernel_only_ms_ncu"] = k_ms
+        out["pairs_per_s_kernel_ncu"] = pairs / (k_ms * 1e-3)
+        out["kernel_only_source"] = "profiles/r2_ref_gpu_kernel.csv (recorded on a B200 of this pool, not in this run)"
     return out
 
 
