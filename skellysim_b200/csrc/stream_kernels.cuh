@@ -4,20 +4,22 @@
 // Why: the periphery's dense operator (Periphery::matvec, SkellySim src/core/periphery.cpp:38-47) reads 8 B per FMA -- it
 // is bound by HBM and leaves the FP64 pipe idle; pair_sym_kernel is bound by the FP64 pipe and leaves HBM idle.  Run one
 // after the other they cost 10.2 + 0.43 ms of the C3 matvec.  The classic GEMV (dense_gemv_kernel: 256 threads, all
-// warps resident) cannot share an SM with the symmetric kernel, whose two CTAs hold the whole register file.  This
-// kernel can: ONE CTA of three warps x 32 registers per SM (a producer warp and two consumer warps).  The register file is split over the SM's four sub-partitions
-// (16 384 registers each); pair_sym_kernel is capped at 240 registers, so its two CTAs (one warp per sub-partition
-// each) leave 1 024 registers per sub-partition free -- exactly one 32-register warp each.  The matrix is moved by the TMA
-// engine, not by threads --
-//   * five lanes of the producer warp post 1-D bulk copies (cp.async.bulk, SASS UBLKCP): 4 rows x 512 columns of A plus the
-//     512 matching entries of x (L2 resident) = 20 KB per stage into a 5-stage ring, 4 stages (64 KB of A) ahead of
+// warps resident) cannot share an SM with the symmetric kernel, whose two CTAs held the whole register file.  This
+// kernel can: ONE CTA of three warps x 32 registers per SM (a producer warp and two consumer warps).  The register file
+// is split over the SM's four sub-partitions (16 384 registers each); pair_sym_kernel is capped at 240 registers, so its
+// two CTAs (one warp per sub-partition each) leave 1 024 registers per sub-partition free -- exactly one 32-register
+// warp each.  The matrix is moved by the TMA engine, not by threads --
+//   * five lanes of the producer warp post 1-D bulk copies (cp.async.bulk, SASS UBLKCP): 4 rows x 512 columns of A plus
+//     the 512 matching entries of x (L2 resident) = 20 KB per stage into a 5-stage ring, 4 stages (64 KB of A) ahead of
 //     use: HBM latency x bandwidth per SM is ~45 KB, so the ring keeps the SM's share of the 6.5 TB/s in flight with
 //     no warp waiting on a load instruction (a first version read x with LDG: every stage then waited one L2 latency,
 //     1.8 TB/s);
-//   * the 64 consumer threads consume a stage with 20 LDS.128 + 32 DFMA each -- 4 % of the SM's FP64 issue slots while it runs,
-//     0.3 % of the symmetric kernel's total;
+//   * the 64 consumer threads consume a stage with 20 LDS.128 + 32 DFMA each -- 4 % of the SM's FP64 issue slots while
+//     it runs, 0.3 % of the symmetric kernel's total;
 //   * the bulk copies carry an L2 evict-first policy: 2.6 GB of read-once matrix must not evict the 4.6 MB of node
 //     records the pair kernels stream from L2.
+// Measured (profiles/r2_overlap.md): alone 3.84 TB/s; beside pair_sym_kernel the 2.59 GB of the C3 operator arrive in
+// 0.95 ms while the pair kernel loses 0.09 ms -- the matvec 12.56 -> 12.25 ms.
 // Rows are handed out in groups of 4 by a ticket counter (first group static); a row's sum is accumulated in a fixed
 // thread -> column mapping and a fixed reduction tree, so results are bitwise reproducible whatever the ticket order.
 #pragma once
@@ -29,7 +31,7 @@
 namespace skb {
 
 constexpr int kStreamConsumers = 64;                 // two consumer warps
-constexpr int kStreamThreads = kStreamConsumers + 32; // + the producer warp (one lane active)
+constexpr int kStreamThreads = kStreamConsumers + 32; // + the producer warp (five lanes active)
 constexpr int kStreamRows = 4;     // rows per group (x is re-used 4 times per load)
 #ifndef SKB_STREAM_COLS
 #define SKB_STREAM_COLS 512
