@@ -190,6 +190,15 @@ template <class M> class FlowEngineT {
               "skb_flow_apply_matvec_dense");
         return res;
     }
+    // ---- switches of the matvec (all optional; defaults are the fast paths with the reference's semantics) ----
+    /// fibers <-> periphery pairs in one geometry pass: -1 auto (default), 0 never, 1 whenever applicable
+    void set_cross(int mode) { check(skb_flow_set_cross(st_->fl, mode), "skb_flow_set_cross"); }
+    /// the pair kernels skip intra-fiber pairs instead of the reference's compute-then-subtract (fcfd.cpp:203-210)
+    void set_self_exclusion(bool fused) {
+        check(skb_flow_set_self_exclusion(st_->fl, fused ? 1 : 0), "skb_flow_set_self_exclusion");
+    }
+    /// Periphery::matvec's dense operator beside the pair kernels on a side stream (default) or after them
+    void set_overlap(bool on) { check(skb_flow_set_overlap(st_->fl, on ? 1 : 0), "skb_flow_set_overlap"); }
     skb_flow *handle() const { return st_->fl; }
 
   private:

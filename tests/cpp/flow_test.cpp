@@ -116,6 +116,9 @@ int main() {
         }
         eng.set_fiber_class(n, D, P);
         eng.set_fiber_operators(Ap, Fp, xs, lprev, plus);
+        eng.set_cross(-1); // the switches of the matvec at their defaults (compile + link + argument checks)
+        eng.set_self_exclusion(false);
+        eng.set_overlap(true);
         Matrix fw = eng.apply_fiber_force(x), v_s, v_b;
         Matrix res = eng_copy.apply_matvec(x, rho, empty, empty, link, eta, v_s, v_b);
         Matrix v_all = eng.matvec_flow(fw, rho, empty, empty, eta);
