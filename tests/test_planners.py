@@ -86,3 +86,27 @@ def test_symmetric_work_list_is_balanced_across_parts():
         items, _ = capi.sym_plan_query(178, part, 8)
         loads.append(sum(g1 - g0 for (_, g0, g1, _) in items))
     assert max(loads) - min(loads) <= 0.03 * max(loads) + 8 * capi.sym_groups_per_block()
+
+
+# ---- skb_partition_query: which rows of [fibers | periphery | bodies] a group member owns (host-only) ----------------
+import numpy as np  # noqa: E402
+from hypothesis import given, settings, strategies as st  # noqa: E402
+
+
+@settings(max_examples=60, deadline=None)
+@given(nodes=st.lists(st.sampled_from([8, 16, 24, 32, 48, 64, 96, 128]), min_size=0, max_size=200),
+       n_shell=st.integers(0, 5000), n_body=st.integers(0, 900), members=st.integers(1, 16))
+def test_row_partition_tiles_every_class_with_whole_fibers(nodes, n_shell, n_body, members):
+    """Every member owns a contiguous run of WHOLE fibers, of periphery rows and of body rows; the runs tile each class
+    in member order with no gap and no overlap; fibers are balanced by node count (what the pair work scales with)."""
+    from skellysim_b200 import capi
+    parts = [capi.partition_query(nodes, n_shell, n_body, members, m) for m in range(members)]
+    for cls, total in ((0, len(nodes)), (2, n_shell), (4, n_body)):
+        assert parts[0][cls] == 0 and parts[-1][cls + 1] == total
+        for a, b in zip(parts, parts[1:]):
+            assert a[cls] <= a[cls + 1] == b[cls]
+    if nodes:
+        off = np.concatenate([[0], np.cumsum(nodes)])
+        own = [off[p[1]] - off[p[0]] for p in parts]
+        # no member is further from the ideal share than the largest fiber
+        assert max(abs(o - off[-1] / members) for o in own) <= max(nodes) + 1e-9
